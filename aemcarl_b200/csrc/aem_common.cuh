@@ -1,0 +1,137 @@
+// aem_common.cuh -- shared definitions of libaemcarl_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aemcarl_b200.h"
+
+namespace aem {
+
+constexpr int HID = 50;    // GRU hidden / d_model
+constexpr int XD = 13;     // rotated joint-state length (cadrl.py:239-274)
+constexpr int HXD = 63;    // [h ; x]
+
+// ---- offsets into the raw weight blob (state_dict order, aemcarl_b200/weights.py) ----
+constexpr int OFF_Z1W = 0;
+constexpr int OFF_Z1B = OFF_Z1W + 100 * 63;
+constexpr int OFF_Z2W = OFF_Z1B + 100;
+constexpr int OFF_Z2B = OFF_Z2W + 50 * 100;
+constexpr int OFF_R1W = OFF_Z2B + 50;
+constexpr int OFF_R1B = OFF_R1W + 100 * 63;
+constexpr int OFF_R2W = OFF_R1B + 100;
+constexpr int OFF_R2B = OFF_R2W + 50 * 100;
+constexpr int OFF_QW = OFF_R2B + 50;
+constexpr int OFF_QB = OFF_QW + 50 * 63;
+constexpr int OFF_PW = OFF_QB + 50;
+constexpr int OFF_PB = OFF_PW + 50;
+constexpr int OFF_ENC = OFF_PB + 1;
+constexpr int ENC_INW = 0;
+constexpr int ENC_INB = ENC_INW + 150 * 50;
+constexpr int ENC_OW = ENC_INB + 150;
+constexpr int ENC_OB = ENC_OW + 50 * 50;
+constexpr int ENC_L1W = ENC_OB + 50;
+constexpr int ENC_L1B = ENC_L1W + 150 * 50;
+constexpr int ENC_L2W = ENC_L1B + 150;
+constexpr int ENC_L2B = ENC_L2W + 50 * 150;
+constexpr int ENC_N1G = ENC_L2B + 50;
+constexpr int ENC_N1B = ENC_N1G + 50;
+constexpr int ENC_N2G = ENC_N1B + 50;
+constexpr int ENC_N2B = ENC_N2G + 50;
+constexpr int ENC_SIZE = ENC_N2B + 50;
+constexpr int OFF_A0W = OFF_ENC + 3 * ENC_SIZE;
+constexpr int OFF_A0B = OFF_A0W + 100 * 56;
+constexpr int OFF_A2W = OFF_A0B + 100;
+constexpr int OFF_A2B = OFF_A2W + 50 * 100;
+constexpr int OFF_A4W = OFF_A2B + 50;
+constexpr int OFF_A4B = OFF_A4W + 50;
+constexpr int NUM_WEIGHTS = OFF_A4B + 1;
+static_assert(NUM_WEIGHTS == AEM_NUM_WEIGHTS, "weight blob size");
+static_assert(ENC_SIZE == 25600, "encoder layer size");
+
+// ---- packed GEMM operand layout ----
+// A packed layer is W^T re-tiled for the register-tiled FP32 GEMM of lookahead.cu:
+//   packed[k][g][c], k < K, g < 16 column groups, c < TNHP (TNH real columns padded to a multiple of 4)
+// plain layer : real column = g * TNH + c
+// two-branch  : branch = g >> 3, real column inside the branch = (g & 7) * TNH + c
+constexpr int NGROUPS = 16;
+constexpr int pad4(int x) { return (x + 3) & ~3; }
+
+struct NetParams {
+    const float *raw;      // raw blob (biases, LayerNorm, ponder, last action layer)
+    const float *packed;   // packed GEMM operands
+    int off_z1r1, off_z2r2, off_q;
+    int off_in[3], off_out[3], off_f1[3], off_f2[3];
+    int off_a0, off_a2;
+    int act_fixed, act_steps;
+};
+
+// tile sizes of the packed layers (shared by the host packer and the kernel)
+constexpr int TNH_Z1R1 = 13;  // two-branch, 100 + 100 columns, K = 63
+constexpr int TNH_Z2R2 = 7;   // two-branch, 50 + 50 columns, K = 100
+constexpr int TNH_50 = 4;     // N = 50 layers (q, out_proj, linear2, action_mlp.2)
+constexpr int TNH_150 = 10;   // N = 150 layers (in_proj, linear1)
+constexpr int TNH_100 = 7;    // N = 100 layer (action_mlp.0)
+
+}  // namespace aem
+
+// ---- handle ----
+struct aem_handle_s {
+    int device;
+    int num_sms;
+    float *raw_d;        // [NUM_WEIGHTS]
+    float *packed_d;
+    size_t packed_floats;
+    aem::NetParams net;
+    bool weights_set, actions_set, params_set;
+    double *actions_d;   // [A][2]
+    int A;
+    aem_env_params params;
+    double *lut_d;       // [10000] normal pdf table (crowd_sim.py:20-28)
+    long long launches;
+    // scratch for the host-buffer call
+    int cap_B, cap_n;
+    double *s_robot, *s_humans, *s_time, *s_newvel, *s_rewards, *s_dmin, *s_hnext, *s_values, *s_oreward;
+    int32_t *s_info, *s_best, *s_odone, *s_oinfo;
+    void *s_stream;
+};
+
+#define AEM_CUDA_CHECK(expr)                                                      \
+    do {                                                                          \
+        cudaError_t e__ = (expr);                                                 \
+        if (e__ != cudaSuccess) return aem_set_cuda_error(e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+int aem_set_cuda_error(cudaError_t e, const char *what, const char *file, int line);
+int aem_set_error(int code, const char *msg);
+
+// launchers implemented in the .cu files
+namespace aem {
+struct LookaheadArgs;
+cudaError_t launch_lookahead(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
+cudaError_t launch_select(const double *values, const double *robot, int B, int A, int32_t *best, cudaStream_t st);
+cudaError_t launch_orca(int B, int n, const double *humans, const double *robot, const aem_env_params &p,
+                        double *new_vel, cudaStream_t st);
+cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const double *humans,
+                                 const double *new_vel, const double *global_time, const double *actions,
+                                 const double *lut, const aem_env_params &p, double *rewards, int32_t *info,
+                                 double *dmin, double *humans_next, cudaStream_t st);
+cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans, const double *new_vel,
+                             double *global_time, const double *actions, const int32_t *chosen,
+                             const double *rewards, const int32_t *info, const double *dmin, double time_step,
+                             double *out_reward, int32_t *out_done, int32_t *out_info, double *out_dmin,
+                             cudaStream_t st);
+
+struct LookaheadArgs {
+    NetParams net;
+    int mode;            // 0 = lookahead from env state, 1 = rotated states, 2 = GRU-ACT only
+    int n, T, S, A;      // humans, tokens per sample, samples per tile, actions
+    int total_samples;
+    double dt, gamma_bar;
+    const double *robot, *humans_next, *actions, *rewards;
+    const float *states;   // mode 1: [S][n][13]; mode 2: [S*T][13]
+    double *values;
+    float *net_values;
+    uint8_t *steps;
+    float *gru_out;        // mode 2: [S*T][50]
+};
+}  // namespace aem

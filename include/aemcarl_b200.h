@@ -1,0 +1,134 @@
+/*
+ * aemcarl_b200.h -- C ABI of libaemcarl_b200.so (sm_100a).
+ *
+ * Drop-in boundary for AEMCARL's one-step-lookahead hot path.  The reference has no FFI layer of its own
+ * (it is pure Python); the entry points below are what a maintainer of SJWang2015/AEMCARL binds with
+ * ctypes to replace, call for call:
+ *
+ *   aem_orca            <- crowd_sim/envs/policy/orca.py:82-132  (ORCA.predict -> rvo2.PyRVOSimulator.doStep,
+ *                          called n times per env.step at crowd_sim/envs/crowd_sim.py:562-568)
+ *   aem_env_lookahead   <- crowd_sim/envs/crowd_sim.py:554-651,676-680 (onestep_lookahead == step(update=False)
+ *                          for every action of the action space; gridmap reward crowd_sim.py:41-219)
+ *   aem_lookahead       <- crowd_nav/policy/multi_human_rl.py:336-372 (propagate cadrl.py:156-181, rotate
+ *                          cadrl.py:239-274, ValueNetworkTransformerAndGRU.forward qnetwork_factory.py:641-687,
+ *                          ATCBasic/GRUEXND components.py:38-137, r + gamma^(dt*v_pref) * V, strict-'>' argmax)
+ *   aem_env_apply       <- crowd_sim/envs/crowd_sim.py:653-669 (step(update=True): advance robot/humans/time)
+ *   aem_value_forward   <- model(state) on already rotated states (explorer.py:137, trainer.py:52,75)
+ *   aem_gru_act         <- ATCBasic.forward components.py:107-137 (fused GRU-cell / adaptive-computation-time)
+ *   aem_decide_step_host<- Robot.act + CrowdSim.step through HOST buffers (explorer.py:51-53), the e2e call
+ *
+ * Conventions: plain pointers and sizes only; `*_d` = device pointer, `*_h` = host pointer; all device entry
+ * points are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and the
+ * caller owns every buffer.  Return value 0 = ok, otherwise an AEM_ERR_* code with a message available from
+ * aem_last_error().  One handle per (process, device); a handle is not thread-safe.
+ *
+ * Array layouts (row-major):
+ *   robot   [B][9]   f64  px,py,vx,vy,radius,gx,gy,v_pref,theta   (FullState, state.py:1-18)
+ *   humans  [B][n][8] f64 px,py,vx,vy,radius,gx,gy,v_pref
+ *   new_vel [B][n][2] f64 ORCA velocity of every human (FP32 value widened, as rvo2 returns it)
+ *   humans_next [B][n][5] f64 px,py,vx,vy,radius  (Agent.get_next_observable_state, agent.py:63-74)
+ *   actions [A][2]   f64  ActionXY table of CADRL.build_action_space (cadrl.py:129-154), A <= 128
+ *   rewards / values / dmin [B][A] f64 ; info [B][A] i32 ; net_values [B][A] f32 ; act_steps [B][A] u8
+ */
+#ifndef AEMCARL_B200_H
+#define AEMCARL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AEM_VERSION 100          /* 0.1.0 */
+#define AEM_MAX_HUMANS 32
+#define AEM_MAX_ACTIONS 128
+#define AEM_NUM_WEIGHTS 113752   /* live floats of the flag-5 network in state_dict order */
+
+enum {
+    AEM_OK = 0,
+    AEM_ERR_INVALID = 1,   /* bad argument (sizes, null pointers, n > AEM_MAX_HUMANS ...) */
+    AEM_ERR_CUDA = 2,      /* CUDA runtime error (message in aem_last_error) */
+    AEM_ERR_STATE = 3      /* weights / action space / env params not set yet */
+};
+
+/* info codes (crowd_sim/envs/utils/info.py): Nothing, Danger, ReachGoal, Collision, Timeout */
+enum { AEM_INFO_NOTHING = 0, AEM_INFO_DANGER = 1, AEM_INFO_REACHGOAL = 2, AEM_INFO_COLLISION = 3,
+       AEM_INFO_TIMEOUT = 4 };
+
+/* crowd_sim.py:265-299 CrowdSim.configure + robot.visible (test.py:127) + ORCA.safety_space */
+typedef struct {
+    double time_step;
+    double time_limit;
+    double success_reward;
+    double collision_penalty;
+    double discomfort_dist;
+    double agent_timestep;
+    double human_timestep;
+    double reward_increment;
+    double position_variance;
+    double direction_variance;
+    int32_t robot_visible;
+    int32_t pad_;
+    double orca_safety_space;
+} aem_env_params;
+
+typedef struct aem_handle_s *aem_handle;
+
+int aem_version(void);
+const char *aem_last_error(void);
+
+/* device = CUDA ordinal.  Allocates the weight copies, LUT and scratch on that device. */
+int aem_create(int device, aem_handle *out);
+int aem_destroy(aem_handle h);
+
+/* weights_h: AEM_NUM_WEIGHTS floats in state_dict order (aemcarl_b200/weights.py WEIGHT_SPEC).  Synchronous. */
+int aem_load_weights(aem_handle h, const float *weights_h, size_t count);
+/* actions_h [A][2] f64.  Synchronous. */
+int aem_set_action_space(aem_handle h, const double *actions_h, int A);
+int aem_set_env_params(aem_handle h, const aem_env_params *p);
+/* ATCBasic act_fixed / act_steps (components.py:119-123); default adaptive (act_fixed = 0). */
+int aem_set_act_mode(aem_handle h, int act_fixed, int act_steps);
+
+/* ---- device-pointer entry points ---- */
+int aem_orca(aem_handle h, int B, int n, const double *humans_d, const double *robot_d, double *new_vel_d,
+             void *stream);
+
+int aem_env_lookahead(aem_handle h, int B, int n, const double *robot_d, const double *humans_d,
+                      const double *new_vel_d, const double *global_time_d, double *rewards_d, int32_t *info_d,
+                      double *dmin_d, double *humans_next_d, void *stream);
+
+/* values_d = rewards + gamma_bar * V (f64); best_d = first strict maximum (-1 if every value is NaN; 0 when the
+ * robot already is at its goal, policy.py:45-49).  net_values_d / act_steps_d may be NULL. */
+int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const double *humans_next_d,
+                  const double *rewards_d, double gamma_bar, double *values_d, float *net_values_d,
+                  int32_t *best_d, uint8_t *act_steps_d, void *stream);
+
+/* out_reward_d [B] f64, out_done_d [B] i32, out_info_d [B] i32, out_dmin_d [B] f64 may each be NULL. */
+int aem_env_apply(aem_handle h, int B, int n, double *robot_d, double *humans_d, const double *new_vel_d,
+                  double *global_time_d, const int32_t *chosen_d, const double *rewards_d, const int32_t *info_d,
+                  const double *dmin_d, double *out_reward_d, int32_t *out_done_d, int32_t *out_info_d,
+                  double *out_dmin_d, void *stream);
+
+/* states_d [S][n][13] f32 (rotated joint states) -> values_d [S] f32, steps_d [S] u8 (may be NULL) */
+int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *values_d, uint8_t *steps_d,
+                      void *stream);
+
+/* x_d [S*T][13] f32, rows grouped in samples of T tokens -> out_d [S*T][50] f32, steps_d [S] u8 (may be NULL) */
+int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint8_t *steps_d, void *stream);
+
+/* ---- host-buffer call: one full env-step (predict + step) for B environments ----
+ * In/out (updated in place): robot_h [B][9], humans_h [B][n][8], global_time_h [B].
+ * Out: chosen_h [B] i32, reward_h [B] f64, done_h [B] i32, info_h [B] i32; values_h [B][A] f64 may be NULL.
+ * Copies host->device, runs orca + env_lookahead + lookahead + env_apply, copies back, synchronises. */
+int aem_decide_step_host(aem_handle h, int B, int n, double gamma_bar, double *robot_h, double *humans_h,
+                         double *global_time_h, int32_t *chosen_h, double *reward_h, int32_t *done_h,
+                         int32_t *info_h, double *values_h);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+long long aem_launch_count(aem_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
