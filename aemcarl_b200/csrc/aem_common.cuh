@@ -84,6 +84,7 @@ struct aem_handle_s {
     aem::NetParams net;
     bool weights_set, actions_set, params_set;
     double *actions_d;   // [A][2]
+    double actions_h[AEM_MAX_ACTIONS * 2];
     int A;
     aem_env_params params;
     double *lut_d;       // [10000] normal pdf table (crowd_sim.py:20-28)
@@ -113,8 +114,8 @@ cudaError_t launch_orca(int B, int n, const double *humans, const double *robot,
                         double *new_vel, cudaStream_t st);
 cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const double *humans,
                                  const double *new_vel, const double *global_time, const double *actions,
-                                 const double *lut, const aem_env_params &p, double *rewards, int32_t *info,
-                                 double *dmin, double *humans_next, cudaStream_t st);
+                                 const double *lut, const aem_env_params &p, double amax, double *rewards,
+                                 int32_t *info, double *dmin, double *humans_next, cudaStream_t st);
 cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans, const double *new_vel,
                              double *global_time, const double *actions, const int32_t *chosen,
                              const double *rewards, const int32_t *info, const double *dmin, double time_step,

@@ -1,0 +1,391 @@
+// capi.cu -- C ABI of libaemcarl_b200.so (declared in include/aemcarl_b200.h).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "aem_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+int aem_set_error(int code, const char *msg)
+{
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+int aem_set_cuda_error(cudaError_t e, const char *what, const char *file, int line)
+{
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return AEM_ERR_CUDA;
+}
+
+namespace {
+
+using namespace aem;
+
+// pack nn.Linear weights W[out][in] into packed[k][g][c] (see aem_common.cuh)
+void pack_plain(std::vector<float> &dst, const float *W, int N, int K, int TNH)
+{
+    const int TNHP = pad4(TNH), NP = NGROUPS * TNHP;
+    const size_t base = dst.size();
+    dst.resize(base + (size_t)K * NP, 0.0f);
+    for (int k = 0; k < K; ++k)
+        for (int g = 0; g < NGROUPS; ++g)
+            for (int c = 0; c < TNH; ++c) {
+                const int col = g * TNH + c;
+                if (col < N) dst[base + (size_t)k * NP + g * TNHP + c] = W[(size_t)col * K + k];
+            }
+}
+
+void pack_two(std::vector<float> &dst, const float *W0, const float *W1, int N, int K, int TNH)
+{
+    const int TNHP = pad4(TNH), NP = NGROUPS * TNHP;
+    const size_t base = dst.size();
+    dst.resize(base + (size_t)K * NP, 0.0f);
+    for (int k = 0; k < K; ++k)
+        for (int g = 0; g < NGROUPS; ++g)
+            for (int c = 0; c < TNH; ++c) {
+                const int col = (g & 7) * TNH + c;
+                const float *W = (g >> 3) ? W1 : W0;
+                if (col < N) dst[base + (size_t)k * NP + g * TNHP + c] = W[(size_t)col * K + k];
+            }
+}
+
+cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int check_ready(aem_handle h, bool need_weights, bool need_env)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (need_weights && !h->weights_set) return aem_set_error(AEM_ERR_STATE, "aem_load_weights has not been called");
+    if (!h->actions_set) return aem_set_error(AEM_ERR_STATE, "aem_set_action_space has not been called");
+    if (need_env && !h->params_set) return aem_set_error(AEM_ERR_STATE, "aem_set_env_params has not been called");
+    return AEM_OK;
+}
+
+double action_amax(aem_handle h)
+{
+    double amax = 0.0;
+    for (int a = 0; a < h->A; ++a) {
+        const double s = hypot(h->actions_h[2 * a], h->actions_h[2 * a + 1]) * h->params.agent_timestep;
+        if (s > amax) amax = s;
+    }
+    return amax;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aem_version(void) { return AEM_VERSION; }
+const char *aem_last_error(void) { return g_err; }
+
+int aem_create(int device, aem_handle *out)
+{
+    if (!out) return aem_set_error(AEM_ERR_INVALID, "out is null");
+    int count = 0;
+    AEM_CUDA_CHECK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return aem_set_error(AEM_ERR_INVALID, "no such CUDA device");
+    AEM_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AEM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return aem_set_error(AEM_ERR_INVALID, "libaemcarl_b200 is built for sm_100a (B200) only");
+    aem_handle h = new aem_handle_s();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    AEM_CUDA_CHECK(cudaMalloc(&h->raw_d, sizeof(float) * NUM_WEIGHTS));
+    AEM_CUDA_CHECK(cudaMalloc(&h->actions_d, sizeof(double) * AEM_MAX_ACTIONS * 2));
+    AEM_CUDA_CHECK(cudaMalloc(&h->lut_d, sizeof(double) * 10000));
+    {   // crowd_sim.py:20-28 norm.pdf((i - 5000) / 1000), same expression as oracle/aem_oracle.c
+        std::vector<double> lut(10000);
+        for (int i = 0; i < 10000; ++i) {
+            const double x = (double)(i - 5000) / 1000.0;
+            lut[i] = exp(-x * x / 2.0) / sqrt(2.0 * 3.141592653589793);
+        }
+        AEM_CUDA_CHECK(cudaMemcpy(h->lut_d, lut.data(), sizeof(double) * 10000, cudaMemcpyHostToDevice));
+    }
+    h->net.act_fixed = 0;
+    h->net.act_steps = 1;
+    *out = h;
+    return AEM_OK;
+}
+
+int aem_destroy(aem_handle h)
+{
+    if (!h) return AEM_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->raw_d); cudaFree(h->packed_d); cudaFree(h->actions_d); cudaFree(h->lut_d);
+    cudaFree(h->s_robot); cudaFree(h->s_humans); cudaFree(h->s_time); cudaFree(h->s_newvel);
+    cudaFree(h->s_rewards); cudaFree(h->s_dmin); cudaFree(h->s_hnext); cudaFree(h->s_values);
+    cudaFree(h->s_oreward); cudaFree(h->s_info); cudaFree(h->s_best); cudaFree(h->s_odone); cudaFree(h->s_oinfo);
+    if (h->s_stream) cudaStreamDestroy(as_stream(h->s_stream));
+    delete h;
+    return AEM_OK;
+}
+
+int aem_load_weights(aem_handle h, const float *w, size_t count)
+{
+    if (!h || !w) return aem_set_error(AEM_ERR_INVALID, "null argument");
+    if (count != (size_t)NUM_WEIGHTS) return aem_set_error(AEM_ERR_INVALID, "weight blob must hold 113752 floats");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    std::vector<float> pk;
+    NetParams &net = h->net;
+    net.off_z1r1 = (int)pk.size(); pack_two(pk, w + OFF_Z1W, w + OFF_R1W, 100, HXD, TNH_Z1R1);
+    net.off_z2r2 = (int)pk.size(); pack_two(pk, w + OFF_Z2W, w + OFF_R2W, HID, 100, TNH_Z2R2);
+    net.off_q = (int)pk.size();    pack_plain(pk, w + OFF_QW, HID, HXD, TNH_50);
+    for (int l = 0; l < 3; ++l) {
+        const float *E = w + OFF_ENC + l * ENC_SIZE;
+        net.off_in[l] = (int)pk.size();  pack_plain(pk, E + ENC_INW, 150, HID, TNH_150);
+        net.off_out[l] = (int)pk.size(); pack_plain(pk, E + ENC_OW, HID, HID, TNH_50);
+        net.off_f1[l] = (int)pk.size();  pack_plain(pk, E + ENC_L1W, 150, HID, TNH_150);
+        net.off_f2[l] = (int)pk.size();  pack_plain(pk, E + ENC_L2W, HID, 150, TNH_50);
+    }
+    net.off_a0 = (int)pk.size(); pack_plain(pk, w + OFF_A0W, 100, 56, TNH_100);
+    net.off_a2 = (int)pk.size(); pack_plain(pk, w + OFF_A2W, HID, 100, TNH_50);
+    if (pk.size() > h->packed_floats) {
+        cudaFree(h->packed_d);
+        h->packed_d = nullptr;
+        AEM_CUDA_CHECK(cudaMalloc(&h->packed_d, sizeof(float) * pk.size()));
+        h->packed_floats = pk.size();
+    }
+    AEM_CUDA_CHECK(cudaDeviceSynchronize());   // no kernel may still read the old copy
+    AEM_CUDA_CHECK(cudaMemcpy(h->raw_d, w, sizeof(float) * NUM_WEIGHTS, cudaMemcpyHostToDevice));
+    AEM_CUDA_CHECK(cudaMemcpy(h->packed_d, pk.data(), sizeof(float) * pk.size(), cudaMemcpyHostToDevice));
+    net.raw = h->raw_d;
+    net.packed = h->packed_d;
+    h->weights_set = true;
+    return AEM_OK;
+}
+
+int aem_set_action_space(aem_handle h, const double *actions, int A)
+{
+    if (!h || !actions) return aem_set_error(AEM_ERR_INVALID, "null argument");
+    if (A < 1 || A > AEM_MAX_ACTIONS) return aem_set_error(AEM_ERR_INVALID, "A must be in [1, 128]");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(cudaDeviceSynchronize());
+    memcpy(h->actions_h, actions, sizeof(double) * 2 * A);
+    AEM_CUDA_CHECK(cudaMemcpy(h->actions_d, actions, sizeof(double) * 2 * A, cudaMemcpyHostToDevice));
+    h->A = A;
+    h->actions_set = true;
+    return AEM_OK;
+}
+
+int aem_set_env_params(aem_handle h, const aem_env_params *p)
+{
+    if (!h || !p) return aem_set_error(AEM_ERR_INVALID, "null argument");
+    if (!(p->time_step > 0) || !(p->human_timestep >= 0))
+        return aem_set_error(AEM_ERR_INVALID, "time_step must be positive");
+    h->params = *p;
+    h->params_set = true;
+    return AEM_OK;
+}
+
+int aem_set_act_mode(aem_handle h, int act_fixed, int act_steps)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (act_fixed && act_steps < 1) return aem_set_error(AEM_ERR_INVALID, "act_steps must be >= 1");
+    h->net.act_fixed = act_fixed ? 1 : 0;
+    h->net.act_steps = act_steps;
+    return AEM_OK;
+}
+
+int aem_orca(aem_handle h, int B, int n, const double *humans_d, const double *robot_d, double *new_vel_d,
+             void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (!h->params_set) return aem_set_error(AEM_ERR_STATE, "aem_set_env_params has not been called");
+    if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (n - 1 + (h->params.robot_visible ? 1 : 0) > 32) return aem_set_error(AEM_ERR_INVALID, "too many neighbours");
+    if (!humans_d || !robot_d || !new_vel_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_orca(B, n, humans_d, robot_d, h->params, new_vel_d, as_stream(stream)));
+    h->launches += (B > 0);
+    return AEM_OK;
+}
+
+int aem_env_lookahead(aem_handle h, int B, int n, const double *robot_d, const double *humans_d,
+                      const double *new_vel_d, const double *global_time_d, double *rewards_d, int32_t *info_d,
+                      double *dmin_d, double *humans_next_d, void *stream)
+{
+    int rc = check_ready(h, false, true);
+    if (rc) return rc;
+    if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (!robot_d || !humans_d || !new_vel_d || !global_time_d || !rewards_d)
+        return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_env_lookahead(B, n, h->A, robot_d, humans_d, new_vel_d, global_time_d, h->actions_d,
+                                        h->lut_d, h->params, action_amax(h), rewards_d, info_d, dmin_d,
+                                        humans_next_d, as_stream(stream)));
+    h->launches += (B > 0);
+    return AEM_OK;
+}
+
+int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const double *humans_next_d,
+                  const double *rewards_d, double gamma_bar, double *values_d, float *net_values_d, int32_t *best_d,
+                  uint8_t *act_steps_d, void *stream)
+{
+    int rc = check_ready(h, true, true);
+    if (rc) return rc;
+    if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (!robot_d || !humans_next_d || !rewards_d || !values_d || !best_d)
+        return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    if ((long long)B * h->A > 0x7fffffffLL) return aem_set_error(AEM_ERR_INVALID, "B * A overflows int32");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    LookaheadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.net = h->net;
+    a.mode = 0;
+    a.n = n; a.T = n + 1;
+    a.S = 128 / a.T; if (a.S > 32) a.S = 32;
+    a.A = h->A;
+    a.total_samples = B * h->A;
+    a.dt = h->params.time_step;
+    a.gamma_bar = gamma_bar;
+    a.robot = robot_d; a.humans_next = humans_next_d; a.actions = h->actions_d; a.rewards = rewards_d;
+    a.values = values_d; a.net_values = net_values_d; a.steps = act_steps_d;
+    AEM_CUDA_CHECK(launch_lookahead(h, a, as_stream(stream)));
+    AEM_CUDA_CHECK(launch_select(values_d, robot_d, B, h->A, best_d, as_stream(stream)));
+    h->launches += 2 * (B > 0);
+    return AEM_OK;
+}
+
+int aem_env_apply(aem_handle h, int B, int n, double *robot_d, double *humans_d, const double *new_vel_d,
+                  double *global_time_d, const int32_t *chosen_d, const double *rewards_d, const int32_t *info_d,
+                  const double *dmin_d, double *out_reward_d, int32_t *out_done_d, int32_t *out_info_d,
+                  double *out_dmin_d, void *stream)
+{
+    int rc = check_ready(h, false, true);
+    if (rc) return rc;
+    if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (!robot_d || !humans_d || !new_vel_d || !global_time_d || !chosen_d)
+        return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_env_apply(B, n, h->A, robot_d, humans_d, new_vel_d, global_time_d, h->actions_d, chosen_d,
+                                    rewards_d, info_d, dmin_d, h->params.time_step, out_reward_d, out_done_d,
+                                    out_info_d, out_dmin_d, as_stream(stream)));
+    h->launches += (B > 0);
+    return AEM_OK;
+}
+
+int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *values_d, uint8_t *steps_d,
+                      void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (!h->weights_set) return aem_set_error(AEM_ERR_STATE, "aem_load_weights has not been called");
+    if (S < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad S / n");
+    if (!states_d || !values_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    LookaheadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.net = h->net;
+    a.mode = 1;
+    a.n = n; a.T = n + 1;
+    a.S = 128 / a.T; if (a.S > 32) a.S = 32;
+    a.A = 1;
+    a.total_samples = S;
+    a.states = states_d;
+    a.net_values = values_d; a.steps = steps_d;
+    AEM_CUDA_CHECK(launch_lookahead(h, a, as_stream(stream)));
+    h->launches += (S > 0);
+    return AEM_OK;
+}
+
+int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint8_t *steps_d, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (!h->weights_set) return aem_set_error(AEM_ERR_STATE, "aem_load_weights has not been called");
+    if (S < 0 || T < 1 || T > AEM_MAX_HUMANS + 1) return aem_set_error(AEM_ERR_INVALID, "bad S / T");
+    if (!x_d || !out_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    LookaheadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.net = h->net;
+    a.mode = 2;
+    a.n = T - 1; a.T = T;
+    a.S = 128 / T; if (a.S > 32) a.S = 32;
+    a.A = 1;
+    a.total_samples = S;
+    a.states = x_d;
+    a.gru_out = out_d; a.steps = steps_d;
+    AEM_CUDA_CHECK(launch_lookahead(h, a, as_stream(stream)));
+    h->launches += (S > 0);
+    return AEM_OK;
+}
+
+static int ensure_scratch(aem_handle h, int B, int n)
+{
+    if (B <= h->cap_B && n <= h->cap_n) return AEM_OK;
+    const int cB = B > h->cap_B ? B : h->cap_B, cn = n > h->cap_n ? n : h->cap_n;
+    cudaFree(h->s_robot); cudaFree(h->s_humans); cudaFree(h->s_time); cudaFree(h->s_newvel);
+    cudaFree(h->s_rewards); cudaFree(h->s_dmin); cudaFree(h->s_hnext); cudaFree(h->s_values);
+    cudaFree(h->s_oreward); cudaFree(h->s_info); cudaFree(h->s_best); cudaFree(h->s_odone); cudaFree(h->s_oinfo);
+    h->cap_B = h->cap_n = 0;
+    const size_t BA = (size_t)cB * AEM_MAX_ACTIONS;
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_robot, sizeof(double) * cB * 9));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_humans, sizeof(double) * cB * cn * 8));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_time, sizeof(double) * cB));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_newvel, sizeof(double) * cB * cn * 2));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_rewards, sizeof(double) * BA));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_dmin, sizeof(double) * BA));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_hnext, sizeof(double) * cB * cn * 5));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_values, sizeof(double) * BA));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_oreward, sizeof(double) * cB));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_info, sizeof(int32_t) * BA));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_best, sizeof(int32_t) * cB));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_odone, sizeof(int32_t) * cB));
+    AEM_CUDA_CHECK(cudaMalloc(&h->s_oinfo, sizeof(int32_t) * cB));
+    if (!h->s_stream) {
+        cudaStream_t st;
+        AEM_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        h->s_stream = st;
+    }
+    h->cap_B = cB; h->cap_n = cn;
+    return AEM_OK;
+}
+
+int aem_decide_step_host(aem_handle h, int B, int n, double gamma_bar, double *robot_h, double *humans_h,
+                         double *global_time_h, int32_t *chosen_h, double *reward_h, int32_t *done_h,
+                         int32_t *info_h, double *values_h)
+{
+    int rc = check_ready(h, true, true);
+    if (rc) return rc;
+    if (B < 1 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (!robot_h || !humans_h || !global_time_h || !chosen_h || !reward_h || !done_h || !info_h)
+        return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    rc = ensure_scratch(h, B, n);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(h->s_stream);
+    const int A = h->A;
+    AEM_CUDA_CHECK(cudaMemcpyAsync(h->s_robot, robot_h, sizeof(double) * B * 9, cudaMemcpyHostToDevice, st));
+    AEM_CUDA_CHECK(cudaMemcpyAsync(h->s_humans, humans_h, sizeof(double) * B * n * 8, cudaMemcpyHostToDevice, st));
+    AEM_CUDA_CHECK(cudaMemcpyAsync(h->s_time, global_time_h, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    rc = aem_orca(h, B, n, h->s_humans, h->s_robot, h->s_newvel, st);
+    if (rc) return rc;
+    rc = aem_env_lookahead(h, B, n, h->s_robot, h->s_humans, h->s_newvel, h->s_time, h->s_rewards, h->s_info,
+                           h->s_dmin, h->s_hnext, st);
+    if (rc) return rc;
+    rc = aem_lookahead(h, B, n, h->s_robot, h->s_hnext, h->s_rewards, gamma_bar, h->s_values, nullptr, h->s_best,
+                       nullptr, st);
+    if (rc) return rc;
+    rc = aem_env_apply(h, B, n, h->s_robot, h->s_humans, h->s_newvel, h->s_time, h->s_best, h->s_rewards, h->s_info,
+                       h->s_dmin, h->s_oreward, h->s_odone, h->s_oinfo, nullptr, st);
+    if (rc) return rc;
+    AEM_CUDA_CHECK(cudaMemcpyAsync(robot_h, h->s_robot, sizeof(double) * B * 9, cudaMemcpyDeviceToHost, st));
+    AEM_CUDA_CHECK(cudaMemcpyAsync(humans_h, h->s_humans, sizeof(double) * B * n * 8, cudaMemcpyDeviceToHost, st));
+    AEM_CUDA_CHECK(cudaMemcpyAsync(global_time_h, h->s_time, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    AEM_CUDA_CHECK(cudaMemcpyAsync(chosen_h, h->s_best, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    AEM_CUDA_CHECK(cudaMemcpyAsync(reward_h, h->s_oreward, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    AEM_CUDA_CHECK(cudaMemcpyAsync(done_h, h->s_odone, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    AEM_CUDA_CHECK(cudaMemcpyAsync(info_h, h->s_oinfo, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    if (values_h)
+        AEM_CUDA_CHECK(cudaMemcpyAsync(values_h, h->s_values, sizeof(double) * B * A, cudaMemcpyDeviceToHost, st));
+    AEM_CUDA_CHECK(cudaStreamSynchronize(st));
+    return AEM_OK;
+}
+
+long long aem_launch_count(aem_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

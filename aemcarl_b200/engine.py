@@ -1,0 +1,169 @@
+"""Engine: one aem_handle on one CUDA device; torch owns device memory and streams (plumbing only), every
+computation is a kernel of libaemcarl_b200.so launched on torch's current stream."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EnvParams, check
+
+F64, F32, I32, U8 = torch.float64, torch.float32, torch.int32, torch.uint8
+
+
+def make_env_params(time_step=0.2, time_limit=20.0, success_reward=1.0, collision_penalty=-0.25,
+                    discomfort_dist=0.2, agent_timestep=0.4, human_timestep=0.5, reward_increment=2.0,
+                    position_variance=2.0, direction_variance=2.0, robot_visible=False, orca_safety_space=0.0):
+    """env.config defaults with the README reward flags (README.md:56, test.py:36-40)."""
+    return EnvParams(time_step, time_limit, success_reward, collision_penalty, discomfort_dist, agent_timestep,
+                     human_timestep, reward_increment, position_variance, direction_variance,
+                     int(bool(robot_visible)), 0, orca_safety_space)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise _lib.AemError("aemcarl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)          # make sure the primary context exists
+        h = ctypes.c_void_p()
+        check(self.lib.aem_create(self.device.index, ctypes.byref(h)))
+        self.h = h
+        self.A = 0
+        self.params = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.aem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration -------------------------------------------------------------------------
+    def load_weights(self, flat):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        check(self.lib.aem_load_weights(self.h, flat.ctypes.data_as(ctypes.c_void_p), flat.size))
+
+    def set_action_space(self, actions):
+        actions = np.ascontiguousarray(actions, dtype=np.float64).reshape(-1, 2)
+        check(self.lib.aem_set_action_space(self.h, actions.ctypes.data_as(ctypes.c_void_p), actions.shape[0]))
+        self.A = actions.shape[0]
+        self.actions = actions
+
+    def set_env_params(self, params):
+        check(self.lib.aem_set_env_params(self.h, ctypes.byref(params)))
+        self.params = params
+
+    def set_act_mode(self, act_fixed, act_steps):
+        check(self.lib.aem_set_act_mode(self.h, int(bool(act_fixed)), int(act_steps)))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, t, dtype, shape=None):
+        assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype)
+        if shape is not None:
+            assert tuple(t.shape) == tuple(shape), (tuple(t.shape), shape)
+        return t
+
+    # ---- device entry points -------------------------------------------------------------------
+    def orca(self, humans, robot, out=None):
+        B, n, _ = humans.shape
+        self._chk(humans, F64, (B, n, 8)); self._chk(robot, F64, (B, 9))
+        if out is None:
+            out = torch.empty((B, n, 2), dtype=F64, device=self.device)
+        check(self.lib.aem_orca(self.h, B, n, _ptr(humans), _ptr(robot), _ptr(out), self._stream()))
+        return out
+
+    def env_lookahead(self, robot, humans, new_vel, global_time, out=None):
+        B, n, _ = humans.shape
+        A = self.A
+        self._chk(humans, F64, (B, n, 8)); self._chk(robot, F64, (B, 9))
+        self._chk(new_vel, F64, (B, n, 2)); self._chk(global_time, F64, (B,))
+        if out is None:
+            out = (torch.empty((B, A), dtype=F64, device=self.device), torch.empty((B, A), dtype=I32, device=self.device),
+                   torch.empty((B, A), dtype=F64, device=self.device),
+                   torch.empty((B, n, 5), dtype=F64, device=self.device))
+        rewards, info, dmin, hnext = out
+        check(self.lib.aem_env_lookahead(self.h, B, n, _ptr(robot), _ptr(humans), _ptr(new_vel), _ptr(global_time),
+                                         _ptr(rewards), _ptr(info), _ptr(dmin), _ptr(hnext), self._stream()))
+        return rewards, info, dmin, hnext
+
+    def lookahead(self, robot, humans_next, rewards, gamma_bar, out=None, want_net=True):
+        B, n, _ = humans_next.shape
+        A = self.A
+        self._chk(robot, F64, (B, 9)); self._chk(humans_next, F64, (B, n, 5)); self._chk(rewards, F64, (B, A))
+        if out is None:
+            out = (torch.empty((B, A), dtype=F64, device=self.device),
+                   torch.empty((B, A), dtype=F32, device=self.device) if want_net else None,
+                   torch.empty((B,), dtype=I32, device=self.device),
+                   torch.empty((B, A), dtype=U8, device=self.device) if want_net else None)
+        values, net, best, steps = out
+        check(self.lib.aem_lookahead(self.h, B, n, _ptr(robot), _ptr(humans_next), _ptr(rewards), float(gamma_bar),
+                                     _ptr(values), _ptr(net), _ptr(best), _ptr(steps), self._stream()))
+        return values, net, best, steps
+
+    def env_apply(self, robot, humans, new_vel, global_time, chosen, rewards=None, info=None, dmin=None):
+        B, n, _ = humans.shape
+        self._chk(chosen, I32, (B,))
+        o_reward = torch.empty((B,), dtype=F64, device=self.device)
+        o_done = torch.empty((B,), dtype=I32, device=self.device)
+        o_info = torch.empty((B,), dtype=I32, device=self.device)
+        o_dmin = torch.empty((B,), dtype=F64, device=self.device)
+        check(self.lib.aem_env_apply(self.h, B, n, _ptr(robot), _ptr(humans), _ptr(new_vel), _ptr(global_time),
+                                     _ptr(chosen), _ptr(rewards), _ptr(info), _ptr(dmin), _ptr(o_reward),
+                                     _ptr(o_done), _ptr(o_info), _ptr(o_dmin), self._stream()))
+        return o_reward, o_done, o_info, o_dmin
+
+    def value_forward(self, states):
+        S, n, d = states.shape
+        self._chk(states, F32, (S, n, 13))
+        values = torch.empty((S,), dtype=F32, device=self.device)
+        steps = torch.empty((S,), dtype=U8, device=self.device)
+        check(self.lib.aem_value_forward(self.h, S, n, _ptr(states), _ptr(values), _ptr(steps), self._stream()))
+        return values, steps
+
+    def gru_act(self, x, T):
+        rows, d = x.shape
+        assert d == 13 and rows % T == 0
+        self._chk(x, F32)
+        S = rows // T
+        out = torch.empty((rows, 50), dtype=F32, device=self.device)
+        steps = torch.empty((S,), dtype=U8, device=self.device)
+        check(self.lib.aem_gru_act(self.h, S, T, _ptr(x), _ptr(out), _ptr(steps), self._stream()))
+        return out, steps
+
+    # ---- host-buffer call (the e2e path) -------------------------------------------------------
+    def decide_step_host(self, robot, humans, global_time, gamma_bar, want_values=False):
+        """robot [B,9], humans [B,n,8], global_time [B]: contiguous float64 numpy arrays, updated IN PLACE."""
+        B, n, _ = humans.shape
+        for a in (robot, humans, global_time):
+            assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous
+        chosen = np.empty(B, dtype=np.int32)
+        reward = np.empty(B, dtype=np.float64)
+        done = np.empty(B, dtype=np.int32)
+        info = np.empty(B, dtype=np.int32)
+        values = np.empty((B, self.A), dtype=np.float64) if want_values else None
+        vp = values.ctypes.data_as(ctypes.c_void_p) if want_values else ctypes.c_void_p(0)
+        check(self.lib.aem_decide_step_host(self.h, B, n, float(gamma_bar), robot.ctypes.data_as(ctypes.c_void_p),
+                                            humans.ctypes.data_as(ctypes.c_void_p),
+                                            global_time.ctypes.data_as(ctypes.c_void_p),
+                                            chosen.ctypes.data_as(ctypes.c_void_p),
+                                            reward.ctypes.data_as(ctypes.c_void_p),
+                                            done.ctypes.data_as(ctypes.c_void_p),
+                                            info.ctypes.data_as(ctypes.c_void_p), vp))
+        return chosen, reward, done, info, values
+
+    def launch_count(self):
+        return int(self.lib.aem_launch_count(self.h))

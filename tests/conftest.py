@@ -1,0 +1,44 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import pyoracle
+    pyoracle.lib()
+    return pyoracle
+
+
+@pytest.fixture(scope="session")
+def actions():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "action_rotate.npz"))["actions"]
+
+
+@pytest.fixture(scope="session")
+def engine(actions):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from aemcarl_b200.engine import Engine, make_env_params
+    eng = Engine(0)
+    eng.set_action_space(actions)
+    eng.set_env_params(make_env_params())
+    return eng

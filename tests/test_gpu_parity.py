@@ -1,0 +1,259 @@
+"""GPU parity tests: every kernel of libaemcarl_b200.so against the CPU oracle and the golden fixtures.
+
+Tolerances (stated per kernel):
+  orca            bit-exact (FP32 ops individually rounded, same order as the oracle)
+  env_lookahead   rewards |diff| <= 1e-12 (FP64; libm atan2/hypot and summation order differ), info codes and
+                  next human states exact
+  lookahead       raw network value: <= 1e-4 relative (north_star); measured ~1e-6.  ACT step counts equal.
+                  argmax identical except on documented near-ties: top-2 gap <= 1e-4 * |value|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from aemcarl_b200 import weights as wts
+from aemcarl_b200.engine import make_env_params
+
+pytestmark = pytest.mark.gpu
+
+DECISIONS = ["circle5", "circle5_mixed", "circle5_visible", "square10", "circle18"]
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def load_decisions(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "decisions_%s.npz" % tag))
+    pb = float(g["ponder_bias"])
+    W = wts.synthetic_weights(int(g["weight_seed"]), None if np.isnan(pb) else pb)
+    return g, W
+
+
+def random_states(rng, B, n):
+    robot = np.zeros((B, 9))
+    robot[:, 0:2] = rng.uniform(-4, 4, (B, 2))
+    robot[:, 2:4] = rng.uniform(-1, 1, (B, 2))
+    robot[:, 4] = 0.3
+    robot[:, 5:7] = rng.uniform(-4, 4, (B, 2))
+    robot[:, 7] = 1.0
+    robot[:, 8] = np.pi / 2
+    humans = np.zeros((B, n, 8))
+    humans[:, :, 0:2] = rng.uniform(-4.5, 4.5, (B, n, 2))
+    # a few humans close to the robot / to each other so blobs, collisions and dense ORCA constraints occur
+    k = min(3, n)
+    humans[:, :k, 0:2] = robot[:, None, 0:2] + rng.uniform(-1.3, 1.3, (B, k, 2))
+    humans[:, :, 2:4] = rng.uniform(-0.8, 0.8, (B, n, 2))
+    humans[:, :, 4] = 0.3
+    humans[:, :, 5:7] = rng.uniform(-4.5, 4.5, (B, n, 2))
+    humans[:, :, 7] = 1.0
+    gt = rng.uniform(0, 19.5, B)
+    return robot, humans, gt
+
+
+@pytest.mark.parametrize("tag", DECISIONS)
+def test_orca_bit_exact_on_golden_states(engine, oracle, golden_dir, tag):
+    g, _ = load_decisions(golden_dir, tag)
+    vis = int(g["robot_visible"])
+    engine.set_env_params(make_env_params(robot_visible=vis))
+    ref = oracle.orca(g["humans"], g["robot"], oracle.default_params(robot_visible=vis))
+    out = engine.orca(dev(g["humans"]), dev(g["robot"])).cpu().numpy()
+    engine.set_env_params(make_env_params())
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("n,visible", [(1, 0), (2, 1), (5, 0), (5, 1), (10, 0), (18, 0), (18, 1), (32, 0)])
+def test_orca_bit_exact_random(engine, oracle, n, visible):
+    rng = np.random.RandomState(100 + n + visible)
+    robot, humans, _ = random_states(rng, 257, n)
+    # overlapping agents exercise the 1/timeStep branch, crowded ones linearProgram3
+    humans[:40, 1 % n, 0:2] = humans[:40, 0, 0:2] + 0.2
+    engine.set_env_params(make_env_params(robot_visible=visible))
+    ref = oracle.orca(humans, robot, oracle.default_params(robot_visible=visible))
+    out = engine.orca(dev(humans), dev(robot)).cpu().numpy()
+    engine.set_env_params(make_env_params())
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("tag", DECISIONS)
+def test_env_lookahead_golden(engine, oracle, golden_dir, actions, tag):
+    g, _ = load_decisions(golden_dir, tag)
+    vis = int(g["robot_visible"])
+    engine.set_env_params(make_env_params(robot_visible=vis))
+    robot, humans, gt = dev(g["robot"]), dev(g["humans"]), dev(g["global_time"])
+    nv = engine.orca(humans, robot)
+    rew, info, dmin, hnext = [t.cpu().numpy() for t in engine.env_lookahead(robot, humans, nv, gt)]
+    engine.set_env_params(make_env_params())
+    assert np.array_equal(hnext, g["humans_next"])
+    assert np.array_equal(info, g["infos"])
+    assert np.abs(rew - g["rewards"]).max() <= 1e-12
+    danger = g["infos"] == 1
+    assert np.allclose(dmin[danger], g["danger_dmin"][danger], rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("n", [1, 5, 10, 18, 32])
+def test_env_lookahead_random_vs_oracle(engine, oracle, actions, n):
+    rng = np.random.RandomState(200 + n)
+    B = 96
+    robot, humans, gt = random_states(rng, B, n)
+    robot[0, 0:2] = [-5.9, -5.8]          # lower clamp of the disc bounds
+    humans[0, 0, 0:2] = [-5.5, -5.6]
+    gt[1] = 19.0                          # timeout branch
+    robot[2, 5:7] = robot[2, 0:2] + [0.1, 0.0]   # goal branch
+    humans[3, :, 2:4] = 0.0               # stationary humans -> empty blobs
+    for params in (dict(), dict(agent_timestep=0.4, human_timestep=0.6, reward_increment=4.0,
+                                position_variance=4.0, direction_variance=3.0)):
+        engine.set_env_params(make_env_params(**params))
+        p = oracle.default_params(**params)
+        nv = oracle.orca(humans, robot, p)
+        ref = oracle.env_lookahead(robot, humans, nv, gt, actions, p)
+        out = [t.cpu().numpy() for t in engine.env_lookahead(dev(robot), dev(humans), dev(nv), dev(gt))]
+        assert np.array_equal(out[3], ref[3])
+        assert np.array_equal(out[1], ref[1])
+        assert np.abs(out[0] - ref[0]).max() <= 1e-12
+        assert np.array_equal(np.isinf(out[2]), np.isinf(ref[2]))
+        fin = np.isfinite(ref[2])
+        assert np.abs(out[2][fin] - ref[2][fin]).max() <= 1e-15
+        assert (ref[0] < 0).sum() > 50     # the occupancy reward is actually exercised
+    engine.set_env_params(make_env_params())
+
+
+def check_values(net, ref_net, steps, ref_steps, values, ref_values, best, ref_best):
+    rel = np.abs(net - ref_net) / np.maximum(np.abs(ref_net), 1e-3)
+    assert rel.max() <= 1e-4, rel.max()
+    assert np.array_equal(steps, ref_steps)
+    assert np.abs(values - ref_values).max() <= 1e-4 * np.maximum(np.abs(ref_values).max(), 1.0)
+    for b in np.nonzero(best != ref_best)[0]:        # documented near-tie rule
+        v = ref_values[b]
+        assert abs(v[best[b]] - v[ref_best[b]]) <= 1e-4 * max(abs(v[ref_best[b]]), 1e-3), (b, best[b], ref_best[b])
+    return rel.max()
+
+
+@pytest.mark.parametrize("tag", DECISIONS)
+def test_lookahead_golden(engine, golden_dir, tag):
+    """values / ACT steps / argmax against what the UNMODIFIED reference produced (eval mode)."""
+    g, W = load_decisions(golden_dir, tag)
+    engine.load_weights(W)
+    values, net, best, steps = engine.lookahead(dev(g["robot"]), dev(g["humans_next"]), dev(g["rewards"]),
+                                                pow(0.9, 0.2 * 1.0))
+    check_values(net.cpu().numpy(), g["net_values"], steps.cpu().numpy(), g["act_steps"], values.cpu().numpy(),
+                 g["values"], best.cpu().numpy(), g["best"])
+
+
+@pytest.mark.parametrize("tag", ["circle5", "square10", "circle18"])
+@pytest.mark.parametrize("wname", ["k1", "k2", "k3", "mixed"])
+def test_lookahead_golden_act_counts(engine, golden_dir, tag, wname):
+    """ACT halting counts 1 / 2 / 3 / mixed (ponder bias steered) against the reference module."""
+    g = np.load(os.path.join(golden_dir, "values_%s.npz" % tag))
+    pb = float(g["ponder_bias_" + wname])
+    engine.load_weights(wts.synthetic_weights(int(g["seed_" + wname]), None if np.isnan(pb) else pb))
+    R = g["robot"].shape[0]
+    rewards = np.zeros((R, 81))
+    values, net, best, steps = engine.lookahead(dev(g["robot"]), dev(g["humans_next"]), dev(rewards), 1.0)
+    net, steps = net.cpu().numpy(), steps.cpu().numpy()
+    ref = g["net_values_" + wname]
+    rel = np.abs(net - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert rel.max() <= 1e-4, rel.max()
+    assert np.array_equal(steps, g["act_steps_" + wname])
+
+
+@pytest.mark.parametrize("n,B", [(1, 3), (2, 5), (3, 40), (5, 1), (5, 64), (7, 33), (10, 17), (18, 9), (32, 4)])
+def test_lookahead_vs_oracle_shapes(engine, oracle, actions, n, B):
+    """ragged sizes: partial tiles, one env, 1..32 humans"""
+    rng = np.random.RandomState(300 + n)
+    W = wts.synthetic_weights(11 + n, -0.05)
+    engine.load_weights(W)
+    robot, humans, gt = random_states(rng, B, n)
+    hnext = np.concatenate([humans[:, :, 0:2] + 0.2 * humans[:, :, 2:4], humans[:, :, 2:5]], axis=2)
+    rewards = rng.uniform(-0.1, 0.0, (B, 81))
+    gbar = pow(0.9, 0.2)
+    rv, rnet, rbest, rsteps = oracle.lookahead(W, robot, hnext, rewards, actions, gamma_bar=gbar, nthreads=8)
+    values, net, best, steps = engine.lookahead(dev(robot), dev(hnext), dev(rewards), gbar)
+    check_values(net.cpu().numpy(), rnet, steps.cpu().numpy(), rsteps, values.cpu().numpy(), rv, best.cpu().numpy(),
+                 rbest)
+
+
+def test_lookahead_act_fixed(engine, oracle, actions):
+    rng = np.random.RandomState(5)
+    W = wts.synthetic_weights(21)
+    engine.load_weights(W)
+    robot, humans, gt = random_states(rng, 8, 5)
+    hnext = np.concatenate([humans[:, :, 0:2], humans[:, :, 2:5]], axis=2)
+    rewards = np.zeros((8, 81))
+    for steps_fixed in (1, 2, 4):
+        engine.set_act_mode(True, steps_fixed)
+        rv, rnet, rbest, rsteps = oracle.lookahead(W, robot, hnext, rewards, actions, gamma_bar=1.0, act_fixed=True,
+                                                   act_steps=steps_fixed, nthreads=8)
+        values, net, best, steps = engine.lookahead(dev(robot), dev(hnext), dev(rewards), 1.0)
+        check_values(net.cpu().numpy(), rnet, steps.cpu().numpy(), rsteps, values.cpu().numpy(), rv,
+                     best.cpu().numpy(), rbest)
+    engine.set_act_mode(False, 1)
+
+
+def test_select_semantics(engine, actions):
+    """first strict maximum wins, NaN never wins, goal short-circuit returns action 0 (multi_human_rl.py:321-372)"""
+    W = wts.synthetic_weights(3)
+    engine.load_weights(W)
+    rng = np.random.RandomState(1)
+    robot, humans, gt = random_states(rng, 4, 5)
+    robot[3, 5:7] = robot[3, 0:2]                      # robot already at its goal
+    hnext = np.concatenate([humans[:, :, 0:2], humans[:, :, 2:5]], axis=2)
+    rewards = np.zeros((4, 81))
+    rewards[0, 10] = 50.0
+    rewards[0, 40] = 50.0 + 0.0                        # exact tie is decided by the lowest index only if equal
+    rewards[1, :] = np.nan                             # all NaN -> -1
+    rewards[2, 5] = np.nan
+    values, net, best, steps = engine.lookahead(dev(robot), dev(hnext), dev(rewards), 0.0)
+    best = best.cpu().numpy()
+    assert best[0] == 10 and best[1] == -1 and best[2] != 5 and best[3] == 0
+
+
+@pytest.mark.parametrize("n", [5, 18])
+def test_value_forward_and_gru_act_vs_oracle(engine, oracle, n):
+    rng = np.random.RandomState(400 + n)
+    W = wts.synthetic_weights(31, -0.1)
+    engine.load_weights(W)
+    S = 77
+    states = rng.randn(S, n, 13).astype(np.float32)
+    states[:, :, 0] = np.abs(states[:, :1, 0]) * 3
+    states[:, :, 1:6] = states[:, :1, 1:6]
+    rv, rs = oracle.value_forward_batch(W, states, nthreads=8)
+    v, s = engine.value_forward(dev(states))
+    rel = np.abs(v.cpu().numpy() - rv) / np.maximum(np.abs(rv), 1e-3)
+    assert rel.max() <= 1e-4
+    assert np.array_equal(s.cpu().numpy(), rs)
+    T = n + 1
+    x = rng.randn(S * T, 13).astype(np.float32)
+    ro, rsteps = oracle.gru_act(W, x, T)
+    o, st = engine.gru_act(dev(x), T)
+    assert np.array_equal(st.cpu().numpy(), rsteps)
+    assert np.abs(o.cpu().numpy() - ro).max() <= 1e-5
+
+
+def test_decide_step_host_matches_device_pipeline(engine, oracle, actions):
+    rng = np.random.RandomState(9)
+    W = wts.synthetic_weights(1)
+    engine.load_weights(W)
+    B, n = 50, 5
+    robot, humans, gt = random_states(rng, B, n)
+    gbar = pow(0.9, 0.2)
+    p = oracle.default_params()
+    nv = oracle.orca(humans, robot, p)
+    rew, info, dmin, hnext = oracle.env_lookahead(robot, humans, nv, gt, actions, p)
+    rv, rnet, rbest, rsteps = oracle.lookahead(W, robot, hnext, rew, actions, gamma_bar=gbar, nthreads=8)
+    r2, h2, t2 = robot.copy(), humans.copy(), gt.copy()
+    chosen, reward, done, inf, values = engine.decide_step_host(r2, h2, t2, gbar, want_values=True)
+    same = chosen == rbest
+    assert same.mean() > 0.9
+    assert np.abs(values - rv).max() <= 1e-4
+    r3, h3, t3 = robot.copy(), humans.copy(), gt.copy()
+    oracle.env_apply(r3, h3, nv, t3, actions, chosen, p)
+    assert np.array_equal(r2, r3) and np.array_equal(h2, h3) and np.array_equal(t2, t3)
+    assert np.array_equal(inf, info[np.arange(B), chosen])
+    assert np.array_equal(reward, rew[np.arange(B), chosen]) or np.abs(reward - rew[np.arange(B), chosen]).max() < 1e-12
+    assert np.array_equal(done, (inf >= 2).astype(np.int32))
