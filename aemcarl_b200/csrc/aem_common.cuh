@@ -122,6 +122,10 @@ cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans,
                              double *out_reward, int32_t *out_done, int32_t *out_info, double *out_dmin,
                              cudaStream_t st);
 
+cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double *global_time, const int32_t *done,
+                             const int32_t *info, const double *pool_robot, const double *pool_humans, int P,
+                             int32_t *case_idx, int case_stride, unsigned long long *outcome_counts, cudaStream_t st);
+
 struct LookaheadArgs {
     NetParams net;
     int mode;            // 0 = lookahead from env state, 1 = rotated states, 2 = GRU-ACT only

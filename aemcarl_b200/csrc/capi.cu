@@ -269,6 +269,22 @@ int aem_env_apply(aem_handle h, int B, int n, double *robot_d, double *humans_d,
     return AEM_OK;
 }
 
+int aem_env_reset_done(aem_handle h, int B, int n, double *robot_d, double *humans_d, double *global_time_d,
+                       const int32_t *done_d, const int32_t *info_d, const double *pool_robot_d,
+                       const double *pool_humans_d, int P, int32_t *case_idx_d, int case_stride,
+                       unsigned long long *outcome_counts_d, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (B < 0 || n < 1 || n > AEM_MAX_HUMANS || P < 1) return aem_set_error(AEM_ERR_INVALID, "bad B / n / P");
+    if (!robot_d || !humans_d || !global_time_d || !done_d || !pool_robot_d || !pool_humans_d || !case_idx_d)
+        return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_env_reset(B, n, robot_d, humans_d, global_time_d, done_d, info_d, pool_robot_d,
+                                    pool_humans_d, P, case_idx_d, case_stride, outcome_counts_d, as_stream(stream)));
+    h->launches += (B > 0);
+    return AEM_OK;
+}
+
 int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *values_d, uint8_t *steps_d,
                       void *stream)
 {

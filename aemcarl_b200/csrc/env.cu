@@ -291,4 +291,39 @@ cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans,
     return cudaGetLastError();
 }
 
+// Explorer.run_k_episodes (explorer.py:44-80) keeps one env busy with consecutive cases; here every finished env of
+// the batch is re-seeded from a pool of pre-generated scenarios (CrowdSim.reset, crowd_sim.py:486-552 runs on the
+// host with numpy's MT19937 stream) and the episode outcome is counted.
+__global__ void env_reset_kernel(int B, int n, double *__restrict__ robot, double *__restrict__ humans,
+                                 double *__restrict__ global_time, const int32_t *__restrict__ done,
+                                 const int32_t *__restrict__ info, const double *__restrict__ pool_robot,
+                                 const double *__restrict__ pool_humans, int P, int32_t *__restrict__ case_idx,
+                                 int case_stride, unsigned long long *__restrict__ outcome_counts)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || !done[b]) return;
+    const int c = case_idx[b];
+    const int src = ((c % P) + P) % P;
+    for (int k = 0; k < 9; ++k) robot[(size_t)b * 9 + k] = pool_robot[(size_t)src * 9 + k];
+    for (int k = 0; k < n * 8; ++k) humans[(size_t)b * n * 8 + k] = pool_humans[(size_t)src * n * 8 + k];
+    global_time[b] = 0.0;
+    case_idx[b] = c + case_stride;
+    if (outcome_counts && info) {
+        const int code = info[b];
+        if (code >= 0 && code < 5) atomicAdd(outcome_counts + code, 1ULL);
+    }
+}
+
+cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double *global_time, const int32_t *done,
+                             const int32_t *info, const double *pool_robot, const double *pool_humans, int P,
+                             int32_t *case_idx, int case_stride, unsigned long long *outcome_counts, cudaStream_t st)
+{
+    if (B <= 0) return cudaSuccess;
+    const int threads = 128;
+    env_reset_kernel<<<(B + threads - 1) / threads, threads, 0, st>>>(B, n, robot, humans, global_time, done, info,
+                                                                      pool_robot, pool_humans, P, case_idx,
+                                                                      case_stride, outcome_counts);
+    return cudaGetLastError();
+}
+
 }  // namespace aem

@@ -126,6 +126,16 @@ class Engine:
                                      _ptr(o_done), _ptr(o_info), _ptr(o_dmin), self._stream()))
         return o_reward, o_done, o_info, o_dmin
 
+    def env_reset_done(self, robot, humans, global_time, done, info, pool_robot, pool_humans, case_idx, case_stride,
+                       outcome_counts=None):
+        B, n, _ = humans.shape
+        P = pool_robot.shape[0]
+        self._chk(done, I32, (B,)); self._chk(case_idx, I32, (B,))
+        self._chk(pool_robot, F64, (P, 9)); self._chk(pool_humans, F64, (P, n, 8))
+        check(self.lib.aem_env_reset_done(self.h, B, n, _ptr(robot), _ptr(humans), _ptr(global_time), _ptr(done),
+                                          _ptr(info), _ptr(pool_robot), _ptr(pool_humans), P, _ptr(case_idx),
+                                          int(case_stride), _ptr(outcome_counts), self._stream()))
+
     def value_forward(self, states):
         S, n, d = states.shape
         self._chk(states, F32, (S, n, 13))

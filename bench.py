@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- lookahead env-steps/s (predict + step) of the AEMCARL hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs B] [--humans n] [--impl ours|reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+One "step" = one pass of the hot path over the whole batch: for every environment ORCA for the humans, the
+per-action env lookahead (collision / goal / timeout / occupancy reward), the fused 81-action value lookahead
++ argmax (MultiHumanRL.predict) and CrowdSim.step for the chosen action; finished episodes are re-seeded.
+Workload at N = 1: BASELINE.json configs[1] -- 4096 envs x 5 humans x 81 actions (80 + stop), random-init
+weights (synthetic_weights(seed 0)), circle_crossing scenarios of the train stream.  Environments are independent,
+so N GPUs run N shards of 4096 envs each (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lookahead env-steps/sec (predict+step), 5 humans"
+UNIT = "env-steps/s"
+
+
+def mac_dense(T, K):
+    """GEMM MACs of one (env, action) sample with T tokens and K ACT steps."""
+    return T * K * 25800 + 3 * T * (25000 + 100 * T) + 10650
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step(po, W, robot, humans, gt, actions, params, gbar, nthreads):
+    """The CPU restatement of one full env-step (predict + step) on a batch -- the CPU baseline."""
+    nv = po.orca(humans, robot, params, nthreads)
+    rew, info, dmin, hnext = po.env_lookahead(robot, humans, nv, gt, actions, params, nthreads)
+    vals, net, best, steps = po.lookahead(W, robot, hnext, rew, actions, dt=params.time_step, gamma_bar=gbar,
+                                          nthreads=nthreads)
+    best = np.where(best < 0, 0, best).astype(np.int32)
+    po.env_apply(robot, humans, nv, gt, actions, best, params)
+    return best, info[np.arange(len(best)), best]
+
+
+def cpu_baseline(robot, humans, gt, W, actions, gbar, budget_s=12.0):
+    """oracle port timed on this box's host cores on a bounded sample of the same workload states."""
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    params = po.default_params()
+    B = robot.shape[0]
+    pilot = min(B, max(cores, 8))
+    r, h, t = robot[:pilot].copy(), humans[:pilot].copy(), gt[:pilot].copy()
+    t0 = time.perf_counter()
+    oracle_step(po, W, r, h, t, actions, params, gbar, cores)
+    dt = time.perf_counter() - t0
+    ns = int(min(B, max(pilot, budget_s / max(dt / pilot, 1e-9))))
+    r, h, t = robot[:ns].copy(), humans[:ns].copy(), gt[:ns].copy()
+    t0 = time.perf_counter()
+    oracle_step(po, W, r, h, t, actions, params, gbar, cores)
+    dt = time.perf_counter() - t0
+    return {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of the %d envs of this workload, one full env-step (ORCA + env lookahead + 81-action value "
+                      "lookahead + step) by oracle/aem_oracle.c on %d threads, %.1f s" % (ns, B, cores, dt)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and cannot
+    travel to the GPU box (and needs gym / rvo2 which do not exist here), so this arm times the oracle port
+    (oracle/aem_oracle.c, validated against the unmodified reference in tests/golden) on all host threads."""
+    if rank != 0:
+        return
+    from aemcarl_b200 import scenarios, weights as wts
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    actions = po.build_action_space()
+    W = wts.synthetic_weights(0)
+    n = args.humans
+    ns = args.ref_envs
+    params = po.default_params()
+    gbar = pow(0.9, params.time_step * 1.0)
+    robot, humans = scenarios.generate_pool("train", 0, ns, n, "circle_crossing")
+    gt = np.zeros(ns)
+    pool_r, pool_h = robot.copy(), humans.copy()
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        best, info = oracle_step(po, W, robot, humans, gt, actions, params, gbar, cores)
+        dt = time.perf_counter() - t0
+        done = info >= 2
+        robot[done], humans[done], gt[done] = pool_r[done], pool_h[done], 0.0
+        if it >= args.warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    value = ns * args.steps / total
+    sample = "%d envs per step (bounded sample of the %d-env workload), all %d host threads" % (ns, args.envs, cores)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "batched lookahead inference: %d envs x %d humans x 81 actions, random-init weights"
+                                  % (args.envs, n), "envs_per_step": ns},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--humans", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-envs", type=int, default=256, help="--impl reference: envs per step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from aemcarl_b200 import weights as wts
+    from aemcarl_b200.engine import Engine, make_env_params
+    from aemcarl_b200.policy_math import build_action_space
+    from aemcarl_b200.vec_env import VecCrowdSim
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    B, n = args.envs, args.humans
+    eng = Engine(local_rank)
+    actions = build_action_space(1.0)
+    eng.set_action_space(actions)
+    eng.set_env_params(make_env_params())
+    W = wts.synthetic_weights(0)
+    eng.load_weights(W)
+    env = VecCrowdSim(eng, B, n, "circle_crossing", "train", first_case=rank * B, pool_size=B,
+                      case_stride=world * B)
+    gbar = env.gamma_bar()
+    dev = eng.device
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step(ev=None):
+        e = eng
+        if ev:
+            ev[0].record()
+        e.orca(env.humans, env.robot, out=env.new_vel)
+        e.env_lookahead(env.robot, env.humans, env.new_vel, env.global_time,
+                        out=(env.rewards, env.info, env.dmin, env.humans_next))
+        if ev:
+            ev[1].record()
+        e.lookahead(env.robot, env.humans_next, env.rewards, gbar,
+                    out=(env.values, env.net_values, env.best, env.act_steps))
+        if ev:
+            ev[2].record()
+        env.apply(auto_reset=True)
+        if ev:
+            ev[3].record()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    snap = env.state_numpy()                       # workload states for the CPU baseline (after warm-up)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    l0 = eng.launch_count()
+    barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    for i in range(args.steps):
+        flush.zero_()                              # L2 flush between timed iterations (outside the event pairs)
+        step(evs[i])
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count() - l0
+    step_ms = np.array([e[0].elapsed_time(e[3]) for e in evs])
+    look_ms = np.array([e[1].elapsed_time(e[2]) for e in evs])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = B * world * args.steps / (total_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (lookahead_kernel) ----
+    ks = env.act_steps.to(torch.int64)
+    T = n + 1
+    hist = torch.bincount(ks.flatten(), minlength=4).cpu().numpy().tolist()
+    macs = float(sum(cnt * mac_dense(T, k) for k, cnt in enumerate(hist) if k > 0))
+    flops = 2.0 * macs
+    peaks, peak_kind = load_peaks()
+    kernel_ms = float(look_ms.mean())
+    achieved = flops / (kernel_ms / 1e3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "lookahead_ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "lookahead_kernel", "kernel_ms": kernel_ms,
+                "kernel_share_of_step": float(look_ms.sum() / step_ms.sum()),
+                "peak_source": "bf16_tflops_sustained of %s MEASURED_PEAKS.json" % peak_kind,
+                "pipe": "fp32_ffma (FP32-exact parity path, no tensor-core math)",
+                "fp32_pipe_peak_tflops": fp32_peak, "frac_fp32_pipe": achieved / fp32_peak,
+                "algorithmic_flops_per_launch": flops, "act_steps_hist": hist}
+
+    # ---- e2e: the same env-step through the C-ABI host-buffer call (H2D + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        robot_h = torch.empty((B, 9), dtype=torch.float64).pin_memory().numpy()
+        humans_h = torch.empty((B, n, 8), dtype=torch.float64).pin_memory().numpy()
+        time_h = torch.empty((B,), dtype=torch.float64).pin_memory().numpy()
+        robot_h[:], humans_h[:], time_h[:] = snap
+        for _ in range(3):
+            chosen, reward, done, info, _ = eng.decide_step_host(robot_h, humans_h, time_h, gbar)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            chosen, reward, done, info, _ = eng.decide_step_host(robot_h, humans_h, time_h, gbar)
+            d = done != 0
+            if d.any():                            # host-side re-seed of finished episodes (inside the timed region)
+                robot_h[d] = env.pool_robot_h[d]
+                humans_h[d] = env.pool_humans_h[d]
+                time_h[d] = 0.0
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        state_bytes = B * (9 + 8 * n + 1) * 8
+        e2e = {"value": B * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
+               "d2h_bytes_per_step": state_bytes + B * (4 + 8 + 4 + 4), "ms_per_step": 1e3 * e2e_s / args.steps,
+               "api": "aem_decide_step_host (pinned host buffers, host wall clock, max over ranks)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(snap[0], snap[1], snap[2], W, actions, gbar)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "batched lookahead inference: %d envs x %d humans x 81 actions per GPU, "
+                                      "random-init weights (synthetic_weights seed 0), circle_crossing train-stream "
+                                      "scenarios, predict + step" % (B, n),
+                          "envs_per_gpu": B, "humans": n, "actions": 81, "l2": "flushed between timed iterations "
+                          "(256 MB memset outside the event pairs)", "parallelism": "env-sharded x%d" % world},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+               "cpu_baseline": cpu,
+               "kernel_ms": {"lookahead": kernel_ms, "orca+env_lookahead": float(np.mean(
+                   [e[0].elapsed_time(e[1]) for e in evs])), "apply+reset": float(np.mean(
+                       [e[2].elapsed_time(e[3]) for e in evs]))}}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

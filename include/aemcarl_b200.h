@@ -13,6 +13,7 @@
  *                          cadrl.py:239-274, ValueNetworkTransformerAndGRU.forward qnetwork_factory.py:641-687,
  *                          ATCBasic/GRUEXND components.py:38-137, r + gamma^(dt*v_pref) * V, strict-'>' argmax)
  *   aem_env_apply       <- crowd_sim/envs/crowd_sim.py:653-669 (step(update=True): advance robot/humans/time)
+ *   aem_env_reset_done  <- CrowdSim.reset for finished episodes of a batch (crowd_sim.py:486-552, explorer.py:44-47)
  *   aem_value_forward   <- model(state) on already rotated states (explorer.py:137, trainer.py:52,75)
  *   aem_gru_act         <- ATCBasic.forward components.py:107-137 (fused GRU-cell / adaptive-computation-time)
  *   aem_decide_step_host<- Robot.act + CrowdSim.step through HOST buffers (explorer.py:51-53), the e2e call
@@ -109,6 +110,15 @@ int aem_env_apply(aem_handle h, int B, int n, double *robot_d, double *humans_d,
                   double *global_time_d, const int32_t *chosen_d, const double *rewards_d, const int32_t *info_d,
                   const double *dmin_d, double *out_reward_d, int32_t *out_done_d, int32_t *out_info_d,
                   double *out_dmin_d, void *stream);
+
+/* Vectorised Explorer reset (explorer.py:44-47 + CrowdSim.reset crowd_sim.py:486-552): every env with done_d[b] != 0
+ * is re-seeded from scenario `case_idx_d[b] mod P` of a host-generated pool (pool_robot_d [P][9], pool_humans_d
+ * [P][n][8]), its clock is zeroed, case_idx_d[b] += case_stride, and outcome_counts_d[info_d[b]] (5 x u64, may be
+ * NULL) is incremented. */
+int aem_env_reset_done(aem_handle h, int B, int n, double *robot_d, double *humans_d, double *global_time_d,
+                       const int32_t *done_d, const int32_t *info_d, const double *pool_robot_d,
+                       const double *pool_humans_d, int P, int32_t *case_idx_d, int case_stride,
+                       unsigned long long *outcome_counts_d, void *stream);
 
 /* states_d [S][n][13] f32 (rotated joint states) -> values_d [S] f32, steps_d [S] u8 (may be NULL) */
 int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *values_d, uint8_t *steps_d,
