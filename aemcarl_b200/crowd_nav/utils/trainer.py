@@ -1,0 +1,93 @@
+"""Value-network regression (crowd_nav/utils/trainer.py:22-86): MSE(model(inputs)[0], values) with SGD / Adam /
+RMSprop exactly as configured in the reference.  The one addition is the data-parallel hook: when
+torch.distributed is initialised, the flat gradient (113,752 live floats, one bucket) is all-reduced (NCCL over
+NVLink on GPUs, gloo in the CPU tests) and averaged between loss.backward() and optimizer.step() -- the only
+collective of the whole system."""
+import logging
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.optim as optim
+from torch.utils.data import DataLoader
+
+
+def allreduce_gradients(model):
+    """average gradients over ranks with ONE flat all-reduce; no-op without an initialised process group"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    if not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= dist.get_world_size()
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return flat.numel()
+
+
+def broadcast_parameters(model, src=0):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for p in model.state_dict().values():
+            dist.broadcast(p, src)
+
+
+class Trainer(object):
+    def __init__(self, model, memory, device, batch_size):
+        self.model = model
+        self.device = device
+        self.criterion = nn.MSELoss().to(device)
+        self.memory = memory
+        self.data_loader = None
+        self.batch_size = batch_size
+        self.optimizer = None
+
+    def set_learning_rate(self, learning_rate, optimizer_type="SGD"):
+        logging.info("Current learning rate: %f,Optimizer Type %s", learning_rate, optimizer_type)
+        if optimizer_type == "Adam":
+            self.optimizer = optim.Adam(self.model.parameters(), lr=learning_rate, betas=(0.9, 0.99), eps=1e-03)
+        elif optimizer_type == "RMSprop":
+            self.optimizer = optim.RMSprop(self.model.parameters(), lr=learning_rate, alpha=0.9)
+        else:
+            if optimizer_type != "SGD":
+                print("Not support optimizer: ", optimizer_type)
+            self.optimizer = optim.SGD(self.model.parameters(), lr=learning_rate, momentum=0.9, weight_decay=0.00)
+
+    def _step(self, inputs, values):
+        self.optimizer.zero_grad()
+        outputs, _ = self.model(inputs)
+        loss = self.criterion(outputs, values)
+        loss.backward()
+        allreduce_gradients(self.model)
+        self.optimizer.step()
+        return loss.data.item()
+
+    def optimize_epoch(self, num_epochs):
+        if self.optimizer is None:
+            raise ValueError("Learning rate is not set!")
+        if self.data_loader is None:
+            self.data_loader = DataLoader(self.memory, self.batch_size, shuffle=True, drop_last=True)
+        average_epoch_loss = 0
+        for epoch in range(num_epochs):
+            epoch_loss = 0
+            for inputs, values in self.data_loader:
+                epoch_loss += self._step(inputs, values)
+            average_epoch_loss = epoch_loss / len(self.memory)
+            logging.debug("Average loss in epoch %d: %.2E", epoch, average_epoch_loss)
+        return average_epoch_loss
+
+    def optimize_batch(self, num_batches):
+        if self.optimizer is None:
+            raise ValueError("Learning rate is not set!")
+        if self.data_loader is None:
+            self.data_loader = DataLoader(self.memory, self.batch_size, shuffle=True)
+        losses = 0
+        for _ in range(num_batches):
+            inputs, values = next(iter(self.data_loader))
+            losses += self._step(inputs, values)
+        average_loss = losses / num_batches
+        logging.debug("Average loss : %.2E", average_loss)
+        return average_loss

@@ -177,3 +177,16 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.aem_launch_count(self.h))
+
+
+_ENGINES = {}
+
+
+def get_engine(device=0, role="default"):
+    """Process-wide Engine cache: one aem_handle per (device, role).  Roles keep independent action tables /
+    env params apart (e.g. the policy's 81-action table vs. the env's single arbitrary action)."""
+    idx = device if isinstance(device, int) else (torch.device(device).index or 0)
+    key = (idx, role)
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(idx)
+    return _ENGINES[key]

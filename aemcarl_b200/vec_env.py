@@ -64,6 +64,13 @@ class VecCrowdSim:
         self.case_idx.copy_((torch.arange(self.B, device=self.device) + self.case_stride).to(I32))
         self.outcomes.zero_()
 
+    def load_cases(self, first):
+        """env b plays pool scenario (first + b) mod pool from t = 0"""
+        idx = (torch.arange(self.B, device=self.device) + int(first)) % self.pool_size
+        self.robot.copy_(self.pool_robot[idx])
+        self.humans.copy_(self.pool_humans[idx])
+        self.global_time.zero_()
+
     def lookahead(self):
         """predict(): ORCA for the humans, per-action env lookahead, fused value lookahead, argmax."""
         e = self.engine

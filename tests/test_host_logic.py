@@ -1,0 +1,155 @@
+"""CPU: host-side mirror of the reference interface -- scenario generation, configs, value types, the nn.Module
+state_dict surface, replay memory, and the no-fallback rule."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from aemcarl_b200 import scenarios, weights as wts
+from aemcarl_b200.crowd_nav.default_configs import env_config, policy_config, train_config
+from aemcarl_b200.crowd_nav.policy.policy_factory import policy_factory
+from aemcarl_b200.crowd_nav.utils.memory import ReplayMemory
+from aemcarl_b200.crowd_sim import make
+from aemcarl_b200.crowd_sim.envs.utils.action import ActionXY
+from aemcarl_b200.crowd_sim.envs.utils.robot import Robot
+from aemcarl_b200.crowd_sim.envs.utils.state import FullState, JointState, ObservableState
+
+
+@pytest.mark.parametrize("tag,n,rule", [("circle5", 5, "circle_crossing"), ("square10", 10, "square_crossing"),
+                                        ("circle18", 18, "circle_crossing")])
+def test_scenarios_bit_exact(golden_dir, tag, n, rule):
+    g = np.load(os.path.join(golden_dir, "scenarios.npz"))
+    for phase in ("test", "val", "train"):
+        ref = g["%s_%s" % (tag, phase)]
+        for case in range(ref.shape[0]):
+            rb, hs = scenarios.generate_case(phase, case, n, rule)
+            assert np.array_equal(hs[:, [0, 1, 5, 6]], ref[case])
+            assert np.array_equal(rb, [0, -4, 0, 0, 0.3, 0, 4, 1.0, np.pi / 2])
+
+
+def test_case_seeds():
+    assert scenarios.case_seed("val", 3) == 3
+    assert scenarios.case_seed("test", 0) == 1000
+    assert scenarios.case_seed("train", 0) == 2000
+
+
+def make_env(n=5, sim="circle_crossing"):
+    cfg = env_config(sim__human_num=n)
+    env = make("CrowdSim-v0")
+    env.configure(cfg)
+    env.test_sim = sim
+    robot = Robot(cfg, "robot")
+    torch.manual_seed(0)
+    policy = policy_factory["actenvcarl"]()
+    policy.configure(policy_config())
+    robot.set_policy(policy)
+    return env, robot, policy
+
+
+def test_crowdsim_reset_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "scenarios.npz"))
+    env, robot, policy = make_env()
+    with pytest.raises(AttributeError, match="robot has to be set"):
+        env.reset("test")
+    env.set_robot(robot)
+    with pytest.raises(AssertionError):
+        env.reset("bogus")
+    for case in range(6):
+        ob = env.reset("test", case)
+        got = np.array([[h.px, h.py, h.gx, h.gy] for h in env.humans])
+        assert np.array_equal(got, g["circle5_test"][case])
+        assert len(ob) == 5 and isinstance(ob[0], ObservableState)
+        assert env.global_time == 0 and policy.time_step == 0.2 and robot.time_step == 0.2
+    assert env.case_counter["test"] == 6                      # counter advanced and wraps mod case_size
+    assert env.case_size == {"train": np.iinfo(np.uint32).max - 2000, "val": 100, "test": 500}
+    assert (robot.px, robot.py, robot.gx, robot.gy, robot.theta) == (0, -4.0, 0, 4.0, np.pi / 2)
+    env.reset("test", 499)
+    assert env.case_counter["test"] == 0
+
+
+def test_value_types():
+    fs = FullState(1, 2, 3, 4, 0.3, 5, 6, 1.0, 0.5)
+    os_ = ObservableState(7, 8, 9, 10, 0.4)
+    assert fs + os_ == (1, 2, 3, 4, 0.3, 5, 6, 1.0, 0.5, 7, 8, 9, 10, 0.4)      # state.py:17-18,36-37
+    JointState(fs, [os_])
+    with pytest.raises(AssertionError):
+        JointState(os_, [os_])
+    assert ActionXY(1, 2).vx == 1
+
+
+def test_policy_surface_and_errors():
+    env, robot, policy = make_env()
+    assert policy.name == "ACTENVCARL" and policy.trainable and policy.multiagent_training
+    assert policy.gamma == 0.9 and policy.kinematics == "holonomic" and policy.query_env
+    state = JointState(FullState(0, -4, 0, 0, 0.3, 0, 4, 1.0, np.pi / 2), [ObservableState(1, 1, 0, 0, 0.3)])
+    with pytest.raises(AttributeError, match="Phase, device"):
+        policy.predict(state)
+    policy.phase, policy.device = "train", torch.device("cuda:0")
+    with pytest.raises(AttributeError, match="Epsilon"):
+        policy.predict(state)
+    # goal short-circuit comes before anything else (multi_human_rl.py:321-322)
+    policy.phase = "test"
+    at_goal = JointState(FullState(0, 4, 0, 0, 0.3, 0, 4, 1.0, 0), [ObservableState(1, 1, 0, 0, 0.3)])
+    assert policy.predict(at_goal) == ActionXY(0, 0)
+    policy.build_action_space(1.0)
+    assert len(policy.action_space) == 81 and policy.action_space[0] == ActionXY(0, 0)
+    assert abs(policy.action_space[6].vx - 0.11904303084504313) < 1e-16
+    with pytest.raises(RuntimeError, match="CUDA"):
+        policy.set_device(torch.device("cpu"))
+
+
+def test_state_dict_surface_matches_reference_checkpoints():
+    _, _, policy = make_env()
+    sd = policy.get_model().state_dict()
+    assert sum(v.numel() for v in sd.values()) == 139352
+    keys = list(sd.keys())
+    for k, shape in wts.WEIGHT_SPEC + wts.DEAD_TEMPLATE_SPEC:
+        assert k in keys and tuple(sd[k].shape) == tuple(shape)
+    flat = policy.get_model().flat_weights()
+    assert flat.shape == (wts.NUM_WEIGHTS,)
+    rt = wts.unflatten(flat)
+    assert all(np.array_equal(rt[k], sd[k].numpy()) for k, _ in wts.WEIGHT_SPEC)
+    m2 = policy_factory["actenvcarl"]()
+    m2.configure(policy_config())
+    m2.get_model().load_state_dict(sd)                                            # checkpoint round trip
+    assert np.array_equal(m2.get_model().flat_weights(), flat)
+
+
+def test_module_forward_batch_global_halting_matches_oracle_per_sample_at_batch_one(oracle):
+    _, _, policy = make_env()
+    m = policy.get_model()
+    W = m.flat_weights()
+    rng = np.random.RandomState(0)
+    for _ in range(5):
+        st = rng.randn(5, 13).astype(np.float32)
+        st[:, 1:6] = st[0, 1:6]
+        with torch.no_grad():
+            v, _ = m.forward_torch(torch.from_numpy(st).unsqueeze(0))
+        vo, ko = oracle.value_forward(W, st)
+        assert abs(v.item() - vo) <= 2e-6 * max(abs(vo), 1e-2) + 2e-7
+        assert m.get_step_cnt() == ko
+
+
+def test_replay_memory_ring():
+    mem = ReplayMemory(3)
+    for i in range(5):
+        mem.push(i)
+    assert len(mem) == 3 and mem.is_full() and sorted(mem.memory) == [2, 3, 4] and mem[mem.position - 1] == 4
+
+
+def test_default_configs_have_reference_keys():
+    e, p, t = env_config(readme_reward_flags=False), policy_config(), train_config()
+    assert e.getfloat("reward", "human_timestep") == 0.6 and e.getint("env", "test_size") == 500
+    assert env_config().getfloat("reward", "human_timestep") == 0.5
+    assert p.get("actenvcarl", "action_dims") == "100, 50, 1" and p.get("actenvcarl", "act_fixed") is False
+    assert t.getint("trainer", "batch_size") == 100 and t.getint("train", "capacity") == 100000
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from aemcarl_b200._lib import AemError
+    from aemcarl_b200.engine import Engine
+    with pytest.raises(AemError, match="no CPU fallback"):
+        Engine(0)

@@ -1,0 +1,111 @@
+"""CPU: the oracle (oracle/aem_oracle.c) is pinned against golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py).  ORCA outputs inside the fixtures come from our own restatement behind the rvo2 stub
+(parity unpinned at that boundary, see test_orca_properties.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from aemcarl_b200 import weights as wts
+
+DECISIONS = ["circle5", "circle5_mixed", "circle5_visible", "square10", "circle18"]
+
+
+def test_action_table_bit_exact(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "action_rotate.npz"))
+    assert np.array_equal(oracle.build_action_space(1.0), g["actions"])
+    assert abs(float(g["gamma_bar"]) - 0.9791483623609768) < 1e-16
+    assert np.allclose(g["speeds"], [0.12885124808584156, 0.2862305178902687, 0.47845399210662953,
+                                     0.7132362736976232, 1.0], rtol=0, atol=1e-16)
+
+
+def test_rotate_matches_reference(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "action_rotate.npz"))
+    out = oracle.rotate(g["rotate_in"])
+    assert np.abs(out - g["rotate_out"]).max() <= 4e-6          # FP32 trig of two libms
+
+
+@pytest.mark.parametrize("tag", ["readme", "config"])
+def test_occupancy_reward_matches_reference(oracle, golden_dir, actions, tag):
+    g = np.load(os.path.join(golden_dir, "reward_map.npz"))
+    ats, hts, pv, dv = g[tag + "_params"]
+    worst, nonzero = 0.0, 0
+    for t in range(len(g[tag + "_robot"])):
+        n = int(g[tag + "_n"][t])
+        hs = g[tag + "_humans"][t][:n]
+        rp = g[tag + "_robot"][t]
+        for ai in range(0, 81, 2):
+            a = actions[ai]
+            p = oracle.occupancy(hs, rp[0] + a[0] * ats, rp[1] + a[1] * ats, 0.3, hts, pv, dv)
+            ref = g[tag + "_prob"][t][ai]
+            worst = max(worst, abs(p - ref))
+            nonzero += ref > 0
+    assert worst <= 1e-13 and nonzero > 300
+
+
+@pytest.mark.parametrize("tag", DECISIONS)
+def test_full_decision_pipeline_matches_reference(oracle, golden_dir, actions, tag):
+    """robot/human states recorded while the reference played episodes -> rewards, info, next states, network
+    values, ACT step counts and argmax of the reference's own predict()"""
+    g = np.load(os.path.join(golden_dir, "decisions_%s.npz" % tag))
+    pb = float(g["ponder_bias"])
+    W = wts.synthetic_weights(int(g["weight_seed"]), None if np.isnan(pb) else pb)
+    params = oracle.default_params(robot_visible=int(g["robot_visible"]))
+    nv = oracle.orca(g["humans"], g["robot"], params)
+    rew, info, dmin, hnext = oracle.env_lookahead(g["robot"], g["humans"], nv, g["global_time"], actions, params)
+    assert np.array_equal(hnext, g["humans_next"])
+    assert np.array_equal(info, g["infos"])
+    assert np.abs(rew - g["rewards"]).max() <= 1e-13
+    vals, net, best, steps = oracle.lookahead(W, g["robot"], g["humans_next"], g["rewards"], actions, nthreads=8)
+    rel = np.abs(net - g["net_values"]) / np.maximum(np.abs(g["net_values"]), 1e-2)
+    assert rel.max() <= 2e-5, rel.max()
+    assert np.array_equal(steps, g["act_steps"])
+    assert np.array_equal(best, g["best"])
+    assert np.abs(vals - g["values"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("tag", ["circle5", "square10", "circle18"])
+def test_act_halting_counts_match_reference(oracle, golden_dir, actions, tag):
+    g = np.load(os.path.join(golden_dir, "values_%s.npz" % tag))
+    seen = set()
+    for wname in ("k1", "k2", "k3", "mixed"):
+        pb = float(g["ponder_bias_" + wname])
+        W = wts.synthetic_weights(int(g["seed_" + wname]), None if np.isnan(pb) else pb)
+        R = g["robot"].shape[0]
+        vals, net, best, steps = oracle.lookahead(W, g["robot"], g["humans_next"], np.zeros((R, 81)), actions,
+                                                  gamma_bar=1.0, nthreads=8)
+        ref = g["net_values_" + wname]
+        assert (np.abs(net - ref) / np.maximum(np.abs(ref), 1e-2)).max() <= 2e-5
+        assert np.array_equal(steps, g["act_steps_" + wname])
+        seen |= set(np.unique(steps).tolist())
+    assert seen == {1, 2, 3}
+
+
+def test_episode_replay_matches_reference(oracle, golden_dir, actions):
+    """Re-play the reference's recorded episodes with the oracle pipeline: same action at every step, same outcome."""
+    g = np.load(os.path.join(golden_dir, "decisions_circle5.npz"))
+    from aemcarl_b200 import scenarios
+    W = wts.synthetic_weights(int(g["weight_seed"]), None)
+    params = oracle.default_params()
+    gbar = pow(0.9, 0.2)
+    for case in g["cases"][:2]:
+        ref_actions = g["actions_case%d" % case]
+        outcome, nsteps = g["outcome_case%d" % case]
+        rb, hs = scenarios.generate_case("test", int(case), 5, "circle_crossing")
+        robot, humans, gt = rb[None].copy(), hs[None].copy(), np.zeros(1)
+        mismatch, code = 0, -1
+        for step in range(int(nsteps)):
+            nv = oracle.orca(humans, robot, params)
+            rew, info, dmin, hnext = oracle.env_lookahead(robot, humans, nv, gt, actions, params)
+            vals, net, best, steps = oracle.lookahead(W, robot, hnext, rew, actions, gamma_bar=gbar, nthreads=8)
+            if best[0] != ref_actions[step]:
+                v = vals[0]
+                assert abs(v[best[0]] - v[ref_actions[step]]) <= 1e-6 * max(abs(v[best[0]]), 1e-3)
+                mismatch += 1
+            chosen = np.array([ref_actions[step]], dtype=np.int32)
+            code = info[0, chosen[0]]
+            oracle.env_apply(robot, humans, nv, gt, actions, chosen, params)
+            if code >= 2:
+                break
+        assert code == outcome and step + 1 == nsteps
+        assert mismatch <= 1
