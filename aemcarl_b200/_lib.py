@@ -52,6 +52,7 @@ SYMBOLS = {
     "aem_set_action_space": (ctypes.c_int, [_VP, _VP, ctypes.c_int]),
     "aem_set_env_params": (ctypes.c_int, [_VP, ctypes.POINTER(EnvParams)]),
     "aem_set_act_mode": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int]),
+    "aem_set_precision": (ctypes.c_int, [_VP, ctypes.c_int]),
     "aem_orca": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),
     "aem_env_lookahead": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 9),
     "aem_lookahead": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, ctypes.c_double] + [_VP] * 5),

@@ -19,6 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 # orca.cu: every FP32 op individually rounded (bit parity with the oracle); see the file header
 SOURCES = {
     "lookahead.cu": [],
+    "lookahead_tc.cu": [],
     "env.cu": ["-fmad=false"],   # FP64 env arithmetic is a sequence of individually rounded Python float ops
     "orca.cu": ["-fmad=false"],
     "capi.cu": [],
@@ -41,7 +42,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "aem_common.cuh"), os.path.join(HERE, "..", "include", "aemcarl_b200.h"),
+    headers = [os.path.join(CSRC, "aem_common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(HERE, "..", "include", "aemcarl_b200.h"),
                os.path.abspath(__file__)]
     objs = []
     for src, extra in SOURCES.items():

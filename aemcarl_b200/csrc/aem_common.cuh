@@ -56,6 +56,15 @@ static_assert(ENC_SIZE == 25600, "encoder layer size");
 constexpr int NGROUPS = 16;
 constexpr int pad4(int x) { return (x + 3) & ~3; }
 
+// ---- tensor-core path (lookahead_tc.cu): one entry per tcgen05 GEMM ----
+// images: img[k/4][n][4] floats (canonical K-major no-swizzle UMMA layout), hi part and lo part, N and K permuted /
+// padded as capi.cu pack_tc documents.
+struct TcLayer { int off_hi, off_lo, bytes, N, ksteps, bias_off; };
+enum { TL_Z1S = 0, TL_QS = 1, TL_Z1 = 2, TL_Z2 = 3, TL_R1 = 4, TL_R2 = 5, TL_Q = 6,
+       TL_ENC = 7,      // + 7 * l : INA, INB, OUT, F1A, F1B, F2A, F2B
+       TL_A0 = 28, TL_A2 = 29, TL_NUM = 30 };
+constexpr int TC_PBLK_FLOATS = 3200;
+
 struct NetParams {
     const float *raw;      // raw blob (biases, LayerNorm, ponder, last action layer)
     const float *packed;   // packed GEMM operands
@@ -63,6 +72,11 @@ struct NetParams {
     int off_in[3], off_out[3], off_f1[3], off_f2[3];
     int off_a0, off_a2;
     int act_fixed, act_steps;
+    // tensor-core path
+    const float *tc_img;   // weight images
+    const float *tc_pblk;  // permuted biases, LayerNorm, ponder and last-layer parameters
+    int tc_pblk_floats, tc_pb_ln, tc_pb_pw, tc_pb_a4;
+    TcLayer tc_layers[TL_NUM];
 };
 
 // tile sizes of the packed layers (shared by the host packer and the kernel)
@@ -81,6 +95,9 @@ struct aem_handle_s {
     float *raw_d;        // [NUM_WEIGHTS]
     float *packed_d;
     size_t packed_floats;
+    float *tc_img_d, *tc_pblk_d;
+    size_t tc_img_floats;
+    int precision;       // 0 = FP32 FFMA kernel, 1 = tcgen05 3xTF32 kernel
     aem::NetParams net;
     bool weights_set, actions_set, params_set;
     double *actions_d;   // [A][2]
@@ -109,6 +126,7 @@ int aem_set_error(int code, const char *msg);
 namespace aem {
 struct LookaheadArgs;
 cudaError_t launch_lookahead(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
+cudaError_t launch_lookahead_tc(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
 cudaError_t launch_select(const double *values, const double *robot, int B, int A, int32_t *best, cudaStream_t st);
 cudaError_t launch_orca(int B, int n, const double *humans, const double *robot, const aem_env_params &p,
                         double *new_vel, cudaStream_t st);

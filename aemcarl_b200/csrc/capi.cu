@@ -53,6 +53,97 @@ void pack_two(std::vector<float> &dst, const float *W0, const float *W1, int N, 
             }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// tensor-core images (lookahead_tc.cu).  For every GEMM: W_perm[c][k] = W[out_map(c)][in_map(k)] (0 where a map
+// returns -1), split into hi = round-to-nearest TF32 and lo = w - hi, and laid out as img[k/4][c][k%4].
+// Thread `half` (0/1) of a token row owns one contiguous block of the permuted columns.
+// ---------------------------------------------------------------------------------------------------------
+float tf32_rna_host(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u += 0x1000u;
+    u &= 0xffffe000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+// output maps (c -> real output index)
+int out50(int c) { int h = c / 32, j = c % 32; return j < 25 ? 25 * h + j : -1; }            // N_pad 64
+int out100(int c) { int h = c / 56, j = c % 56; return j < 50 ? 50 * h + j : -1; }           // N_pad 112
+int unit75(int h, int j) { return h == 0 ? (j < 37 ? j : -1) : (j < 38 ? 37 + j : -1); }      // 75 hidden units -> 40 | 40
+// input maps (k -> real input index)
+int in_hx(int k)    // A1 / A3 layout [h0(25) x0..6 | h1(25) x7..12 0] -> index into [h(50) ; x(13)]
+{
+    int h = k / 32, j = k % 32;
+    if (j < 25) return 25 * h + j;
+    int xi = 7 * h + (j - 25);
+    return (xi < 13 && !(h == 1 && j == 31)) ? 50 + xi : -1;
+}
+int in100(int k) { int h = k / 52, j = k % 52; return j < 50 ? 50 * h + j : -1; }            // K_pad 104
+int in50(int k) { int h = k / 28, j = k % 28; return j < 25 ? 25 * h + j : -1; }             // K_pad 56
+int in_joint(int k) { int h = k / 28, j = k % 28; return j < 25 ? 6 + 25 * h + j : 3 * h + (j - 25); }
+
+struct TcPack {
+    std::vector<float> img, pblk;
+    aem::TcLayer layers[aem::TL_NUM];
+    template <class OM, class IM>
+    void add(int id, const float *W, int in_dim, const float *bias, int N, int K, OM om, IM im)
+    {
+        aem::TcLayer &L = layers[id];
+        L.N = N; L.ksteps = K / 8; L.bytes = N * K * 4;
+        L.off_hi = (int)img.size();
+        img.resize(img.size() + (size_t)2 * N * K, 0.0f);
+        L.off_lo = L.off_hi + N * K;
+        for (int c = 0; c < N; ++c)
+            for (int k = 0; k < K; ++k) {
+                const int o = om(c), i = im(k);
+                const float w = (o >= 0 && i >= 0) ? W[(size_t)o * in_dim + i] : 0.0f;
+                const float hi = tf32_rna_host(w);
+                const size_t at = ((size_t)(k / 4) * N + c) * 4 + (k % 4);
+                img[L.off_hi + at] = hi;
+                img[L.off_lo + at] = w - hi;
+            }
+        L.bias_off = (int)pblk.size();
+        for (int c = 0; c < N; ++c) {
+            const int o = om(c);
+            pblk.push_back((o >= 0 && bias) ? bias[o] : 0.0f);
+        }
+    }
+};
+
+void pack_tc(const float *w, TcPack &P)
+{
+    using namespace aem;
+    auto step1 = [](int k) { return in_hx(k < 8 ? 24 + k : 56 + (k - 8)); };   // A1 columns {24..31, 56..63}
+    P.add(TL_Z1S, w + OFF_Z1W, HXD, w + OFF_Z1B, 112, 16, out100, step1);
+    P.add(TL_QS, w + OFF_QW, HXD, w + OFF_QB, 64, 16, out50, step1);
+    P.add(TL_Z1, w + OFF_Z1W, HXD, w + OFF_Z1B, 112, 64, out100, in_hx);
+    P.add(TL_Z2, w + OFF_Z2W, 100, w + OFF_Z2B, 64, 104, out50, in100);
+    P.add(TL_R1, w + OFF_R1W, HXD, w + OFF_R1B, 112, 64, out100, in_hx);
+    P.add(TL_R2, w + OFF_R2W, 100, w + OFF_R2B, 64, 104, out50, in100);
+    P.add(TL_Q, w + OFF_QW, HXD, w + OFF_QB, 64, 64, out50, in_hx);
+    for (int l = 0; l < 3; ++l) {
+        const float *E = w + OFF_ENC + l * ENC_SIZE;
+        const int LB = TL_ENC + 7 * l;
+        for (int hd = 0; hd < 2; ++hd)       // in_proj per head: columns [q(25+7) | k(25+7) | v(25+7)]
+            P.add(LB + hd, E + ENC_INW, HID, E + ENC_INB, 96, 56,
+                  [hd](int c) { int s = c / 32, j = c % 32; return j < 25 ? s * 50 + 25 * hd + j : -1; }, in50);
+        P.add(LB + 2, E + ENC_OW, HID, E + ENC_OB, 64, 56, out50, in50);
+        for (int ch = 0; ch < 2; ++ch)       // linear1 in two chunks of 75 hidden units
+            P.add(LB + 3 + ch, E + ENC_L1W, HID, E + ENC_L1B, 80, 56,
+                  [ch](int c) { int u = unit75(c / 40, c % 40); return u >= 0 ? 75 * ch + u : -1; }, in50);
+        for (int ch = 0; ch < 2; ++ch)       // linear2 accumulated over the two chunks; bias applied once (chunk b)
+            P.add(LB + 5 + ch, E + ENC_L2W, 150, ch == 1 ? E + ENC_L2B : nullptr, 64, 80, out50,
+                  [ch](int k) { int u = unit75(k / 40, k % 40); return u >= 0 ? 75 * ch + u : -1; });
+    }
+    P.add(TL_A0, w + OFF_A0W, 56, w + OFF_A0B, 112, 56, out100, in_joint);
+    P.add(TL_A2, w + OFF_A2W, 100, w + OFF_A2B, 64, 104, out50, in100);
+}
+
 cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int check_ready(aem_handle h, bool need_weights, bool need_env)
@@ -116,7 +207,7 @@ int aem_destroy(aem_handle h)
 {
     if (!h) return AEM_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->raw_d); cudaFree(h->packed_d); cudaFree(h->actions_d); cudaFree(h->lut_d);
+    cudaFree(h->raw_d); cudaFree(h->packed_d); cudaFree(h->tc_img_d); cudaFree(h->tc_pblk_d); cudaFree(h->actions_d); cudaFree(h->lut_d);
     cudaFree(h->s_robot); cudaFree(h->s_humans); cudaFree(h->s_time); cudaFree(h->s_newvel);
     cudaFree(h->s_rewards); cudaFree(h->s_dmin); cudaFree(h->s_hnext); cudaFree(h->s_values);
     cudaFree(h->s_oreward); cudaFree(h->s_info); cudaFree(h->s_best); cudaFree(h->s_odone); cudaFree(h->s_oinfo);
@@ -155,6 +246,34 @@ int aem_load_weights(aem_handle h, const float *w, size_t count)
     AEM_CUDA_CHECK(cudaMemcpy(h->packed_d, pk.data(), sizeof(float) * pk.size(), cudaMemcpyHostToDevice));
     net.raw = h->raw_d;
     net.packed = h->packed_d;
+    {   // tensor-core images + parameter block
+        TcPack P;
+        pack_tc(w, P);
+        net.tc_pb_ln = (int)P.pblk.size();
+        for (int l = 0; l < 3; ++l) {
+            const float *E = w + OFF_ENC + l * ENC_SIZE;
+            P.pblk.insert(P.pblk.end(), E + ENC_N1G, E + ENC_N1G + 200);    // n1g n1b n2g n2b are contiguous
+        }
+        net.tc_pb_pw = (int)P.pblk.size();
+        P.pblk.insert(P.pblk.end(), w + OFF_PW, w + OFF_PW + 51);           // ponder weight (50) + bias
+        net.tc_pb_a4 = (int)P.pblk.size();
+        P.pblk.insert(P.pblk.end(), w + OFF_A4W, w + OFF_A4W + 51);         // last action layer (50) + bias
+        while (P.pblk.size() % 4) P.pblk.push_back(0.0f);
+        if (P.pblk.size() > (size_t)TC_PBLK_FLOATS) return aem_set_error(AEM_ERR_INVALID, "tc parameter block too large");
+        if (P.img.size() > h->tc_img_floats) {
+            cudaFree(h->tc_img_d);
+            h->tc_img_d = nullptr;
+            AEM_CUDA_CHECK(cudaMalloc(&h->tc_img_d, sizeof(float) * P.img.size()));
+            h->tc_img_floats = P.img.size();
+        }
+        if (!h->tc_pblk_d) AEM_CUDA_CHECK(cudaMalloc(&h->tc_pblk_d, sizeof(float) * TC_PBLK_FLOATS));
+        AEM_CUDA_CHECK(cudaMemcpy(h->tc_img_d, P.img.data(), sizeof(float) * P.img.size(), cudaMemcpyHostToDevice));
+        AEM_CUDA_CHECK(cudaMemcpy(h->tc_pblk_d, P.pblk.data(), sizeof(float) * P.pblk.size(), cudaMemcpyHostToDevice));
+        net.tc_img = h->tc_img_d;
+        net.tc_pblk = h->tc_pblk_d;
+        net.tc_pblk_floats = (int)P.pblk.size();
+        for (int i = 0; i < TL_NUM; ++i) net.tc_layers[i] = P.layers[i];
+    }
     h->weights_set = true;
     return AEM_OK;
 }
@@ -188,6 +307,14 @@ int aem_set_act_mode(aem_handle h, int act_fixed, int act_steps)
     if (act_fixed && act_steps < 1) return aem_set_error(AEM_ERR_INVALID, "act_steps must be >= 1");
     h->net.act_fixed = act_fixed ? 1 : 0;
     h->net.act_steps = act_steps;
+    return AEM_OK;
+}
+
+int aem_set_precision(aem_handle h, int precision)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (precision != 0 && precision != 1) return aem_set_error(AEM_ERR_INVALID, "precision must be 0 (fp32) or 1 (tf32x3)");
+    h->precision = precision;
     return AEM_OK;
 }
 
@@ -245,7 +372,7 @@ int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const doubl
     a.gamma_bar = gamma_bar;
     a.robot = robot_d; a.humans_next = humans_next_d; a.actions = h->actions_d; a.rewards = rewards_d;
     a.values = values_d; a.net_values = net_values_d; a.steps = act_steps_d;
-    AEM_CUDA_CHECK(launch_lookahead(h, a, as_stream(stream)));
+    AEM_CUDA_CHECK(h->precision ? launch_lookahead_tc(h, a, as_stream(stream)) : launch_lookahead(h, a, as_stream(stream)));
     AEM_CUDA_CHECK(launch_select(values_d, robot_d, B, h->A, best_d, as_stream(stream)));
     h->launches += 2 * (B > 0);
     return AEM_OK;
@@ -303,7 +430,7 @@ int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *
     a.total_samples = S;
     a.states = states_d;
     a.net_values = values_d; a.steps = steps_d;
-    AEM_CUDA_CHECK(launch_lookahead(h, a, as_stream(stream)));
+    AEM_CUDA_CHECK(h->precision ? launch_lookahead_tc(h, a, as_stream(stream)) : launch_lookahead(h, a, as_stream(stream)));
     h->launches += (S > 0);
     return AEM_OK;
 }
@@ -325,7 +452,7 @@ int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint
     a.total_samples = S;
     a.states = x_d;
     a.gru_out = out_d; a.steps = steps_d;
-    AEM_CUDA_CHECK(launch_lookahead(h, a, as_stream(stream)));
+    AEM_CUDA_CHECK(h->precision ? launch_lookahead_tc(h, a, as_stream(stream)) : launch_lookahead(h, a, as_stream(stream)));
     h->launches += (S > 0);
     return AEM_OK;
 }

@@ -68,6 +68,12 @@ class Engine:
     def set_act_mode(self, act_fixed, act_steps):
         check(self.lib.aem_set_act_mode(self.h, int(bool(act_fixed)), int(act_steps)))
 
+    def set_precision(self, precision):
+        """'fp32' (FFMA kernel, default) or 'tf32x3' (tcgen05 tensor-core kernel)"""
+        mode = {"fp32": 0, "tf32x3": 1, 0: 0, 1: 1}[precision]
+        check(self.lib.aem_set_precision(self.h, mode))
+        self.precision = mode
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

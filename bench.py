@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--humans", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-envs", type=int, default=256, help="--impl reference: envs per step (bounded sample)")
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3"],
+                    help="value-network GEMM arithmetic: tcgen05 3xTF32 (default) or the FP32 FFMA kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -198,6 +200,7 @@ def main():
     eng.set_env_params(make_env_params())
     W = wts.synthetic_weights(0)
     eng.load_weights(W)
+    eng.set_precision(args.precision)
     env = VecCrowdSim(eng, B, n, "circle_crossing", "train", first_case=rank * B, pool_size=B,
                       case_stride=world * B)
     gbar = env.gamma_bar()
@@ -273,7 +276,9 @@ def main():
                 "traffic": traffic, "kernel": "lookahead_kernel", "kernel_ms": kernel_ms,
                 "kernel_share_of_step": float(look_ms.sum() / step_ms.sum()),
                 "peak_source": "bf16_tflops_sustained of %s MEASURED_PEAKS.json" % peak_kind,
-                "pipe": "fp32_ffma (FP32-exact parity path, no tensor-core math)",
+                "pipe": ("tcgen05 kind::tf32, 3xTF32 split (3 MMAs per product, FP32 accumulate in TMEM)"
+                         if args.precision == "tf32x3" else "fp32_ffma (no tensor-core math)"),
+                "kernel_variant": "lookahead_tc_kernel" if args.precision == "tf32x3" else "lookahead_kernel",
                 "fp32_pipe_peak_tflops": fp32_peak, "frac_fp32_pipe": achieved / fp32_peak,
                 "algorithmic_flops_per_launch": flops, "act_steps_hist": hist}
 
@@ -314,7 +319,9 @@ def main():
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "scaling": "weak", "vs_baseline": None,
+               "dtype": "tf32x3 (fp32-equivalent split, fp32 accumulate)" if args.precision == "tf32x3" else "f32",
+               "data": "synthetic",
                "config": {"workload": "batched lookahead inference: %d envs x %d humans x 81 actions per GPU, "
                                       "random-init weights (synthetic_weights seed 0), circle_crossing train-stream "
                                       "scenarios, predict + step" % (B, n),

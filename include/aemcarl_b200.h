@@ -91,6 +91,11 @@ int aem_set_env_params(aem_handle h, const aem_env_params *p);
 /* ATCBasic act_fixed / act_steps (components.py:119-123); default adaptive (act_fixed = 0). */
 int aem_set_act_mode(aem_handle h, int act_fixed, int act_steps);
 
+/* Arithmetic of the value-network GEMMs inside aem_lookahead / aem_value_forward / aem_gru_act:
+ *   0 = FP32 FFMA (k-ascending accumulation, the order of the CPU oracle)            [default]
+ *   1 = tcgen05 tensor cores, 3xTF32 split with FP32 accumulation in tensor memory (~1e-6 relative of mode 0). */
+int aem_set_precision(aem_handle h, int precision);
+
 /* ---- device-pointer entry points ---- */
 int aem_orca(aem_handle h, int B, int n, const double *humans_d, const double *robot_d, double *new_vel_d,
              void *stream);

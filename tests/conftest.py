@@ -32,8 +32,8 @@ def actions():
     return np.load(os.path.join(GOLDEN, "action_rotate.npz"))["actions"]
 
 
-@pytest.fixture(scope="session")
-def engine(actions):
+@pytest.fixture(scope="session", params=["fp32", "tf32x3"])
+def engine(actions, request):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -41,4 +41,6 @@ def engine(actions):
     eng = Engine(0)
     eng.set_action_space(actions)
     eng.set_env_params(make_env_params())
+    eng.set_precision(request.param)
+    eng.precision_name = request.param
     return eng
