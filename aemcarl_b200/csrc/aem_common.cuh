@@ -76,7 +76,7 @@ struct NetParams {
     const float *tc_img;   // weight images
     const float *tc_pblk;  // permuted biases, LayerNorm, ponder and last-layer parameters
     int tc_pblk_floats, tc_pb_ln, tc_pb_pw, tc_pb_a4;
-    TcLayer tc_layers[TL_NUM];
+    const TcLayer *tc_layers_d;   // [TL_NUM] in global memory
 };
 
 // tile sizes of the packed layers (shared by the host packer and the kernel)
@@ -96,6 +96,7 @@ struct aem_handle_s {
     float *packed_d;
     size_t packed_floats;
     float *tc_img_d, *tc_pblk_d;
+    aem::TcLayer *tc_layers_d;
     size_t tc_img_floats;
     int precision;       // 0 = FP32 FFMA kernel, 1 = tcgen05 3xTF32 kernel
     aem::NetParams net;

@@ -207,7 +207,7 @@ int aem_destroy(aem_handle h)
 {
     if (!h) return AEM_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->raw_d); cudaFree(h->packed_d); cudaFree(h->tc_img_d); cudaFree(h->tc_pblk_d); cudaFree(h->actions_d); cudaFree(h->lut_d);
+    cudaFree(h->raw_d); cudaFree(h->packed_d); cudaFree(h->tc_img_d); cudaFree(h->tc_pblk_d); cudaFree(h->tc_layers_d); cudaFree(h->actions_d); cudaFree(h->lut_d);
     cudaFree(h->s_robot); cudaFree(h->s_humans); cudaFree(h->s_time); cudaFree(h->s_newvel);
     cudaFree(h->s_rewards); cudaFree(h->s_dmin); cudaFree(h->s_hnext); cudaFree(h->s_values);
     cudaFree(h->s_oreward); cudaFree(h->s_info); cudaFree(h->s_best); cudaFree(h->s_odone); cudaFree(h->s_oinfo);
@@ -272,7 +272,9 @@ int aem_load_weights(aem_handle h, const float *w, size_t count)
         net.tc_img = h->tc_img_d;
         net.tc_pblk = h->tc_pblk_d;
         net.tc_pblk_floats = (int)P.pblk.size();
-        for (int i = 0; i < TL_NUM; ++i) net.tc_layers[i] = P.layers[i];
+        if (!h->tc_layers_d) AEM_CUDA_CHECK(cudaMalloc(&h->tc_layers_d, sizeof(TcLayer) * TL_NUM));
+        AEM_CUDA_CHECK(cudaMemcpy(h->tc_layers_d, P.layers, sizeof(TcLayer) * TL_NUM, cudaMemcpyHostToDevice));
+        net.tc_layers_d = h->tc_layers_d;
     }
     h->weights_set = true;
     return AEM_OK;

@@ -22,7 +22,7 @@ namespace tc {
 
 using namespace aemtc;
 
-constexpr int NT = 288;                 // 8 epilogue warps + 1 issuer warp
+constexpr int NT = 256;                 // 8 warps: two threads per token row; thread 0 also issues TMA + MMA
 constexpr int NBUF = 5;                 // weight ring
 constexpr int WBUF_BYTES = 29696;       // >= largest image (Z1: 112 x 64 x 4 = 28672)
 constexpr int KV_PITCH = 101;
@@ -87,6 +87,32 @@ __device__ __forceinline__ void ld_cols(uint32_t addr, float *v)
     tmem_wait_ld();
 }
 
+// streaming epilogue: out[c] = ReLU(D[c] + bias[c]) for NV columns (multiple of 4), written as the hi / lo parts of the
+// next A operand.  A rolled loop over 8-column chunks keeps the instruction footprint small.
+template <int NV>
+__device__ __forceinline__ void relu_stream(uint32_t d_addr, const float *__restrict__ bias, uint32_t hi_addr,
+                                            uint32_t lo_addr)
+{
+#pragma unroll 1
+    for (int c = 0; c + 8 <= NV; c += 8) {
+        float v[8];
+        ld8f(d_addr + c, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + bias[c + j], 0.0f);
+        st8_split(hi_addr + c, lo_addr + c, v);
+    }
+    if (NV % 8) {
+        constexpr int c = NV & ~7;
+        float v[8];
+        ld8f(d_addr + c, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j] + bias[c + j], 0.0f);
+        st4_split(hi_addr + c, lo_addr + c, v);
+    }
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ void rotate13(const float *s, float *o)   // cadrl.py:239-274, see lookahead.cu
@@ -132,7 +158,7 @@ struct Issuer {
         if (st == 1) return idx == 0 ? TL_Z1 : (idx == 1 ? TL_Z2 : (idx == 2 ? TL_R1 : (idx == 3 ? TL_R2 : TL_Q)));
         return idx < 21 ? TL_ENC + idx : (idx == 21 ? TL_A0 : TL_A2);
     }
-    __device__ __forceinline__ void prefetch()
+    __device__ __noinline__ void prefetch()
     {
         while (pf_stage >= 0 && nloaded - nfree < NBUF) {
             const TcLayer &L = layers[layer_at(pf_stage, pf_idx)];
@@ -158,7 +184,7 @@ struct Issuer {
     {
         if (pf_stage == -1) { pf_stage = next_stage; pf_idx = 0; pf_part = 0; }
     }
-    __device__ __forceinline__ const float *take_chunk()
+    __device__ __noinline__ const float *take_chunk()
     {
         while (nloaded <= nused) prefetch();
         const int buf = nused % NBUF;
@@ -167,7 +193,7 @@ struct Issuer {
         return reinterpret_cast<const float *>(wbuf + (size_t)buf * WBUF_BYTES);
     }
     // D[d] (+)= A * W^T for one layer, 3 passes.  special: the step-1 images consume A columns {24..31, 56..63}.
-    __device__ __forceinline__ void issue(int layer, uint32_t a_hi, uint32_t a_lo, uint32_t d, bool special,
+    __device__ __noinline__ void issue(int layer, uint32_t a_hi, uint32_t a_lo, uint32_t d, bool special,
                                           bool accumulate)
     {
         const TcLayer &L = layers[layer];
@@ -193,6 +219,54 @@ struct Issuer {
     }
 };
 
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __noinline__ uint32_t take_chunk_addr(Issuer *iss)
+{
+    return smem_u32(iss->take_chunk());
+}
+
+// Warp-uniform MMA issue of one layer (all 32 lanes of warp 0 execute it, one elected lane issues): N and the number
+// of k-steps are compile-time, so every descriptor is base + constant and the loop is fully unrolled -- the single-thread
+// issue rate, not the tensor pipe, was the bottleneck of the first version (profiles/r01_lookahead_tc_ncu.md).
+template <int N, int KS>
+__device__ __forceinline__ void issue_t(Issuer *iss, int lane, uint32_t tm, uint32_t a_hi, uint32_t a_lo, uint32_t d,
+                                        bool special, bool accumulate)
+{
+    constexpr uint32_t LBO = (uint32_t)N * 16;
+    constexpr uint64_t DHI = ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t wa = 0;
+    if (lane == 0) wa = take_chunk_addr(iss);
+    wa = __shfl_sync(0xffffffffu, wa, 0);
+    uint32_t base = (wa & 0x3FFFFu) >> 4;
+    const bool leader = elect_one();
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t acol = special ? (ks == 0 ? 24u : 56u) : (uint32_t)(8 * ks);
+        const uint64_t bd = DHI | (uint64_t)(base + ks * ((2 * LBO) >> 4));
+        if (leader) {
+            mma_tf32_ts(tm + d, tm + a_hi + acol, bd, IDESC, (ks == 0 && !accumulate) ? 0u : 1u);
+            mma_tf32_ts(tm + d, tm + a_lo + acol, bd, IDESC, 1u);
+        }
+    }
+    wa = 0;
+    if (lane == 0) wa = take_chunk_addr(iss);
+    wa = __shfl_sync(0xffffffffu, wa, 0);
+    base = (wa & 0x3FFFFu) >> 4;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t acol = special ? (ks == 0 ? 24u : 56u) : (uint32_t)(8 * ks);
+        const uint64_t bd = DHI | (uint64_t)(base + ks * ((2 * LBO) >> 4));
+        if (leader) mma_tf32_ts(tm + d, tm + a_hi + acol, bd, IDESC, 1u);
+    }
+}
+
 __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs args)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -211,8 +285,8 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
 
     const NetParams &net = args.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_issuer_warp = (warp == 8);
-    const bool is_issuer = is_issuer_warp && lane == 0;
+    constexpr bool is_issuer_warp = false;   // no dedicated warp: thread 0 issues while the others wait anyway
+    const bool is_issuer = (tid == 0);
     const int half = (warp >> 2) & 1, q4 = warp & 3;
     const int row = q4 * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
@@ -224,30 +298,40 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
         for (int i = 0; i < NEV; ++i) mbar_init(&evb[i], 1);
         fence_mbar_init();
     }
-    if (is_issuer_warp) tmem_alloc(tmem_slot, 512);
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
     for (int i = tid; i < net.tc_pblk_floats; i += NT) pblk[i] = net.tc_pblk[i];
+    __shared__ TcLayer s_layers[TL_NUM];
+    if (tid < TL_NUM) s_layers[tid] = net.tc_layers_d[tid];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = *tmem_slot;
     const uint32_t tl = tm + lane_base;     // this thread's lane quarter
 
-    Issuer iss;
-    iss.tm = tm; iss.wbuf = wbuf; iss.wfull = wfull; iss.img = net.tc_img; iss.layers = net.tc_layers;
-    iss.nloaded = iss.nused = iss.nfree = 0;
-    iss.pf_stage = -2; iss.pf_idx = 0; iss.pf_part = 0; iss.tiles_left = 0;
-    if ((int)blockIdx.x < ntiles) {
-        iss.pf_stage = 0;
-        iss.tiles_left = (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x;
+    // issuer state lives in shared memory (thread 0 only): local memory would be an L2 round trip per access here,
+    // because 216 KB of the 228 KB L1/shared array are carved out as shared memory
+    __shared__ Issuer s_iss;
+    Issuer &iss = s_iss;
+    Issuer *iss_p = &s_iss;
+    if (tid == 0) {
+        iss.tm = tm; iss.wbuf = wbuf; iss.wfull = wfull; iss.img = net.tc_img; iss.layers = s_layers;
+        iss.nloaded = iss.nused = iss.nfree = 0;
+        iss.pf_stage = -2; iss.pf_idx = 0; iss.pf_part = 0; iss.tiles_left = 0;
+        if ((int)blockIdx.x < ntiles) {
+            iss.pf_stage = 0;
+            iss.tiles_left = (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x;
+        }
     }
+    __syncthreads();
     int nev = 0;     // commit events, counted identically by every thread
 
     // group barrier: every A operand written / every accumulator read before the issuer may launch the next MMAs
 #define GROUP_BARRIER()                                   \
     do {                                                  \
-        if (!is_issuer_warp) { tmem_wait_st(); tc_fence_before(); } \
+        tmem_wait_st();                                   \
+        tc_fence_before();                                \
         __syncthreads();                                  \
-        if (is_issuer) tc_fence_after();                  \
+        if (warp == 0) tc_fence_after();                  \
     } while (0)
 #define COMMIT(e) mma_commit(&evb[(e) % NEV])
 #define WAIT_EVENT(e)                                                   \
@@ -265,8 +349,9 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
     } while (0)
 
     const float *PB = pblk;
-    const TcLayer *LY = net.tc_layers;
+    const TcLayer *LY = s_layers;
 
+#pragma unroll 1
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int s0 = tile * S;
         const int nsamp = min(S, args.total_samples - s0);
@@ -314,7 +399,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
                     for (int k = 0; k < XD; ++k) o[k] = src[k];
                 }
 #pragma unroll
-                for (int i = 0; i < 3; ++i) selfs[i] = o[3 * half + i];   // self_state = first 6 features of human row 0
+                for (int i = 0; i < 3; ++i) selfs[i] = half ? o[3 + i] : o[i];   // self_state = first 6 features of human row 0
                 if (args.mode != 2 && tok == 0) {
                     o[6] = 0.0f; o[7] = 0.0f; o[8] = o[4]; o[9] = o[5]; o[10] = o[3]; o[11] = 0.0f; o[12] = o[3];
                 }
@@ -323,10 +408,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
                 for (int i = 0; i < 3; ++i) selfs[i] = 0.0f;
             }
 #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const int xi = 7 * half + i;
-                xh[i] = (xi < XD) ? o[xi < XD ? xi : 0] : 0.0f;
-            }
+            for (int i = 0; i < 7; ++i) xh[i] = half ? (i < 6 ? o[7 + (i < 6 ? i : 0)] : 0.0f) : o[i];
             {
                 float v[32];
 #pragma unroll
@@ -341,39 +423,40 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
 
         // ---------------- phase 1: GRU + adaptive computation time ----------------
         const int max_steps = net.act_fixed ? net.act_steps : 3;
+#pragma unroll 1
         for (int step = 1; step <= max_steps; ++step) {
             const bool kfull = step > 1;
             // ---- z1 = ReLU(W1z [h;x] + b)
             GROUP_BARRIER();
             const int e_z1 = nev++;
-            if (is_issuer) {
-                iss.issue(kfull ? TL_Z1 : TL_Z1S, A1H, A1L, D1, !kfull, false);
-                COMMIT(e_z1);
-                ISSUER_DRAIN(e_z1);
-            } else if (!is_issuer_warp) {
+            if (warp == 0) {
+                if (kfull) issue_t<112, 8>(iss_p, lane, tm, A1H, A1L, D1, false, false);
+                else issue_t<112, 2>(iss_p, lane, tm, A1H, A1L, D1, true, false);
+                if (lane == 0) { COMMIT(e_z1); ISSUER_DRAIN(e_z1); }
+            }
+            __syncwarp();
+            {
                 WAIT_EVENT(e_z1);
-                float v[56];
-                ld_cols<56>(tl + D1 + 56 * half, v);
-                const float *b = PB + LY[TL_Z1].bias_off + 56 * half;
-#pragma unroll
-                for (int j = 0; j < 52; ++j) v[j] = fmaxf(v[j] + b[j], 0.0f);
-                st_split<52>(tl + A2H + 52 * half, tl + A2L + 52 * half, v);
+                relu_stream<52>(tl + D1 + 56 * half, PB + LY[TL_Z1].bias_off + 56 * half, tl + A2H + 52 * half,
+                                tl + A2L + 52 * half);
             }
             // ---- z = sigmoid(ReLU(W2z z1 + b))   (+ r1 issued back to back: it only depends on A1)
             GROUP_BARRIER();
             const int e_z2 = nev++;
             const int e_r1 = kfull ? nev++ : -1;
-            if (is_issuer) {
-                iss.issue(TL_Z2, A2H, A2L, D2, false, false);
-                COMMIT(e_z2);
+            if (warp == 0) {
+                issue_t<64, 13>(iss_p, lane, tm, A2H, A2L, D2, false, false);
+                if (lane == 0) COMMIT(e_z2);
+                __syncwarp();
                 if (kfull) {
-                    iss.issue(TL_R1, A1H, A1L, D1, false, false);
-                    COMMIT(e_r1);
-                    ISSUER_DRAIN(e_r1);
+                    issue_t<112, 8>(iss_p, lane, tm, A1H, A1L, D1, false, false);
+                    if (lane == 0) { COMMIT(e_r1); ISSUER_DRAIN(e_r1); }
                 } else {
-                    ISSUER_DRAIN(e_z2);
+                    if (lane == 0) { ISSUER_DRAIN(e_z2); }
                 }
-            } else if (!is_issuer_warp) {
+            }
+            __syncwarp();
+            {
                 WAIT_EVENT(e_z2);
                 float v[32];
                 ld_cols<32>(tl + D2 + 32 * half, v);
@@ -385,20 +468,17 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
                 // ---- r1 -> A2, r = sigmoid(ReLU(W2r r1 + b)), [r*h ; x] -> A3
                 if (!is_issuer_warp) {
                     WAIT_EVENT(e_r1);
-                    float v[56];
-                    ld_cols<56>(tl + D1 + 56 * half, v);
-                    const float *b = PB + LY[TL_R1].bias_off + 56 * half;
-#pragma unroll
-                    for (int j = 0; j < 52; ++j) v[j] = fmaxf(v[j] + b[j], 0.0f);
-                    st_split<52>(tl + A2H + 52 * half, tl + A2L + 52 * half, v);
+                    relu_stream<52>(tl + D1 + 56 * half, PB + LY[TL_R1].bias_off + 56 * half, tl + A2H + 52 * half,
+                                    tl + A2L + 52 * half);
                 }
                 GROUP_BARRIER();
                 const int e_r2 = nev++;
-                if (is_issuer) {
-                    iss.issue(TL_R2, A2H, A2L, D2, false, false);
-                    COMMIT(e_r2);
-                    ISSUER_DRAIN(e_r2);
-                } else if (!is_issuer_warp) {
+                if (warp == 0) {
+                    issue_t<64, 13>(iss_p, lane, tm, A2H, A2L, D2, false, false);
+                    if (lane == 0) { COMMIT(e_r2); ISSUER_DRAIN(e_r2); }
+                }
+            __syncwarp();
+            {
                     WAIT_EVENT(e_r2);
                     float v[32], hh[32], hl[32];
                     ld_cols<32>(tl + D2 + 32 * half, v);
@@ -418,11 +498,13 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
             // ---- q = tanh(Wq [r*h ; x] + b);  h = (1 - z) h + z q
             GROUP_BARRIER();
             const int e_q = nev++;
-            if (is_issuer) {
-                iss.issue(kfull ? TL_Q : TL_QS, kfull ? A3H : A1H, kfull ? A3L : A1L, D2, !kfull, false);
-                COMMIT(e_q);
-                ISSUER_DRAIN(e_q);
-            } else if (!is_issuer_warp) {
+            if (warp == 0) {
+                if (kfull) issue_t<64, 8>(iss_p, lane, tm, A3H, A3L, D2, false, false);
+                else issue_t<64, 2>(iss_p, lane, tm, A1H, A1L, D2, true, false);
+                if (lane == 0) { COMMIT(e_q); ISSUER_DRAIN(e_q); }
+            }
+            __syncwarp();
+            {
                 WAIT_EVENT(e_q);
                 float v[32], hh[32], hl[32];
                 ld_cols<32>(tl + D2 + 32 * half, v);
@@ -444,7 +526,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
                 st_split<32>(tl + A1H + 32 * half, tl + A1L + 32 * half, v);
                 if (!net.act_fixed) {
                     sx[half * 128 + row] = pd;
-                    named_bar_sync(1, 256);
+                    __syncthreads();
                     const bool active = samp >= 0 && s_act[samp];
                     if (active) {
                         const float p = sigmoidf_(sx[row] + sx[128 + row] + PB[net.tc_pb_pw + 50]);
@@ -513,18 +595,20 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
         }
 
         // ---------------- phase 2: 3 x post-norm encoder layer ----------------
+#pragma unroll 1
         for (int l = 0; l < 3; ++l) {
             const int LB = TL_ENC + 7 * l;
             const float *LN = PB + net.tc_pb_ln + l * 200 + 25 * half;
             // ---- in_proj (one MMA per head) + attention
             GROUP_BARRIER();
             const int e_in = nev++;
-            if (is_issuer) {
-                iss.issue(LB + 0, AEH, AEL, DIN, false, false);
-                iss.issue(LB + 1, AEH, AEL, DIN + 96, false, false);
-                COMMIT(e_in);
-                ISSUER_DRAIN(e_in);
-            } else if (!is_issuer_warp) {
+            if (warp == 0) {
+                issue_t<96, 7>(iss_p, lane, tm, AEH, AEL, DIN, false, false);
+                issue_t<96, 7>(iss_p, lane, tm, AEH, AEL, DIN + 96, false, false);
+                if (lane == 0) { COMMIT(e_in); ISSUER_DRAIN(e_in); }
+            }
+            __syncwarp();
+            {
                 WAIT_EVENT(e_in);
                 float qh[32];
                 {
@@ -541,7 +625,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
                         dst[25 + j] = v[j] + b[64 + j];
                     }
                 }
-                named_bar_sync(1, 256);
+                __syncthreads();
                 float o[28];
 #pragma unroll
                 for (int j = 0; j < 28; ++j) o[j] = 0.0f;
@@ -575,11 +659,12 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
             // ---- out_proj + residual + LayerNorm1
             GROUP_BARRIER();
             const int e_out = nev++;
-            if (is_issuer) {
-                iss.issue(LB + 2, AATH, AATL, DOUT, false, false);
-                COMMIT(e_out);
-                ISSUER_DRAIN(e_out);
-            } else if (!is_issuer_warp) {
+            if (warp == 0) {
+                issue_t<64, 7>(iss_p, lane, tm, AATH, AATL, DOUT, false, false);
+                if (lane == 0) { COMMIT(e_out); ISSUER_DRAIN(e_out); }
+            }
+            __syncwarp();
+            {
                 WAIT_EVENT(e_out);
                 float v[32];
                 ld_cols<32>(tl + DOUT + 32 * half, v);
@@ -588,13 +673,13 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
 #pragma unroll
                 for (int j = 0; j < 25; ++j) { xres[j] += v[j] + b[j]; s += xres[j]; }
                 sx[half * 128 + row] = s;
-                named_bar_sync(1, 256);
+                __syncthreads();
                 const float mean = (sx[row] + sx[128 + row]) / 50.0f;
                 float ss = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 25; ++j) { xres[j] -= mean; ss = fmaf(xres[j], xres[j], ss); }
                 sx[256 + half * 128 + row] = ss;
-                named_bar_sync(1, 256);
+                __syncthreads();
                 const float rstd = 1.0f / sqrtf((sx[256 + row] + sx[384 + row]) / 50.0f + 1e-5f);
                 float a[28];
 #pragma unroll
@@ -606,40 +691,37 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
             GROUP_BARRIER();
             const int e_f1a = nev++;
             const int e_f1b = nev++;
-            if (is_issuer) {
-                iss.issue(LB + 3, AEH, AEL, DF1A, false, false);
-                COMMIT(e_f1a);
-                iss.issue(LB + 4, AEH, AEL, DF1B, false, false);
-                COMMIT(e_f1b);
-                ISSUER_DRAIN(e_f1b);
-            } else if (!is_issuer_warp) {
+            if (warp == 0) {
+                issue_t<80, 7>(iss_p, lane, tm, AEH, AEL, DF1A, false, false);
+                if (lane == 0) COMMIT(e_f1a);
+                __syncwarp();
+                issue_t<80, 7>(iss_p, lane, tm, AEH, AEL, DF1B, false, false);
+                if (lane == 0) { COMMIT(e_f1b); ISSUER_DRAIN(e_f1b); }
+            }
+            __syncwarp();
+            {
                 WAIT_EVENT(e_f1a);
-                float v[40];
-                ld_cols<40>(tl + DF1A + 40 * half, v);
-                const float *b = PB + LY[LB + 3].bias_off + 40 * half;
-#pragma unroll
-                for (int j = 0; j < 40; ++j) v[j] = fmaxf(v[j] + b[j], 0.0f);
-                st_split<40>(tl + AHAH + 40 * half, tl + AHAL + 40 * half, v);
+                relu_stream<40>(tl + DF1A + 40 * half, PB + LY[LB + 3].bias_off + 40 * half, tl + AHAH + 40 * half,
+                                tl + AHAL + 40 * half);
             }
             GROUP_BARRIER();
-            if (is_issuer) {
-                iss.issue(LB + 5, AHAH, AHAL, DF2, false, false);     // completes before f2b (in-order tensor pipe)
-            } else if (!is_issuer_warp) {
+            if (warp == 0) {
+                issue_t<64, 10>(iss_p, lane, tm, AHAH, AHAL, DF2, false, false);    // completes before f2b (in-order tensor pipe)
+            }
+            __syncwarp();
+            {
                 WAIT_EVENT(e_f1b);
-                float v[40];
-                ld_cols<40>(tl + DF1B + 40 * half, v);
-                const float *b = PB + LY[LB + 4].bias_off + 40 * half;
-#pragma unroll
-                for (int j = 0; j < 40; ++j) v[j] = fmaxf(v[j] + b[j], 0.0f);
-                st_split<40>(tl + AHBH + 40 * half, tl + AHBL + 40 * half, v);
+                relu_stream<40>(tl + DF1B + 40 * half, PB + LY[LB + 4].bias_off + 40 * half, tl + AHBH + 40 * half,
+                                tl + AHBL + 40 * half);
             }
             GROUP_BARRIER();
             const int e_f2 = nev++;
-            if (is_issuer) {
-                iss.issue(LB + 6, AHBH, AHBL, DF2, false, true);
-                COMMIT(e_f2);
-                ISSUER_DRAIN(e_f2);
-            } else if (!is_issuer_warp) {
+            if (warp == 0) {
+                issue_t<64, 10>(iss_p, lane, tm, AHBH, AHBL, DF2, false, true);
+                if (lane == 0) { COMMIT(e_f2); ISSUER_DRAIN(e_f2); }
+            }
+            __syncwarp();
+            {
                 WAIT_EVENT(e_f2);
                 float v[32];
                 ld_cols<32>(tl + DF2 + 32 * half, v);
@@ -648,13 +730,13 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
 #pragma unroll
                 for (int j = 0; j < 25; ++j) { xres[j] += v[j] + b[j]; s += xres[j]; }
                 sx[half * 128 + row] = s;
-                named_bar_sync(1, 256);
+                __syncthreads();
                 const float mean = (sx[row] + sx[128 + row]) / 50.0f;
                 float ss = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 25; ++j) { xres[j] -= mean; ss = fmaf(xres[j], xres[j], ss); }
                 sx[256 + half * 128 + row] = ss;
-                named_bar_sync(1, 256);
+                __syncthreads();
                 const float rstd = 1.0f / sqrtf((sx[256 + row] + sx[384 + row]) / 50.0f + 1e-5f);
                 float a[28];
 #pragma unroll
@@ -668,26 +750,24 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
         // ---------------- phase 3: action_mlp 56 -> 100 -> 50 -> 1 ----------------
         GROUP_BARRIER();
         const int e_a0 = nev++;
-        if (is_issuer) {
-            iss.issue(TL_A0, AEH, AEL, DA0, false, false);
-            COMMIT(e_a0);
-            ISSUER_DRAIN(e_a0);
-        } else if (!is_issuer_warp) {
+        if (warp == 0) {
+            issue_t<112, 7>(iss_p, lane, tm, AEH, AEL, DA0, false, false);
+            if (lane == 0) { COMMIT(e_a0); ISSUER_DRAIN(e_a0); }
+        }
+            __syncwarp();
+            {
             WAIT_EVENT(e_a0);
-            float v[56];
-            ld_cols<56>(tl + DA0 + 56 * half, v);
-            const float *b = PB + LY[TL_A0].bias_off + 56 * half;
-#pragma unroll
-            for (int j = 0; j < 52; ++j) v[j] = fmaxf(v[j] + b[j], 0.0f);
-            st_split<52>(tl + AJH + 52 * half, tl + AJL + 52 * half, v);
+            relu_stream<52>(tl + DA0 + 56 * half, PB + LY[TL_A0].bias_off + 56 * half, tl + AJH + 52 * half,
+                            tl + AJL + 52 * half);
         }
         GROUP_BARRIER();
         const int e_a2 = nev++;
-        if (is_issuer) {
-            iss.issue(TL_A2, AJH, AJL, DA2, false, false);
-            COMMIT(e_a2);
-            ISSUER_DRAIN(e_a2);
-        } else if (!is_issuer_warp) {
+        if (warp == 0) {
+            issue_t<64, 13>(iss_p, lane, tm, AJH, AJL, DA2, false, false);
+            if (lane == 0) { COMMIT(e_a2); ISSUER_DRAIN(e_a2); }
+        }
+            __syncwarp();
+            {
             WAIT_EVENT(e_a2);
             float v[32];
             ld_cols<32>(tl + DA2 + 32 * half, v);
@@ -697,7 +777,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
 #pragma unroll
             for (int j = 0; j < 25; ++j) pd = fmaf(fmaxf(v[j] + b[j], 0.0f), w4[j], pd);
             sx[half * 128 + row] = pd;
-            named_bar_sync(1, 256);
+            __syncthreads();
             if (half == 0 && samp >= 0 && tok == 0) {
                 const float val = sx[row] + sx[128 + row] + PB[net.tc_pb_a4 + 50];
                 const int gs = s0 + samp;
@@ -713,7 +793,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
     if (!is_issuer_warp) { tmem_wait_st(); tmem_wait_ld(); }
     tc_fence_before();
     __syncthreads();
-    if (is_issuer_warp) tmem_dealloc(tm, 512);
+    if (warp == 0) tmem_dealloc(tm, 512);
 #undef GROUP_BARRIER
 #undef COMMIT
 #undef WAIT_EVENT
