@@ -113,7 +113,9 @@ __device__ __forceinline__ void relu_stream(uint32_t d_addr, const float *__rest
     }
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// fast transcendental forms (MUFU ex2 / rcp, ~2 ulp): the tensor-core path is specified to 1e-4 relative anyway
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 __device__ __forceinline__ void rotate13(const float *s, float *o)   // cadrl.py:239-274, see lookahead.cu
 {
@@ -480,15 +482,13 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
             __syncwarp();
             {
                     WAIT_EVENT(e_r2);
-                    float v[32], hh[32], hl[32];
+                    float v[32];
                     ld_cols<32>(tl + D2 + 32 * half, v);
-                    ld_cols<32>(tl + A1H + 32 * half, hh);
-                    ld_cols<32>(tl + A1L + 32 * half, hl);
                     const float *b = PB + LY[TL_R2].bias_off + 32 * half;
 #pragma unroll
                     for (int j = 0; j < 25; ++j) {
                         const float r = sigmoidf_(fmaxf(v[j] + b[j], 0.0f));
-                        v[j] = __fmul_rn(r, hh[j] + hl[j]);
+                        v[j] = __fmul_rn(r, hn[j]);          // hn = h of the previous step (registers)
                     }
 #pragma unroll
                     for (int i = 0; i < 7; ++i) v[25 + i] = xh[i];
@@ -506,17 +506,15 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
             __syncwarp();
             {
                 WAIT_EVENT(e_q);
-                float v[32], hh[32], hl[32];
+                float v[32];
                 ld_cols<32>(tl + D2 + 32 * half, v);
-                ld_cols<32>(tl + A1H + 32 * half, hh);
-                ld_cols<32>(tl + A1L + 32 * half, hl);
                 const float *b = PB + LY[TL_Q].bias_off + 32 * half;
                 const float *pw = PB + net.tc_pb_pw + 25 * half;
                 float pd = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 25; ++j) {
-                    const float qv = tanhf(v[j] + b[j]);
-                    const float hold = hh[j] + hl[j];
+                    const float qv = tanhf_(v[j] + b[j]);
+                    const float hold = hn[j];
                     hn[j] = __fadd_rn(__fmul_rn(1.0f - z[j], hold), __fmul_rn(z[j], qv));
                     pd = fmaf(hn[j], pw[j], pd);
                     v[j] = hn[j];
@@ -571,8 +569,9 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
         float xres[25];
         if (!is_issuer_warp) {
             const float cnt = (samp >= 0) ? (float)s_cnt[samp] : 1.0f;
+            const float rc = __fdividef(1.0f, cnt);
 #pragma unroll
-            for (int j = 0; j < 25; ++j) xres[j] = net.act_fixed ? hn[j] : (samp >= 0 ? ACC[j] / cnt : 0.0f);
+            for (int j = 0; j < 25; ++j) xres[j] = net.act_fixed ? hn[j] : (samp >= 0 ? ACC[j] * rc : 0.0f);
         }
 
         if (args.mode == 2) {
@@ -645,12 +644,12 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
                         float d = 0.0f;
 #pragma unroll
                         for (int c = 0; c < 25; ++c) d = fmaf(qh[c], kp[c], d);
-                        const float p = expf(d * 0.2f - m);
+                        const float p = __expf(d * 0.2f - m);
                         sum += p;
 #pragma unroll
                         for (int c = 0; c < 25; ++c) o[c] = fmaf(p, kp[25 + c], o[c]);
                     }
-                    const float inv = 1.0f / sum;
+                    const float inv = __fdividef(1.0f, sum);
 #pragma unroll
                     for (int c = 0; c < 25; ++c) o[c] *= inv;
                 }
@@ -669,18 +668,25 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
                 float v[32];
                 ld_cols<32>(tl + DOUT + 32 * half, v);
                 const float *b = PB + LY[LB + 2].bias_off + 32 * half;
+                // LayerNorm with one exchange: each half sends (sum, sum of squares about its own mean); the halves are
+                // combined with the parallel-variance formula, which keeps the two-pass accuracy
                 float s = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 25; ++j) { xres[j] += v[j] + b[j]; s += xres[j]; }
-                sx[half * 128 + row] = s;
-                __syncthreads();
-                const float mean = (sx[row] + sx[128 + row]) / 50.0f;
+                const float mh = s * 0.04f;
                 float ss = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 25; ++j) { xres[j] -= mean; ss = fmaf(xres[j], xres[j], ss); }
+                for (int j = 0; j < 25; ++j) { const float dd = xres[j] - mh; ss = fmaf(dd, dd, ss); }
+                sx[half * 128 + row] = s;
                 sx[256 + half * 128 + row] = ss;
                 __syncthreads();
-                const float rstd = 1.0f / sqrtf((sx[256 + row] + sx[384 + row]) / 50.0f + 1e-5f);
+                const float so = sx[(half ^ 1) * 128 + row], sso = sx[256 + (half ^ 1) * 128 + row];
+                const float mean = (s + so) * 0.02f;
+                const float dm = (s - so) * 0.04f;                      // difference of the two half means
+                const float var = (ss + sso + dm * dm * 12.5f) * 0.02f;  // + n_a n_b / (n_a + n_b) * dm^2
+#pragma unroll
+                for (int j = 0; j < 25; ++j) xres[j] -= mean;
+                const float rstd = rsqrtf(var + 1e-5f);
                 float a[28];
 #pragma unroll
                 for (int j = 0; j < 25; ++j) { xres[j] = xres[j] * rstd * LN[j] + LN[50 + j]; a[j] = xres[j]; }
@@ -726,18 +732,25 @@ __global__ void __launch_bounds__(NT, 1) lookahead_tc_kernel(const LookaheadArgs
                 float v[32];
                 ld_cols<32>(tl + DF2 + 32 * half, v);
                 const float *b = PB + LY[LB + 6].bias_off + 32 * half;
+                // LayerNorm with one exchange: each half sends (sum, sum of squares about its own mean); the halves are
+                // combined with the parallel-variance formula, which keeps the two-pass accuracy
                 float s = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 25; ++j) { xres[j] += v[j] + b[j]; s += xres[j]; }
-                sx[half * 128 + row] = s;
-                __syncthreads();
-                const float mean = (sx[row] + sx[128 + row]) / 50.0f;
+                const float mh = s * 0.04f;
                 float ss = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 25; ++j) { xres[j] -= mean; ss = fmaf(xres[j], xres[j], ss); }
+                for (int j = 0; j < 25; ++j) { const float dd = xres[j] - mh; ss = fmaf(dd, dd, ss); }
+                sx[half * 128 + row] = s;
                 sx[256 + half * 128 + row] = ss;
                 __syncthreads();
-                const float rstd = 1.0f / sqrtf((sx[256 + row] + sx[384 + row]) / 50.0f + 1e-5f);
+                const float so = sx[(half ^ 1) * 128 + row], sso = sx[256 + (half ^ 1) * 128 + row];
+                const float mean = (s + so) * 0.02f;
+                const float dm = (s - so) * 0.04f;                      // difference of the two half means
+                const float var = (ss + sso + dm * dm * 12.5f) * 0.02f;  // + n_a n_b / (n_a + n_b) * dm^2
+#pragma unroll
+                for (int j = 0; j < 25; ++j) xres[j] -= mean;
+                const float rstd = rsqrtf(var + 1e-5f);
                 float a[28];
 #pragma unroll
                 for (int j = 0; j < 25; ++j) { xres[j] = xres[j] * rstd * LN[100 + j] + LN[150 + j]; a[j] = xres[j]; }
