@@ -267,18 +267,22 @@ def main():
     if os.path.exists(prof):
         try:
             with open(prof) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                pj = json.load(f)
+                traffic = (pj.get("dram_bytes_per_launch") if args.precision == "tf32x3" and B == pj.get("envs")
+                           else None)
         except Exception:
             traffic = None
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "lookahead_kernel", "kernel_ms": kernel_ms,
+                "traffic": traffic,
+                "kernel": "lookahead_tc_kernel" if args.precision == "tf32x3" else "lookahead_kernel",
+                "kernel_ms": kernel_ms,
                 "kernel_share_of_step": float(look_ms.sum() / step_ms.sum()),
                 "peak_source": "bf16_tflops_sustained of %s MEASURED_PEAKS.json" % peak_kind,
                 "pipe": ("tcgen05 kind::tf32, 3xTF32 split (3 MMAs per product, FP32 accumulate in TMEM)"
                          if args.precision == "tf32x3" else "fp32_ffma (no tensor-core math)"),
-                "kernel_variant": "lookahead_tc_kernel" if args.precision == "tf32x3" else "lookahead_kernel",
+
                 "fp32_pipe_peak_tflops": fp32_peak, "frac_fp32_pipe": achieved / fp32_peak,
                 "algorithmic_flops_per_launch": flops, "act_steps_hist": hist}
 
