@@ -20,6 +20,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 SOURCES = {
     "lookahead.cu": [],
     "lookahead_tc.cu": [],
+    "lookahead_h16.cu": [],
     "env.cu": ["-fmad=false"],   # FP64 env arithmetic is a sequence of individually rounded Python float ops
     "orca.cu": ["-fmad=false"],
     "capi.cu": [],

@@ -1,5 +1,6 @@
 // aem_common.cuh -- shared definitions of libaemcarl_b200 (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -64,6 +65,7 @@ enum { TL_Z1S = 0, TL_QS = 1, TL_Z1 = 2, TL_Z2 = 3, TL_R1 = 4, TL_R2 = 5, TL_Q =
        TL_ENC = 7,      // + 7 * l : INA, INB, OUT, F1A, F1B, F2A, F2B
        TL_A0 = 28, TL_A2 = 29, TL_NUM = 30 };
 constexpr int TC_PBLK_FLOATS = 3200;
+constexpr int H16_PBLK_FLOATS = 2880;
 
 struct NetParams {
     const float *raw;      // raw blob (biases, LayerNorm, ponder, last action layer)
@@ -77,6 +79,11 @@ struct NetParams {
     const float *tc_pblk;  // permuted biases, LayerNorm, ponder and last-layer parameters
     int tc_pblk_floats, tc_pb_ln, tc_pb_pw, tc_pb_a4;
     const TcLayer *tc_layers_d;   // [TL_NUM] in global memory
+    // FP16x3 tensor-core path (lookahead_h16.cu); TcLayer offsets are in fp16 elements
+    const __half *h16_img;
+    const float *h16_pblk;
+    int h16_pblk_floats;
+    const TcLayer *h16_layers_d;
 };
 
 // tile sizes of the packed layers (shared by the host packer and the kernel)
@@ -97,8 +104,12 @@ struct aem_handle_s {
     size_t packed_floats;
     float *tc_img_d, *tc_pblk_d;
     aem::TcLayer *tc_layers_d;
+    __half *h16_img_d;
+    float *h16_pblk_d;
+    aem::TcLayer *h16_layers_d;
+    size_t h16_img_halves;
     size_t tc_img_floats;
-    int precision;       // 0 = FP32 FFMA kernel, 1 = tcgen05 3xTF32 kernel
+    int precision;       // 0 = FP32 FFMA kernel, 1 = tcgen05 3xTF32 kernel, 2 = tcgen05 FP16x3 kernel (2 tiles / SM)
     aem::NetParams net;
     bool weights_set, actions_set, params_set;
     double *actions_d;   // [A][2]
@@ -128,6 +139,7 @@ namespace aem {
 struct LookaheadArgs;
 cudaError_t launch_lookahead(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
 cudaError_t launch_lookahead_tc(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
+cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
 cudaError_t launch_select(const double *values, const double *robot, int B, int A, int32_t *best, cudaStream_t st);
 cudaError_t launch_orca(int B, int n, const double *humans, const double *robot, const aem_env_params &p,
                         double *new_vel, cudaStream_t st);

@@ -144,6 +144,89 @@ void pack_tc(const float *w, TcPack &P)
     P.add(TL_A2, w + OFF_A2W, 100, w + OFF_A2B, 64, 104, out50, in100);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// FP16x3 images (lookahead_h16.cu): W_perm[c][k] split into hi = fp16(w), lo = fp16(w - hi), img[k/8][c][k%8].
+// N / K layouts: N50 -> [32 | 32], N100 -> [64 | 64] (converted in place to K = 128), linear1 chunks [48 | 48]
+// (in place, K = 96), in_proj per head [q32 | k32 | v32]; K = 64 operands are [32 | 32].
+// ---------------------------------------------------------------------------------------------------------
+int out100w(int c) { int h = c / 64, j = c % 64; return j < 50 ? 50 * h + j : -1; }
+int in100w(int k) { int h = k / 64, j = k % 64; return j < 50 ? 50 * h + j : -1; }
+int in50w(int k) { int h = k / 32, j = k % 32; return j < 25 ? 25 * h + j : -1; }
+int in_jointw(int k) { int h = k / 32, j = k % 32; return j < 25 ? 6 + 25 * h + j : (j < 28 ? 3 * h + (j - 25) : -1); }
+
+struct H16Pack {
+    std::vector<__half> img;
+    std::vector<float> pblk;
+    aem::TcLayer layers[aem::TL_NUM];
+    template <class OM, class IM>
+    void add(int id, const float *W, int in_dim, const float *bias, int N, int K, OM om, IM im, int expect_bias_off)
+    {
+        aem::TcLayer &L = layers[id];
+        L.N = N; L.ksteps = K / 16; L.bytes = N * K * 2;
+        L.off_hi = (int)img.size();
+        img.resize(img.size() + (size_t)2 * N * K, __float2half(0.0f));
+        L.off_lo = L.off_hi + N * K;
+        for (int c = 0; c < N; ++c)
+            for (int k = 0; k < K; ++k) {
+                const int o = om(c), i = im(k);
+                const float w = (o >= 0 && i >= 0) ? W[(size_t)o * in_dim + i] : 0.0f;
+                const __half hi = __float2half_rn(w);
+                const __half lo = __float2half_rn(w - __half2float(hi));
+                const size_t at = ((size_t)(k / 8) * N + c) * 8 + (k % 8);
+                img[L.off_hi + at] = hi;
+                img[L.off_lo + at] = lo;
+            }
+        L.bias_off = (N * K * 2 > 12288) ? 2 : 1;     // h16 tables: k-halves per image (ring slots are 12 KB)
+        if (expect_bias_off >= 0) {
+            if ((int)pblk.size() != expect_bias_off) { fprintf(stderr, "pack_h16: bias layout mismatch at layer %d\n", id); abort(); }
+            for (int c = 0; c < N; ++c) {
+                const int o = om(c);
+                pblk.push_back((o >= 0 && bias) ? bias[o] : 0.0f);
+            }
+        }
+    }
+};
+
+void pack_h16(const float *w, H16Pack &P)
+{
+    using namespace aem;
+    auto step1 = [](int k) { return in_hx(k < 16 ? 16 + k : 48 + (k - 16)); };     // A1 slots {16..31, 48..63}
+    P.add(TL_Z1, w + OFF_Z1W, HXD, w + OFF_Z1B, 128, 64, out100w, in_hx, 0);
+    P.add(TL_Z2, w + OFF_Z2W, 100, w + OFF_Z2B, 64, 128, out50, in100w, 128);
+    P.add(TL_R1, w + OFF_R1W, HXD, w + OFF_R1B, 128, 64, out100w, in_hx, 192);
+    P.add(TL_R2, w + OFF_R2W, 100, w + OFF_R2B, 64, 128, out50, in100w, 320);
+    P.add(TL_Q, w + OFF_QW, HXD, w + OFF_QB, 64, 64, out50, in_hx, 384);
+    P.add(TL_Z1S, w + OFF_Z1W, HXD, nullptr, 128, 32, out100w, step1, -1);
+    P.add(TL_QS, w + OFF_QW, HXD, nullptr, 64, 32, out50, step1, -1);
+    for (int l = 0; l < 3; ++l) {
+        const float *E = w + OFF_ENC + l * ENC_SIZE;
+        const int LB = TL_ENC + 7 * l, PBL = 448 + 512 * l;
+        for (int hd = 0; hd < 2; ++hd)
+            P.add(LB + hd, E + ENC_INW, HID, E + ENC_INB, 96, 64,
+                  [hd](int c) { int sidx = c / 32, j = c % 32; return j < 25 ? sidx * 50 + 25 * hd + j : -1; }, in50w,
+                  PBL + 96 * hd);
+        P.add(LB + 2, E + ENC_OW, HID, E + ENC_OB, 64, 64, out50, in50w, PBL + 192);
+        for (int ch = 0; ch < 2; ++ch)
+            P.add(LB + 3 + ch, E + ENC_L1W, HID, E + ENC_L1B, 96, 64,
+                  [ch](int c) { int u = unit75(c / 48, c % 48); return u >= 0 ? 75 * ch + u : -1; }, in50w,
+                  PBL + 256 + 96 * ch);
+        for (int ch = 0; ch < 2; ++ch)
+            P.add(LB + 5 + ch, E + ENC_L2W, 150, ch == 1 ? E + ENC_L2B : nullptr, 64, 96, out50,
+                  [ch](int k) { int u = unit75(k / 48, k % 48); return u >= 0 ? 75 * ch + u : -1; },
+                  ch == 1 ? PBL + 448 : -1);
+    }
+    P.add(TL_A0, w + OFF_A0W, 56, w + OFF_A0B, 128, 64, out100w, in_jointw, 1984);
+    P.add(TL_A2, w + OFF_A2W, 100, w + OFF_A2B, 64, 128, out50, in100w, 2112);
+    // LayerNorm (3 x 200), ponder (50 + 1), last action layer (50 + 1)
+    for (int l = 0; l < 3; ++l) {
+        const float *E = w + OFF_ENC + l * ENC_SIZE;
+        P.pblk.insert(P.pblk.end(), E + ENC_N1G, E + ENC_N1G + 200);
+    }
+    P.pblk.insert(P.pblk.end(), w + OFF_PW, w + OFF_PW + 51);
+    P.pblk.insert(P.pblk.end(), w + OFF_A4W, w + OFF_A4W + 51);
+    while (P.pblk.size() < (size_t)H16_PBLK_FLOATS) P.pblk.push_back(0.0f);
+}
+
 cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int check_ready(aem_handle h, bool need_weights, bool need_env)
@@ -207,7 +290,7 @@ int aem_destroy(aem_handle h)
 {
     if (!h) return AEM_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->raw_d); cudaFree(h->packed_d); cudaFree(h->tc_img_d); cudaFree(h->tc_pblk_d); cudaFree(h->tc_layers_d); cudaFree(h->actions_d); cudaFree(h->lut_d);
+    cudaFree(h->raw_d); cudaFree(h->packed_d); cudaFree(h->tc_img_d); cudaFree(h->tc_pblk_d); cudaFree(h->tc_layers_d); cudaFree(h->h16_img_d); cudaFree(h->h16_pblk_d); cudaFree(h->h16_layers_d); cudaFree(h->actions_d); cudaFree(h->lut_d);
     cudaFree(h->s_robot); cudaFree(h->s_humans); cudaFree(h->s_time); cudaFree(h->s_newvel);
     cudaFree(h->s_rewards); cudaFree(h->s_dmin); cudaFree(h->s_hnext); cudaFree(h->s_values);
     cudaFree(h->s_oreward); cudaFree(h->s_info); cudaFree(h->s_best); cudaFree(h->s_odone); cudaFree(h->s_oinfo);
@@ -276,6 +359,26 @@ int aem_load_weights(aem_handle h, const float *w, size_t count)
         AEM_CUDA_CHECK(cudaMemcpy(h->tc_layers_d, P.layers, sizeof(TcLayer) * TL_NUM, cudaMemcpyHostToDevice));
         net.tc_layers_d = h->tc_layers_d;
     }
+    {   // FP16x3 images
+        H16Pack P;
+        pack_h16(w, P);
+        if (P.pblk.size() != (size_t)H16_PBLK_FLOATS) return aem_set_error(AEM_ERR_INVALID, "h16 parameter block size");
+        if (P.img.size() > h->h16_img_halves) {
+            cudaFree(h->h16_img_d);
+            h->h16_img_d = nullptr;
+            AEM_CUDA_CHECK(cudaMalloc(&h->h16_img_d, sizeof(__half) * P.img.size()));
+            h->h16_img_halves = P.img.size();
+        }
+        if (!h->h16_pblk_d) AEM_CUDA_CHECK(cudaMalloc(&h->h16_pblk_d, sizeof(float) * H16_PBLK_FLOATS));
+        if (!h->h16_layers_d) AEM_CUDA_CHECK(cudaMalloc(&h->h16_layers_d, sizeof(TcLayer) * TL_NUM));
+        AEM_CUDA_CHECK(cudaMemcpy(h->h16_img_d, P.img.data(), sizeof(__half) * P.img.size(), cudaMemcpyHostToDevice));
+        AEM_CUDA_CHECK(cudaMemcpy(h->h16_pblk_d, P.pblk.data(), sizeof(float) * H16_PBLK_FLOATS, cudaMemcpyHostToDevice));
+        AEM_CUDA_CHECK(cudaMemcpy(h->h16_layers_d, P.layers, sizeof(TcLayer) * TL_NUM, cudaMemcpyHostToDevice));
+        net.h16_img = h->h16_img_d;
+        net.h16_pblk = h->h16_pblk_d;
+        net.h16_pblk_floats = H16_PBLK_FLOATS;
+        net.h16_layers_d = h->h16_layers_d;
+    }
     h->weights_set = true;
     return AEM_OK;
 }
@@ -315,7 +418,8 @@ int aem_set_act_mode(aem_handle h, int act_fixed, int act_steps)
 int aem_set_precision(aem_handle h, int precision)
 {
     if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
-    if (precision != 0 && precision != 1) return aem_set_error(AEM_ERR_INVALID, "precision must be 0 (fp32) or 1 (tf32x3)");
+    if (precision < 0 || precision > 2)
+        return aem_set_error(AEM_ERR_INVALID, "precision must be 0 (fp32), 1 (tf32x3) or 2 (fp16x3)");
     h->precision = precision;
     return AEM_OK;
 }
@@ -374,7 +478,9 @@ int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const doubl
     a.gamma_bar = gamma_bar;
     a.robot = robot_d; a.humans_next = humans_next_d; a.actions = h->actions_d; a.rewards = rewards_d;
     a.values = values_d; a.net_values = net_values_d; a.steps = act_steps_d;
-    AEM_CUDA_CHECK(h->precision ? launch_lookahead_tc(h, a, as_stream(stream)) : launch_lookahead(h, a, as_stream(stream)));
+    AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
+                   : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
+                                       : launch_lookahead(h, a, as_stream(stream)));
     AEM_CUDA_CHECK(launch_select(values_d, robot_d, B, h->A, best_d, as_stream(stream)));
     h->launches += 2 * (B > 0);
     return AEM_OK;
@@ -432,7 +538,9 @@ int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *
     a.total_samples = S;
     a.states = states_d;
     a.net_values = values_d; a.steps = steps_d;
-    AEM_CUDA_CHECK(h->precision ? launch_lookahead_tc(h, a, as_stream(stream)) : launch_lookahead(h, a, as_stream(stream)));
+    AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
+                   : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
+                                       : launch_lookahead(h, a, as_stream(stream)));
     h->launches += (S > 0);
     return AEM_OK;
 }
@@ -454,7 +562,9 @@ int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint
     a.total_samples = S;
     a.states = x_d;
     a.gru_out = out_d; a.steps = steps_d;
-    AEM_CUDA_CHECK(h->precision ? launch_lookahead_tc(h, a, as_stream(stream)) : launch_lookahead(h, a, as_stream(stream)));
+    AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
+                   : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
+                                       : launch_lookahead(h, a, as_stream(stream)));
     h->launches += (S > 0);
     return AEM_OK;
 }

@@ -1,0 +1,838 @@
+// lookahead_h16.cu -- tensor-core lookahead kernel, FP16x3 operands, TWO tiles in flight per SM (sm_100a).
+//
+// Same function and epilogue structure as lookahead_tc.cu, re-laid-out so that one 128-row tile needs only 256 TMEM
+// columns, <= 128 registers / thread and ~112 KB of shared memory; two CTAs then share an SM and the hardware overlaps
+// the MMA / commit latency of one tile with the epilogue of the other (lookahead_tc.cu serialises them: its ncu profile
+// shows 55 % of the warp time waiting on tcgen05.commit or CTA barriers).
+//   * operands: x = hi + lo with hi = fp16(x), lo = fp16(x - hi); D = A_hi W_hi + A_lo W_hi + A_hi W_lo with
+//     tcgen05.mma.kind::f16 (K = 16 per instruction, FP32 accumulation in TMEM).  For this network's value ranges the
+//     split carries ~22 mantissa bits (tools/tc_probe16.cu: ~1e-6 relative), same class as 3xTF32;
+//   * A operands are packed two fp16 per 32-bit TMEM column (even k in the low half) -> half the columns of TF32;
+//   * layers whose output feeds the next GEMM directly (z1, r1, linear1, action_mlp.0) are converted IN PLACE: each
+//     thread's accumulator columns become the (hi | lo) operand columns of the same thread;
+//   * weight images img[k/8][n][8] (fp16, hi and lo) stream through a 3 x 16 KB bulk-TMA ring.
+// Layout of every layer (N / K permutation and padding) is defined in capi.cu pack_h16.
+#include <cuda_fp16.h>
+
+#include "aem_common.cuh"
+#include "tc_common.cuh"
+
+namespace aem {
+namespace h16 {
+
+using namespace aemtc;
+
+constexpr int NT = 256;
+constexpr int NBUF = 4;                 // a two-layer issue group (in_proj heads, linear1 chunks) holds 4 chunks at once
+constexpr int WBUF_BYTES = 12288;       // 16 KB images (N*K = 8192 fp16) are streamed as two 8 KB k-halves
+constexpr int KV_PITCH = 101;
+constexpr int NEV = 4;
+constexpr int PBLK_MAX = H16_PBLK_FLOATS;
+
+// ---- tensor-memory column map: 256 columns per CTA ----
+constexpr uint32_t A1 = 0;              // [h;x]   K = 64  : hi cols [0,32) lo cols [32,64)
+constexpr uint32_t D1 = 64;             // z1 / r1 accumulators N = 128 = [64 | 64]; converted in place to A2 (K = 128)
+constexpr uint32_t D2 = 192;            // z2 / r2 / q accumulators N = 64
+constexpr uint32_t A3 = 64;             // [r*h;x] K = 64 (aliases the dead A2)
+constexpr uint32_t AE = 0;              // encoder stream operand K = 64
+constexpr uint32_t DIN = 64;            // in_proj accumulators, 2 heads x 96
+constexpr uint32_t AATT = 64;           // attention output operand K = 64 (D_IN is consumed by then)
+constexpr uint32_t DOUT = 128;          // out_proj accumulators N = 64
+constexpr uint32_t DF1A = 64, DF1B = 160;   // linear1 chunks N = 96 = [48 | 48]; converted in place (K = 96)
+constexpr uint32_t DF2 = 0;             // linear2 accumulators N = 64 (aliases the dead AE)
+constexpr uint32_t DA0 = 64;            // action_mlp.0 accumulators N = 128, converted in place
+constexpr uint32_t DA2 = 192;           // action_mlp.2 accumulators N = 64
+
+// parameter block offsets (floats) -- fixed by the layer order of capi.cu pack_h16 (asserted there)
+constexpr int PB_Z1 = 0, PB_Z2 = 128, PB_R1 = 192, PB_R2 = 320, PB_Q = 384, PB_ENC = 448, PB_ENC_STRIDE = 512;
+constexpr int PBE_INA = 0, PBE_OUT = 192, PBE_F1A = 256, PBE_F1B = 352, PBE_F2 = 448;   // INB = INA + 96
+constexpr int PB_A0 = 1984, PB_A2 = 2112, PB_LN = 2176, PB_PW = 2776, PB_A4 = 2827;
+static_assert(PB_A4 + 51 <= H16_PBLK_FLOATS, "parameter block");
+
+constexpr size_t SMEM_BYTES = (size_t)NBUF * WBUF_BYTES + 128 * KV_PITCH * 4 + PBLK_MAX * 4 + 4 * 128 * 4 +
+                              (96 + 4) * 4 + (NBUF + NEV) * 8 + 16;
+
+__device__ __forceinline__ void pair_sync(int q4) { asm volatile("bar.sync %0, 64;" ::"r"(q4 + 1) : "memory"); }
+
+__device__ __forceinline__ void ld8f(uint32_t taddr, float *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void ld4u(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void st4u(uint32_t taddr, const uint32_t *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3])
+                 : "memory");
+}
+// (a, b) -> packed fp16 pair hi and the packed residual pair lo; a sits in the low half (even k)
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// 8 consecutive K slots -> 4 hi columns + 4 lo columns
+__device__ __forceinline__ void st8_pack(uint32_t hi_addr, uint32_t lo_addr, const float *v)
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    st4u(hi_addr, h);
+    st4u(lo_addr, l);
+}
+// NV slots (multiple of 8) starting at slot 0 of this thread's block
+template <int NV>
+__device__ __forceinline__ void st_pack(uint32_t hi_addr, uint32_t lo_addr, const float *v)
+{
+#pragma unroll
+    for (int i = 0; i < NV; i += 8) st8_pack(hi_addr + i / 2, lo_addr + i / 2, v + i);
+}
+// read back 8 slots (4 hi + 4 lo columns) as floats: value = hi + lo
+__device__ __forceinline__ void ld8_unpack(uint32_t hi_addr, uint32_t lo_addr, float *v)
+{
+    uint32_t h[4], l[4];
+    ld4u(hi_addr, h);
+    ld4u(lo_addr, l);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 fh = __half22float2(*reinterpret_cast<const __half2 *>(&h[i]));
+        const float2 fl = __half22float2(*reinterpret_cast<const __half2 *>(&l[i]));
+        v[2 * i] = fh.x + fl.x;
+        v[2 * i + 1] = fh.y + fl.y;
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+// In-place ReLU conversion of this thread's W accumulator columns [base, base + W) into its operand block:
+// hi columns [base, base + W/2), lo columns [base + W/2, base + W).  W = 64 or 48.  The upper half of the accumulators
+// is buffered in registers first because the lo columns overwrite it.
+template <int W>
+__device__ __forceinline__ void relu_inplace(uint32_t base, const float *__restrict__ bias)
+{
+    constexpr int NB = W / 16;            // chunks of 8 that must be buffered (upper half)
+    float buf[NB * 8];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) ld8f(base + W / 2 + 8 * c, buf + 8 * c);
+    tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {        // lower half: read chunk, write hi [4c,4c+4) and lo [W/2+4c, ..)
+        float v[8];
+        ld8f(base + 8 * c, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + bias[8 * c + j], 0.0f);
+        st8_pack(base + 4 * c, base + W / 2 + 4 * c, v);
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        float *v = buf + 8 * c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + bias[W / 2 + 8 * c + j], 0.0f);
+        st8_pack(base + W / 4 + 4 * c, base + W / 2 + W / 4 + 4 * c, v);
+    }
+}
+
+__device__ __forceinline__ void rotate13(const float *s, float *o)   // cadrl.py:239-274, see lookahead.cu
+{
+    const float dx = s[5] - s[0], dy = s[6] - s[1];
+    const float rot = atan2f(dy, dx);
+    const float c = cosf(rot), sn = sinf(rot);
+    o[0] = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    o[1] = s[7];
+    o[2] = 0.0f;
+    o[3] = s[4];
+    o[4] = __fadd_rn(__fmul_rn(s[2], c), __fmul_rn(s[3], sn));
+    o[5] = __fsub_rn(__fmul_rn(s[3], c), __fmul_rn(s[2], sn));
+    const float rx = s[9] - s[0], ry = s[10] - s[1];
+    o[6] = __fadd_rn(__fmul_rn(rx, c), __fmul_rn(ry, sn));
+    o[7] = __fsub_rn(__fmul_rn(ry, c), __fmul_rn(rx, sn));
+    o[8] = __fadd_rn(__fmul_rn(s[11], c), __fmul_rn(s[12], sn));
+    o[9] = __fsub_rn(__fmul_rn(s[12], c), __fmul_rn(s[11], sn));
+    o[10] = s[13];
+    const float ax = s[0] - s[9], ay = s[1] - s[10];
+    o[11] = sqrtf(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)));
+    o[12] = s[4] + s[13];
+}
+
+// ------------------------------------------------------------------------------------------------
+// issuer (thread 0 for the bulk copies / commits; warp 0 issues MMAs warp-uniformly)
+// ------------------------------------------------------------------------------------------------
+struct Issuer {
+    uint8_t *wbuf;
+    uint64_t *wfull;
+    const __half *img;
+    const TcLayer *layers;
+    int nloaded, nused, nfree;
+    int pf_stage, pf_idx, pf_part;
+    int tiles_left;
+};
+__device__ __forceinline__ int stage_len(int st) { return st == 0 ? 3 : (st == 1 ? 5 : 23); }
+__device__ __forceinline__ int layer_at(int st, int idx)
+{
+    if (st == 0) return idx == 0 ? TL_Z1S : (idx == 1 ? TL_Z2 : TL_QS);
+    if (st == 1) return idx == 0 ? TL_Z1 : (idx == 1 ? TL_Z2 : (idx == 2 ? TL_R1 : (idx == 3 ? TL_R2 : TL_Q)));
+    return idx < 21 ? TL_ENC + idx : (idx == 21 ? TL_A0 : TL_A2);
+}
+__device__ __noinline__ void prefetch(Issuer *s)
+{
+    while (s->pf_stage >= 0 && s->nloaded - s->nfree < NBUF) {
+        const TcLayer &L = s->layers[layer_at(s->pf_stage, s->pf_idx)];
+        const int nsplit = L.bias_off;                 // h16 tables: number of k-halves per image (1 or 2)
+        const int part = s->pf_part / nsplit, sub = s->pf_part - part * nsplit;
+        const int bytes = L.bytes / nsplit;
+        const int buf = s->nloaded % NBUF;
+        mbar_expect_tx(&s->wfull[buf], (uint32_t)bytes);
+        bulk_g2s(s->wbuf + (size_t)buf * WBUF_BYTES, s->img + (part ? L.off_lo : L.off_hi) + sub * (bytes / 2),
+                 (uint32_t)bytes, &s->wfull[buf]);
+        ++s->nloaded;
+        if (++s->pf_part == 2 * nsplit) {
+            s->pf_part = 0;
+            if (++s->pf_idx == stage_len(s->pf_stage)) {
+                s->pf_idx = 0;
+                if (s->pf_stage == 2) {
+                    if (s->tiles_left > 0) { --s->tiles_left; s->pf_stage = 0; } else s->pf_stage = -2;
+                } else {
+                    s->pf_stage = -1;
+                }
+            }
+        }
+    }
+}
+__device__ __noinline__ uint32_t take_chunk_addr(Issuer *s)
+{
+    while (s->nloaded <= s->nused) prefetch(s);
+    const int buf = s->nused % NBUF;
+    mbar_wait(&s->wfull[buf], (uint32_t)((s->nused / NBUF) & 1));
+    ++s->nused;
+    return smem_u32(s->wbuf + (size_t)buf * WBUF_BYTES);
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// One layer: KS k-steps (16 K values = 8 operand columns each) per pass.  Operand column of k-step ks:
+//   a_base + HSTRIDE * (ks / KSH) + 8 * (ks % KSH), lo part LO columns further.  SPECIAL: step-1 images use the
+//   k-steps {1, 3} of A1 (the x slots).
+template <int N, int KS, int KSH, int HSTRIDE, int LO, bool SPECIAL, int SPLIT>
+__device__ __forceinline__ void issue_t(Issuer *iss, int lane, uint32_t tm, uint32_t a_base, uint32_t d, bool accumulate)
+{
+    constexpr uint32_t LBO = (uint32_t)N * 16;
+    constexpr uint64_t DHI = ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // F16 x F16 -> F32
+    constexpr int KSS = KS / SPLIT;                      // k-steps per streamed chunk
+    static_assert(KS % SPLIT == 0, "split");
+    const bool leader = elect_one();
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {               // part 0: W_hi (A_hi and A_lo passes), part 1: W_lo (A_hi pass)
+#pragma unroll
+        for (int sub = 0; sub < SPLIT; ++sub) {
+            uint32_t wa = 0;
+            if (lane == 0) wa = take_chunk_addr(iss);
+            wa = __shfl_sync(0xffffffffu, wa, 0);
+            const uint32_t base = (wa & 0x3FFFFu) >> 4;
+#pragma unroll
+            for (int kk = 0; kk < KSS; ++kk) {
+                const int ks = sub * KSS + kk;
+                const uint32_t acol = SPECIAL ? (uint32_t)(8 * (2 * ks + 1))
+                                              : (uint32_t)(HSTRIDE * (ks / KSH) + 8 * (ks % KSH));
+                const uint64_t bd = DHI | (uint64_t)(base + kk * ((2 * LBO) >> 4));
+                if (leader) {
+                    if (part == 0) {
+                        mma_f16_ts(tm + d, tm + a_base + acol, bd, IDESC, (ks == 0 && !accumulate) ? 0u : 1u);
+                        mma_f16_ts(tm + d, tm + a_base + acol + LO, bd, IDESC, 1u);
+                    } else {
+                        mma_f16_ts(tm + d, tm + a_base + acol, bd, IDESC, 1u);
+                    }
+                }
+            }
+        }
+    }
+}
+// shorthand for the three operand layouts
+// (images larger than one ring slot -- N * K = 8192 -- are streamed as two k-halves: SPLIT = 2)
+#define ISSUE_K64(N, a, d, acc) issue_t<N, 4, 4, 0, 32, false, ((N) * 64 > 6144 ? 2 : 1)>(iss_p, lane, tm, a, d, acc)
+#define ISSUE_K64S(N, a, d) issue_t<N, 2, 4, 0, 32, true, 1>(iss_p, lane, tm, a, d, false)        /* step-1 images   */
+#define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 32, false, 2>(iss_p, lane, tm, a, d, false)      /* in-place [64|64] */
+#define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 24, false, 1>(iss_p, lane, tm, a, d, acc)    /* in-place [48|48] */
+
+__global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArgs args)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *wbuf = smem_raw;
+    float *kv = reinterpret_cast<float *>(wbuf + (size_t)NBUF * WBUF_BYTES);
+    float *pblk = kv + 128 * KV_PITCH;
+    float *sx = pblk + PBLK_MAX;                                 // [4][128] exchange
+    int *s_cnt = reinterpret_cast<int *>(sx + 4 * 128);
+    int *s_act = s_cnt + 32;
+    int *s_need = s_act + 32;
+    int *s_flag = s_need + 32;
+    uint64_t *wfull = reinterpret_cast<uint64_t *>(s_flag + 4);
+    uint64_t *evb = wfull + NBUF;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(evb + NEV);
+    __shared__ Issuer s_iss;
+
+    const NetParams &net = args.net;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = (warp >> 2) & 1, q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const int T = args.T, S = args.S;
+    const int ntiles = (args.total_samples + S - 1) / S;
+
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; ++i) mbar_init(&wfull[i], 1);
+        for (int i = 0; i < NEV; ++i) mbar_init(&evb[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    for (int i = tid; i < net.h16_pblk_floats; i += NT) pblk[i] = net.h16_pblk[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_slot;
+    const uint32_t tl = tm + lane_base;
+    Issuer *iss_p = &s_iss;
+    if (tid == 0) {
+        s_iss.wbuf = wbuf; s_iss.wfull = wfull; s_iss.img = net.h16_img; s_iss.layers = net.h16_layers_d;
+        s_iss.nloaded = s_iss.nused = s_iss.nfree = 0;
+        s_iss.pf_stage = -2; s_iss.pf_idx = 0; s_iss.pf_part = 0; s_iss.tiles_left = 0;
+        if ((int)blockIdx.x < ntiles) {
+            s_iss.pf_stage = 0;
+            s_iss.tiles_left = (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x;
+        }
+    }
+    __syncthreads();
+    int nev = 0;
+
+#define GROUP_BARRIER()                     \
+    do {                                    \
+        tmem_wait_st();                     \
+        tc_fence_before();                  \
+        __syncthreads();                    \
+        if (warp == 0) tc_fence_after();    \
+    } while (0)
+#define COMMIT(e) mma_commit(&evb[(e) % NEV])
+#define WAIT_EVENT(e)                                                   \
+    do {                                                                \
+        mbar_wait(&evb[(e) % NEV], (uint32_t)(((e) / NEV) & 1));        \
+        tc_fence_after();                                               \
+    } while (0)
+#define ISSUER_DRAIN(e)                                                 \
+    do {                                                                \
+        prefetch(iss_p);                                                \
+        mbar_wait(&evb[(e) % NEV], (uint32_t)(((e) / NEV) & 1));        \
+        s_iss.nfree = s_iss.nused;                                      \
+        prefetch(iss_p);                                                \
+    } while (0)
+
+    const float *PB = pblk;
+
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int s0 = tile * S;
+        const int nsamp = min(S, args.total_samples - s0);
+        const int nrows = nsamp * T;
+
+        float xh[7], selfs[3], ACC[25], hn[25], z[25];
+        float P = 0.0f;
+        int samp = -1, tok = 0;
+#pragma unroll
+        for (int j = 0; j < 25; ++j) { ACC[j] = 0.0f; hn[j] = 0.0f; }
+
+        // ---------------- phase 0: inputs -> A1 = [h = 0 ; x] ----------------
+        {
+            float o[XD];
+#pragma unroll
+            for (int k = 0; k < XD; ++k) o[k] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) selfs[i] = 0.0f;
+            if (row < nrows) {
+                samp = row / T;
+                tok = row - samp * T;
+                const int gs = s0 + samp;
+                if (args.mode == 0) {
+                    const int b = gs / args.A, a = gs - b * args.A;
+                    const double *rb = args.robot + (size_t)b * 9;
+                    const double ax = args.actions[2 * a], ay = args.actions[2 * a + 1];
+                    const int hi = (tok == 0) ? 0 : tok - 1;
+                    const double *hb = args.humans_next + ((size_t)b * args.n + hi) * 5;
+                    float in14[14];
+                    in14[0] = (float)__dadd_rn(rb[0], __dmul_rn(ax, args.dt));
+                    in14[1] = (float)__dadd_rn(rb[1], __dmul_rn(ay, args.dt));
+                    in14[2] = (float)ax; in14[3] = (float)ay;
+                    in14[4] = (float)rb[4]; in14[5] = (float)rb[5]; in14[6] = (float)rb[6];
+                    in14[7] = (float)rb[7]; in14[8] = (float)rb[8];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) in14[9 + k] = (float)hb[k];
+                    rotate13(in14, o);
+                } else if (args.mode == 1) {
+                    const int hi = (tok == 0) ? 0 : tok - 1;
+                    const float *src = args.states + ((size_t)gs * args.n + hi) * XD;
+#pragma unroll
+                    for (int k = 0; k < XD; ++k) o[k] = src[k];
+                } else {
+                    const float *src = args.states + ((size_t)gs * T + tok) * XD;
+#pragma unroll
+                    for (int k = 0; k < XD; ++k) o[k] = src[k];
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) selfs[i] = half ? o[3 + i] : o[i];
+                if (args.mode != 2 && tok == 0) {
+                    o[6] = 0.0f; o[7] = 0.0f; o[8] = o[4]; o[9] = o[5]; o[10] = o[3]; o[11] = 0.0f; o[12] = o[3];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 7; ++i) xh[i] = half ? (i < 6 ? o[7 + (i < 6 ? i : 0)] : 0.0f) : o[i];
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 25; ++j) v[j] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) v[25 + i] = xh[i];
+            st_pack<32>(tl + A1 + 16 * half, tl + A1 + 32 + 16 * half, v);
+            if (tid < 32) { s_cnt[tid] = 0; s_act[tid] = (tid < nsamp) ? 1 : 0; s_need[tid] = 0; }
+        }
+
+        // ---------------- phase 1: GRU + adaptive computation time ----------------
+        const int max_steps = net.act_fixed ? net.act_steps : 3;
+#pragma unroll 1
+        for (int step = 1; step <= max_steps; ++step) {
+            const bool kfull = step > 1;
+            // ---- z1 -> in place A2
+            GROUP_BARRIER();
+            const int e_z1 = nev++;
+            if (warp == 0) {
+                if (kfull) ISSUE_K64(128, A1, D1, false);
+                else ISSUE_K64S(128, A1, D1);
+                if (lane == 0) { COMMIT(e_z1); ISSUER_DRAIN(e_z1); }
+            }
+            __syncwarp();
+            WAIT_EVENT(e_z1);
+            relu_inplace<64>(tl + D1 + 64 * half, PB + PB_Z1 + 64 * half);
+            // ---- z
+            GROUP_BARRIER();
+            const int e_z2 = nev++;
+            if (warp == 0) {
+                ISSUE_K128(64, D1, D2);
+                if (lane == 0) { COMMIT(e_z2); ISSUER_DRAIN(e_z2); }
+            }
+            __syncwarp();
+            WAIT_EVENT(e_z2);
+            {
+                const float *b = PB + PB_Z2 + 32 * half;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[8];
+                    ld8f(tl + D2 + 32 * half + 8 * c, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (8 * c + j < 25) z[8 * c + j] = sigmoidf_(fmaxf(v[j] + b[8 * c + j], 0.0f));
+                }
+            }
+            if (kfull) {
+                // ---- r1 -> in place A2, r, [r*h ; x] -> A3
+                GROUP_BARRIER();
+                const int e_r1 = nev++;
+                if (warp == 0) {
+                    ISSUE_K64(128, A1, D1, false);
+                    if (lane == 0) { COMMIT(e_r1); ISSUER_DRAIN(e_r1); }
+                }
+                __syncwarp();
+                WAIT_EVENT(e_r1);
+                relu_inplace<64>(tl + D1 + 64 * half, PB + PB_R1 + 64 * half);
+                GROUP_BARRIER();
+                const int e_r2 = nev++;
+                if (warp == 0) {
+                    ISSUE_K128(64, D1, D2);
+                    if (lane == 0) { COMMIT(e_r2); ISSUER_DRAIN(e_r2); }
+                }
+                __syncwarp();
+                WAIT_EVENT(e_r2);
+                {
+                    const float *b = PB + PB_R2 + 32 * half;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float v[8];
+                        ld8f(tl + D2 + 32 * half + 8 * c, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int s = 8 * c + j;
+                            if (s < 25) v[j] = __fmul_rn(sigmoidf_(fmaxf(v[j] + b[s], 0.0f)), hn[s]);
+                            else v[j] = xh[s - 25];
+                        }
+                        st8_pack(tl + A3 + 16 * half + 4 * c, tl + A3 + 32 + 16 * half + 4 * c, v);
+                    }
+                }
+            }
+            // ---- q, h = (1 - z) h + z q
+            GROUP_BARRIER();
+            const int e_q = nev++;
+            if (warp == 0) {
+                if (kfull) ISSUE_K64(64, A3, D2, false);
+                else ISSUE_K64S(64, A1, D2);
+                if (lane == 0) { COMMIT(e_q); ISSUER_DRAIN(e_q); }
+            }
+            __syncwarp();
+            WAIT_EVENT(e_q);
+            {
+                const float *b = PB + PB_Q + 32 * half;
+                const float *pw = PB + PB_PW + 25 * half;
+                float pd = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[8];
+                    ld8f(tl + D2 + 32 * half + 8 * c, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int s = 8 * c + j;
+                        if (s < 25) {
+                            const float qv = tanhf_(v[j] + b[s]);
+                            hn[s] = __fadd_rn(__fmul_rn(1.0f - z[s], hn[s]), __fmul_rn(z[s], qv));
+                            pd = fmaf(hn[s], pw[s], pd);
+                            v[j] = hn[s];
+                        } else {
+                            v[j] = xh[s - 25];
+                        }
+                    }
+                    st8_pack(tl + A1 + 16 * half + 4 * c, tl + A1 + 32 + 16 * half + 4 * c, v);
+                }
+                if (!net.act_fixed) {
+                    sx[half * 128 + row] = pd;
+                    pair_sync(q4);
+                    const bool active = samp >= 0 && s_act[samp];
+                    if (active) {
+                        const float p = sigmoidf_(sx[row] + sx[128 + row] + PB[PB_PW + 50]);
+                        P += p;
+#pragma unroll
+                        for (int j = 0; j < 25; ++j) ACC[j] = __fadd_rn(ACC[j], __fmul_rn(p, hn[j]));
+                        if (half == 0 && P < 0.95f) s_need[samp] = 1;
+                    }
+                }
+            }
+            int cont;
+            if (net.act_fixed) {
+                if (tid < 32 && tid < nsamp) s_cnt[tid] = step;
+                cont = step < max_steps;
+            } else {
+                if (tid == 0) s_flag[0] = 0;
+                __syncthreads();
+                if (tid < 32 && s_act[tid]) {
+                    s_cnt[tid] = step;
+                    const int need = s_need[tid];
+                    s_act[tid] = need;
+                    s_need[tid] = 0;
+                    if (need) s_flag[0] = 1;
+                }
+                __syncthreads();
+                cont = s_flag[0] && step < max_steps;
+            }
+            if (tid == 0 && s_iss.pf_stage == -1) {
+                int ns;
+                if (cont) ns = 1;
+                else if (args.mode == 2) {
+                    if (s_iss.tiles_left > 0) { --s_iss.tiles_left; ns = 0; } else ns = -2;
+                } else ns = 2;
+                s_iss.pf_stage = ns; s_iss.pf_idx = 0; s_iss.pf_part = 0;
+            }
+            if (!cont) break;
+        }
+        __syncthreads();
+
+        float xres[25];
+        {
+            const float cnt = (samp >= 0) ? (float)s_cnt[samp] : 1.0f;
+            const float rc = __fdividef(1.0f, cnt);
+#pragma unroll
+            for (int j = 0; j < 25; ++j) xres[j] = net.act_fixed ? hn[j] : (samp >= 0 ? ACC[j] * rc : 0.0f);
+        }
+        if (args.mode == 2) {
+            if (row < nrows) {
+                float *dst = args.gru_out + ((size_t)s0 * T + row) * HID + 25 * half;
+#pragma unroll
+                for (int j = 0; j < 25; ++j) dst[j] = xres[j];
+                if (args.steps && half == 0 && tok == 0) args.steps[s0 + samp] = (uint8_t)s_cnt[samp];
+            }
+            __syncthreads();
+            continue;
+        }
+        {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = j < 25 ? xres[j] : 0.0f;
+            st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, v);
+        }
+
+        // ---------------- phase 2: 3 x post-norm encoder layer ----------------
+#pragma unroll 1
+        for (int l = 0; l < 3; ++l) {
+            const int PBL = PB_ENC + PB_ENC_STRIDE * l;
+            const float *LN = PB + PB_LN + l * 200 + 25 * half;
+            GROUP_BARRIER();
+            const int e_in = nev++;
+            if (warp == 0) {
+                ISSUE_K64(96, AE, DIN, false);
+                ISSUE_K64(96, AE, DIN + 96, false);
+                if (lane == 0) { COMMIT(e_in); ISSUER_DRAIN(e_in); }
+            }
+            __syncwarp();
+            WAIT_EVENT(e_in);
+            float o[32];
+            {
+                float qh[25];
+                const float *b = PB + PBL + PBE_INA + 96 * half;
+                float *dst = kv + row * KV_PITCH + 50 * half;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {          // q | k | v blocks of 32 columns each
+                    float a[8], k[8], v[8];
+                    ld8f(tl + DIN + 96 * half + 8 * c, a);
+                    ld8f(tl + DIN + 96 * half + 32 + 8 * c, k);
+                    ld8f(tl + DIN + 96 * half + 64 + 8 * c, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int s = 8 * c + j;
+                        if (s < 25) {
+                            qh[s] = a[j] + b[s];
+                            dst[s] = k[j] + b[32 + s];
+                            dst[25 + s] = v[j] + b[64 + s];
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncthreads();       // every thread has consumed D_IN and published k / v
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = 0.0f;
+                if (samp >= 0) {
+                    const float *base = kv + (samp * T) * KV_PITCH + 50 * half;
+                    float m = -INFINITY;
+                    for (int j = 0; j < T; ++j) {
+                        const float *kp = base + j * KV_PITCH;
+                        float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < 24; c += 2) { d0 = fmaf(qh[c], kp[c], d0); d1 = fmaf(qh[c + 1], kp[c + 1], d1); }
+                        d0 = fmaf(qh[24], kp[24], d0);
+                        m = fmaxf(m, (d0 + d1) * 0.2f);
+                    }
+                    float sum = 0.0f;
+                    for (int j = 0; j < T; ++j) {
+                        const float *kp = base + j * KV_PITCH;
+                        float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < 24; c += 2) { d0 = fmaf(qh[c], kp[c], d0); d1 = fmaf(qh[c + 1], kp[c + 1], d1); }
+                        d0 = fmaf(qh[24], kp[24], d0);
+                        const float p = __expf((d0 + d1) * 0.2f - m);
+                        sum += p;
+#pragma unroll
+                        for (int c = 0; c < 25; ++c) o[c] = fmaf(p, kp[25 + c], o[c]);
+                    }
+                    const float inv = __fdividef(1.0f, sum);
+#pragma unroll
+                    for (int c = 0; c < 25; ++c) o[c] *= inv;
+                }
+            }
+            st_pack<32>(tl + AATT + 16 * half, tl + AATT + 32 + 16 * half, o);
+            // ---- out_proj + residual + LayerNorm1
+            GROUP_BARRIER();
+            const int e_out = nev++;
+            if (warp == 0) {
+                ISSUE_K64(64, AATT, DOUT, false);
+                if (lane == 0) { COMMIT(e_out); ISSUER_DRAIN(e_out); }
+            }
+            __syncwarp();
+            WAIT_EVENT(e_out);
+            {
+                const float *b = PB + PBL + PBE_OUT + 32 * half;
+                float s = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[8];
+                    ld8f(tl + DOUT + 32 * half + 8 * c, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (8 * c + j < 25) { xres[8 * c + j] += v[j] + b[8 * c + j]; s += xres[8 * c + j]; }
+                }
+                const float mh = s * 0.04f;
+                float ss = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 25; ++j) { const float dd = xres[j] - mh; ss = fmaf(dd, dd, ss); }
+                sx[half * 128 + row] = s;
+                sx[256 + half * 128 + row] = ss;
+                pair_sync(q4);
+                const float so = sx[(half ^ 1) * 128 + row], sso = sx[256 + (half ^ 1) * 128 + row];
+                const float mean = (s + so) * 0.02f;
+                const float dm = (s - so) * 0.04f;
+                const float rstd = rsqrtf((ss + sso + dm * dm * 12.5f) * 0.02f + 1e-5f);
+                float a[32];
+#pragma unroll
+                for (int j = 0; j < 25; ++j) { xres[j] = (xres[j] - mean) * rstd * LN[j] + LN[50 + j]; a[j] = xres[j]; }
+#pragma unroll
+                for (int j = 25; j < 32; ++j) a[j] = 0.0f;
+                st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, a);
+            }
+            // ---- FFN in two hidden chunks, converted in place
+            GROUP_BARRIER();
+            const int e_f1a = nev++;
+            const int e_f1b = nev++;
+            if (warp == 0) {
+                ISSUE_K64(96, AE, DF1A, false);
+                if (lane == 0) COMMIT(e_f1a);
+                __syncwarp();
+                ISSUE_K64(96, AE, DF1B, false);
+                if (lane == 0) { COMMIT(e_f1b); ISSUER_DRAIN(e_f1b); }
+            }
+            __syncwarp();
+            WAIT_EVENT(e_f1a);
+            relu_inplace<48>(tl + DF1A + 48 * half, PB + PBL + PBE_F1A + 48 * half);
+            GROUP_BARRIER();       // F1B has completed as well (drained above): AE is dead, D_F2 may overwrite it
+            if (warp == 0) ISSUE_K96(64, DF1A, DF2, false);
+            __syncwarp();
+            WAIT_EVENT(e_f1b);
+            relu_inplace<48>(tl + DF1B + 48 * half, PB + PBL + PBE_F1B + 48 * half);
+            GROUP_BARRIER();
+            const int e_f2 = nev++;
+            if (warp == 0) {
+                ISSUE_K96(64, DF1B, DF2, true);
+                if (lane == 0) { COMMIT(e_f2); ISSUER_DRAIN(e_f2); }
+            }
+            __syncwarp();
+            WAIT_EVENT(e_f2);
+            {
+                const float *b = PB + PBL + PBE_F2 + 32 * half;
+                float s = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[8];
+                    ld8f(tl + DF2 + 32 * half + 8 * c, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (8 * c + j < 25) { xres[8 * c + j] += v[j] + b[8 * c + j]; s += xres[8 * c + j]; }
+                }
+                const float mh = s * 0.04f;
+                float ss = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 25; ++j) { const float dd = xres[j] - mh; ss = fmaf(dd, dd, ss); }
+                sx[half * 128 + row] = s;
+                sx[256 + half * 128 + row] = ss;
+                tc_fence_before();
+                pair_sync(q4);      // also: the partner has finished reading its D_F2 columns (AE overwrites them)
+                const float so = sx[(half ^ 1) * 128 + row], sso = sx[256 + (half ^ 1) * 128 + row];
+                const float mean = (s + so) * 0.02f;
+                const float dm = (s - so) * 0.04f;
+                const float rstd = rsqrtf((ss + sso + dm * dm * 12.5f) * 0.02f + 1e-5f);
+                float a[32];
+#pragma unroll
+                for (int j = 0; j < 25; ++j) { xres[j] = (xres[j] - mean) * rstd * LN[100 + j] + LN[150 + j]; a[j] = xres[j]; }
+#pragma unroll
+                for (int j = 25; j < 32; ++j) a[j] = 0.0f;
+                if (l == 2) { a[25] = selfs[0]; a[26] = selfs[1]; a[27] = selfs[2]; }     // joint = [self_state ; env]
+                st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, a);
+            }
+        }
+
+        // ---------------- phase 3: action_mlp ----------------
+        GROUP_BARRIER();
+        const int e_a0 = nev++;
+        if (warp == 0) {
+            ISSUE_K64(128, AE, DA0, false);
+            if (lane == 0) { COMMIT(e_a0); ISSUER_DRAIN(e_a0); }
+        }
+        __syncwarp();
+        WAIT_EVENT(e_a0);
+        relu_inplace<64>(tl + DA0 + 64 * half, PB + PB_A0 + 64 * half);
+        GROUP_BARRIER();
+        const int e_a2 = nev++;
+        if (warp == 0) {
+            ISSUE_K128(64, DA0, DA2);
+            if (lane == 0) { COMMIT(e_a2); ISSUER_DRAIN(e_a2); }
+        }
+        __syncwarp();
+        WAIT_EVENT(e_a2);
+        {
+            const float *b = PB + PB_A2 + 32 * half;
+            const float *w4 = PB + PB_A4 + 25 * half;
+            float pd = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v[8];
+                ld8f(tl + DA2 + 32 * half + 8 * c, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (8 * c + j < 25) pd = fmaf(fmaxf(v[j] + b[8 * c + j], 0.0f), w4[8 * c + j], pd);
+            }
+            sx[half * 128 + row] = pd;
+            pair_sync(q4);
+            if (half == 0 && samp >= 0 && tok == 0) {
+                const float val = sx[row] + sx[128 + row] + PB[PB_A4 + 50];
+                const int gs = s0 + samp;
+                if (args.net_values) args.net_values[gs] = val;
+                if (args.values) args.values[gs] = __dadd_rn(args.rewards[gs], __dmul_rn(args.gamma_bar, (double)val));
+                if (args.steps) args.steps[gs] = (uint8_t)s_cnt[samp];
+            }
+        }
+        __syncthreads();
+    }
+
+    tmem_wait_st();
+    tmem_wait_ld();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 256);
+#undef GROUP_BARRIER
+#undef COMMIT
+#undef WAIT_EVENT
+#undef ISSUER_DRAIN
+}
+
+}  // namespace h16
+
+cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStream_t st)
+{
+    static bool attr_set[64] = {false};
+    if (!attr_set[h->device & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(h16::lookahead_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)h16::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set[h->device & 63] = true;
+    }
+    const int ntiles = (a.total_samples + a.S - 1) / a.S;
+    if (ntiles <= 0) return cudaSuccess;
+    const int maxgrid = 2 * h->num_sms;        // two CTAs (two tiles in flight) per SM
+    const int grid = ntiles < maxgrid ? ntiles : maxgrid;
+    h16::lookahead_h16_kernel<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace aem

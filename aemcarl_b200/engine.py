@@ -69,8 +69,8 @@ class Engine:
         check(self.lib.aem_set_act_mode(self.h, int(bool(act_fixed)), int(act_steps)))
 
     def set_precision(self, precision):
-        """'fp32' (FFMA kernel, default) or 'tf32x3' (tcgen05 tensor-core kernel)"""
-        mode = {"fp32": 0, "tf32x3": 1, 0: 0, 1: 1}[precision]
+        """'fp32' (FFMA kernel, default), 'tf32x3' (tcgen05, one tile / SM) or 'fp16x3' (tcgen05, two tiles / SM)"""
+        mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2, 0: 0, 1: 1, 2: 2}[precision]
         check(self.lib.aem_set_precision(self.h, mode))
         self.precision = mode
 

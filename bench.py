@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--humans", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-envs", type=int, default=256, help="--impl reference: envs per step (bounded sample)")
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3"],
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "fp16x3"],
                     help="value-network GEMM arithmetic: tcgen05 3xTF32 (default) or the FP32 FFMA kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

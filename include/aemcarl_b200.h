@@ -93,7 +93,8 @@ int aem_set_act_mode(aem_handle h, int act_fixed, int act_steps);
 
 /* Arithmetic of the value-network GEMMs inside aem_lookahead / aem_value_forward / aem_gru_act:
  *   0 = FP32 FFMA (k-ascending accumulation, the order of the CPU oracle)            [default]
- *   1 = tcgen05 tensor cores, 3xTF32 split with FP32 accumulation in tensor memory (~1e-6 relative of mode 0). */
+ *   1 = tcgen05 tensor cores, 3xTF32 split with FP32 accumulation in tensor memory (~1e-6 relative of mode 0)
+ *   2 = tcgen05 tensor cores, FP16 hi/lo split (3 MMAs per product, FP32 accumulation), two tiles in flight per SM. */
 int aem_set_precision(aem_handle h, int precision);
 
 /* ---- device-pointer entry points ---- */
