@@ -172,11 +172,12 @@ __device__ __forceinline__ void rotate13(const float *s, float *o)   // cadrl.py
 // ------------------------------------------------------------------------------------------------
 // issuer (thread 0 for the bulk copies / commits; warp 0 issues MMAs warp-uniformly)
 // ------------------------------------------------------------------------------------------------
+struct LayerInfo { int off_hi, off_lo, bytes, nsplit; };      // 16 B per layer, kept in shared memory
 struct Issuer {
     uint8_t *wbuf;
     uint64_t *wfull;
     const __half *img;
-    const TcLayer *layers;
+    const LayerInfo *layers;
     int nloaded, nused, nfree;
     int pf_stage, pf_idx, pf_part;
     int tiles_left;
@@ -191,8 +192,8 @@ __device__ __forceinline__ int layer_at(int st, int idx)
 __device__ __noinline__ void prefetch(Issuer *s)
 {
     while (s->pf_stage >= 0 && s->nloaded - s->nfree < NBUF) {
-        const TcLayer &L = s->layers[layer_at(s->pf_stage, s->pf_idx)];
-        const int nsplit = L.bias_off;                 // h16 tables: number of k-halves per image (1 or 2)
+        const LayerInfo L = s->layers[layer_at(s->pf_stage, s->pf_idx)];
+        const int nsplit = L.nsplit;                   // number of k-halves per image (1 or 2)
         const int part = s->pf_part / nsplit, sub = s->pf_part - part * nsplit;
         const int bytes = L.bytes / nsplit;
         const int buf = s->nloaded % NBUF;
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     uint64_t *evb = wfull + NBUF;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(evb + NEV);
     __shared__ Issuer s_iss;
+    __shared__ LayerInfo s_layers[TL_NUM];     // a global-memory table would cost an L2 round trip per prefetched chunk
 
     const NetParams &net = args.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -314,6 +316,11 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     }
     if (warp == 0) tmem_alloc(tmem_slot, 256);
     for (int i = tid; i < net.h16_pblk_floats; i += NT) pblk[i] = net.h16_pblk[i];
+    if (tid < TL_NUM) {
+        const TcLayer L = net.h16_layers_d[tid];
+        s_layers[tid].off_hi = L.off_hi; s_layers[tid].off_lo = L.off_lo; s_layers[tid].bytes = L.bytes;
+        s_layers[tid].nsplit = L.bias_off;     // h16 tables carry the k-split count in this field
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -321,7 +328,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     const uint32_t tl = tm + lane_base;
     Issuer *iss_p = &s_iss;
     if (tid == 0) {
-        s_iss.wbuf = wbuf; s_iss.wfull = wfull; s_iss.img = net.h16_img; s_iss.layers = net.h16_layers_d;
+        s_iss.wbuf = wbuf; s_iss.wfull = wfull; s_iss.img = net.h16_img; s_iss.layers = s_layers;
         s_iss.nloaded = s_iss.nused = s_iss.nfree = 0;
         s_iss.pf_stage = -2; s_iss.pf_idx = 0; s_iss.pf_part = 0; s_iss.tiles_left = 0;
         if ((int)blockIdx.x < ntiles) {
@@ -447,15 +454,12 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             WAIT_EVENT(e_z2);
             {
                 const float *b = PB + PB_Z2 + 32 * half;
+                float v[32];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float v[8];
-                    ld8f(tl + D2 + 32 * half + 8 * c, v);
-                    tmem_wait_ld();
+                for (int c = 0; c < 4; ++c) ld8f(tl + D2 + 32 * half + 8 * c, v + 8 * c);
+                tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (8 * c + j < 25) z[8 * c + j] = sigmoidf_(fmaxf(v[j] + b[8 * c + j], 0.0f));
-                }
+                for (int j = 0; j < 25; ++j) z[j] = sigmoidf_(fmaxf(v[j] + b[j], 0.0f));
             }
             if (kfull) {
                 // ---- r1 -> in place A2, r, [r*h ; x] -> A3
@@ -673,14 +677,13 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             {
                 const float *b = PB + PBL + PBE_OUT + 32 * half;
                 float s = 0.0f;
+                {
+                    float v[32];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float v[8];
-                    ld8f(tl + DOUT + 32 * half + 8 * c, v);
+                    for (int c = 0; c < 4; ++c) ld8f(tl + DOUT + 32 * half + 8 * c, v + 8 * c);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (8 * c + j < 25) { xres[8 * c + j] += v[j] + b[8 * c + j]; s += xres[8 * c + j]; }
+                    for (int j = 0; j < 25; ++j) { xres[j] += v[j] + b[j]; s += xres[j]; }
                 }
                 const float mh = s * 0.04f;
                 float ss = 0.0f;
@@ -730,14 +733,13 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             {
                 const float *b = PB + PBL + PBE_F2 + 32 * half;
                 float s = 0.0f;
+                {
+                    float v[32];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float v[8];
-                    ld8f(tl + DF2 + 32 * half + 8 * c, v);
+                    for (int c = 0; c < 4; ++c) ld8f(tl + DF2 + 32 * half + 8 * c, v + 8 * c);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (8 * c + j < 25) { xres[8 * c + j] += v[j] + b[8 * c + j]; s += xres[8 * c + j]; }
+                    for (int j = 0; j < 25; ++j) { xres[j] += v[j] + b[j]; s += xres[j]; }
                 }
                 const float mh = s * 0.04f;
                 float ss = 0.0f;

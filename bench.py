@@ -163,8 +163,9 @@ def main():
     ap.add_argument("--humans", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-envs", type=int, default=256, help="--impl reference: envs per step (bounded sample)")
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "fp16x3"],
-                    help="value-network GEMM arithmetic: tcgen05 3xTF32 (default) or the FP32 FFMA kernel")
+    ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3"],
+                    help="value-network GEMM arithmetic: tcgen05 FP16x3 with two tiles per SM (default), tcgen05 3xTF32, "
+                         "or the FP32 FFMA kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -268,20 +269,23 @@ def main():
         try:
             with open(prof) as f:
                 pj = json.load(f)
-                traffic = (pj.get("dram_bytes_per_launch") if args.precision == "tf32x3" and B == pj.get("envs")
-                           else None)
+                traffic = (pj.get("dram_bytes_per_launch") if args.precision == pj.get("precision") and
+                           B == pj.get("envs") else None)
         except Exception:
             traffic = None
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,
-                "kernel": "lookahead_tc_kernel" if args.precision == "tf32x3" else "lookahead_kernel",
+                "kernel": {"tf32x3": "lookahead_tc_kernel", "fp16x3": "lookahead_h16_kernel",
+                           "fp32": "lookahead_kernel"}[args.precision],
                 "kernel_ms": kernel_ms,
                 "kernel_share_of_step": float(look_ms.sum() / step_ms.sum()),
                 "peak_source": "bf16_tflops_sustained of %s MEASURED_PEAKS.json" % peak_kind,
-                "pipe": ("tcgen05 kind::tf32, 3xTF32 split (3 MMAs per product, FP32 accumulate in TMEM)"
-                         if args.precision == "tf32x3" else "fp32_ffma (no tensor-core math)"),
+                "pipe": {"tf32x3": "tcgen05 kind::tf32, 3xTF32 split (3 MMAs per product, FP32 accumulate in TMEM)",
+                         "fp16x3": "tcgen05 kind::f16, FP16 hi/lo split (3 MMAs per product, FP32 accumulate in TMEM), "
+                                   "2 tiles in flight per SM",
+                         "fp32": "fp32_ffma (no tensor-core math)"}[args.precision],
 
                 "fp32_pipe_peak_tflops": fp32_peak, "frac_fp32_pipe": achieved / fp32_peak,
                 "algorithmic_flops_per_launch": flops, "act_steps_hist": hist}
@@ -324,7 +328,9 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None,
-               "dtype": "tf32x3 (fp32-equivalent split, fp32 accumulate)" if args.precision == "tf32x3" else "f32",
+               "dtype": {"tf32x3": "tf32x3 (fp32-equivalent split, fp32 accumulate)",
+                         "fp16x3": "fp16x3 (fp16 hi/lo split = 22 mantissa bits, fp32 accumulate)",
+                         "fp32": "f32"}[args.precision],
                "data": "synthetic",
                "config": {"workload": "batched lookahead inference: %d envs x %d humans x 81 actions per GPU, "
                                       "random-init weights (synthetic_weights seed 0), circle_crossing train-stream "
