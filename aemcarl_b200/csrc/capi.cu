@@ -430,7 +430,9 @@ int aem_orca(aem_handle h, int B, int n, const double *humans_d, const double *r
     if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
     if (!h->params_set) return aem_set_error(AEM_ERR_STATE, "aem_set_env_params has not been called");
     if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (B == 0) return AEM_OK;
     if (n - 1 + (h->params.robot_visible ? 1 : 0) > 32) return aem_set_error(AEM_ERR_INVALID, "too many neighbours");
+    if (B == 0) return AEM_OK;      // empty batch: nothing to do (buffers may be null)
     if (!humans_d || !robot_d || !new_vel_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     AEM_CUDA_CHECK(launch_orca(B, n, humans_d, robot_d, h->params, new_vel_d, as_stream(stream)));
@@ -445,6 +447,7 @@ int aem_env_lookahead(aem_handle h, int B, int n, const double *robot_d, const d
     int rc = check_ready(h, false, true);
     if (rc) return rc;
     if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (B == 0) return AEM_OK;
     if (!robot_d || !humans_d || !new_vel_d || !global_time_d || !rewards_d)
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
@@ -462,6 +465,7 @@ int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const doubl
     int rc = check_ready(h, true, true);
     if (rc) return rc;
     if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (B == 0) return AEM_OK;
     if (!robot_d || !humans_next_d || !rewards_d || !values_d || !best_d)
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
     if ((long long)B * h->A > 0x7fffffffLL) return aem_set_error(AEM_ERR_INVALID, "B * A overflows int32");
@@ -494,6 +498,7 @@ int aem_env_apply(aem_handle h, int B, int n, double *robot_d, double *humans_d,
     int rc = check_ready(h, false, true);
     if (rc) return rc;
     if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (B == 0) return AEM_OK;
     if (!robot_d || !humans_d || !new_vel_d || !global_time_d || !chosen_d)
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
@@ -511,6 +516,7 @@ int aem_env_reset_done(aem_handle h, int B, int n, double *robot_d, double *huma
 {
     if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
     if (B < 0 || n < 1 || n > AEM_MAX_HUMANS || P < 1) return aem_set_error(AEM_ERR_INVALID, "bad B / n / P");
+    if (B == 0) return AEM_OK;
     if (!robot_d || !humans_d || !global_time_d || !done_d || !pool_robot_d || !pool_humans_d || !case_idx_d)
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
@@ -526,6 +532,7 @@ int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *
     if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
     if (!h->weights_set) return aem_set_error(AEM_ERR_STATE, "aem_load_weights has not been called");
     if (S < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad S / n");
+    if (S == 0) return AEM_OK;
     if (!states_d || !values_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     LookaheadArgs a;
@@ -550,6 +557,7 @@ int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint
     if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
     if (!h->weights_set) return aem_set_error(AEM_ERR_STATE, "aem_load_weights has not been called");
     if (S < 0 || T < 1 || T > AEM_MAX_HUMANS + 1) return aem_set_error(AEM_ERR_INVALID, "bad S / T");
+    if (S == 0) return AEM_OK;
     if (!x_d || !out_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     LookaheadArgs a;

@@ -185,9 +185,12 @@ static void gru_cell(const prep_t *p, const float *x, float *h /* in/out [50] */
 /* components.py:107-137  ATCBasic.forward for ONE sample of T tokens
  * (predict() feeds one (env, action) sample per forward, so the batch-global
  *  `selector.any()` of the reference is exactly a per-sample test). */
+static __thread float g_act_margin;   /* min |accum_p - 0.95| seen by the halting tests of the last sample */
+
 static int gru_act_sample(const prep_t *p, const float *x /*[T][13]*/, int T, int act_fixed, int act_steps,
                           float *out /*[T][50]*/)
 {
+    g_act_margin = INFINITY;
     const float *W = p->W;
     float h[MAXT][H], acc[MAXT][H], P[MAXT];
     memset(h, 0, sizeof(h));
@@ -210,6 +213,7 @@ static int gru_act_sample(const prep_t *p, const float *x /*[T][13]*/, int T, in
             P[t] += hp;
             for (int k = 0; k < H; ++k) acc[t][k] += hp * h[t][k];
             if (P[t] < 0.95f) any = 1;                /* accum_p < 1 - epsilon (fp32 compare) */
+            if (fabsf(P[t] - 0.95f) < g_act_margin) g_act_margin = fabsf(P[t] - 0.95f);
         }
         ++cnt;
         if (!any) break;
@@ -300,6 +304,18 @@ void aemo_value_forward(const float *W, const float *state, int n, int act_fixed
     prep_t *p = prep_create(W);
     *value = value_forward_prepared(p, state, n, act_fixed, act_steps, steps);
     free(p);
+}
+
+/* distance of the halting decision from its threshold: min over tokens and executed steps of |accum_p - (1 - eps)|.
+ * The ACT step count (components.py:132-134) is a hard threshold, so an implementation with different rounding may
+ * legitimately take a different number of steps when this margin is at rounding level (documented near-threshold rule). */
+float aemo_act_margin(const float *W, const float *state, int n)
+{
+    prep_t *p = prep_create(W);
+    int steps = 0;
+    (void)value_forward_prepared(p, state, n, 0, 1, &steps);
+    free(p);
+    return g_act_margin;
 }
 
 typedef struct { const prep_t *p; int n; const float *states; int act_fixed, act_steps; float *values; uint8_t *steps; } vfb_ctx;

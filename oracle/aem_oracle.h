@@ -108,6 +108,9 @@ void aemo_rotate(const float *in14, float *out13);
 void aemo_value_forward(const float *W, const float *state, int n, int act_fixed, int act_steps,
                         float *value, int *steps);
 
+/* min |accum_p - 0.95| over tokens / executed steps of one sample (how close the ACT halting test was to flipping) */
+float aemo_act_margin(const float *W, const float *state, int n);
+
 /* multi_human_rl.py:336-372 over a batch of envs: values[B][A] (f64 = reward + gbar*V),
  * net_values[B][A] (f32 raw V), best[B] (first strict maximum), steps[B][A].
  * robot[B][9] f64, humans_next[B][n][5] f64, rewards[B][A] f64, actions[A][2] f64. */

@@ -65,6 +65,7 @@ def lib():
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.aemo_occupancy.restype = ctypes.c_double
         _lib.aemo_num_weights.restype = ctypes.c_int
+        _lib.aemo_act_margin.restype = ctypes.c_float
         assert _lib.aemo_num_weights() == NUM_WEIGHTS
     return _lib
 
@@ -107,6 +108,26 @@ def value_forward(W, state, act_fixed=False, act_steps=1):
     lib().aemo_value_forward(_p(W, F), _p(state, F), n, int(act_fixed), int(act_steps), ctypes.byref(v),
                              ctypes.byref(s))
     return v.value, s.value
+
+
+def act_margin(W, state):
+    """min |accum_p - 0.95| over tokens and executed ACT steps for one sample (state [n][13], rotated)"""
+    W = _f32(W)
+    state = _f32(state)
+    return float(lib().aemo_act_margin(_p(W, F), _p(state, F), state.shape[0]))
+
+
+def rotated_state(robot9, humans_next, action, dt=0.2):
+    """the [n][13] network input of one (env, action) sample exactly as aemo_lookahead builds it"""
+    r = np.asarray(robot9, dtype=np.float64)
+    hn = np.asarray(humans_next, dtype=np.float64).reshape(-1, 5)
+    in14 = np.zeros((hn.shape[0], 14), dtype=np.float32)
+    in14[:, 0] = np.float32(r[0] + action[0] * dt)
+    in14[:, 1] = np.float32(r[1] + action[1] * dt)
+    in14[:, 2], in14[:, 3] = np.float32(action[0]), np.float32(action[1])
+    in14[:, 4:9] = r[4:9].astype(np.float32)
+    in14[:, 9:14] = hn.astype(np.float32)
+    return rotate(in14)
 
 
 def value_forward_batch(W, states, act_fixed=False, act_steps=1, nthreads=1):

@@ -123,15 +123,27 @@ def test_env_lookahead_random_vs_oracle(engine, oracle, actions, n):
     engine.set_env_params(make_env_params())
 
 
-def check_values(net, ref_net, steps, ref_steps, values, ref_values, best, ref_best):
+def check_values(net, ref_net, steps, ref_steps, values, ref_values, best, ref_best, margin_of=None):
+    """north-star tolerance.  `margin_of(b, a)` (optional) returns the oracle's ACT halting margin of sample (b, a):
+    the halting test accum_p < 0.95 (components.py:132-134) is a hard threshold, so an implementation with different
+    rounding may take a different number of GRU steps when accum_p is within rounding distance of 0.95 -- the
+    documented near-threshold rule allows a different step count (hence value) only where that margin is <= 1e-4."""
+    flip = steps != ref_steps
+    if flip.any():
+        assert margin_of is not None, "ACT step counts differ: %d samples" % flip.sum()
+        assert flip.sum() <= max(1, int(1e-4 * flip.size)), flip.sum()
+        for b, a in zip(*np.nonzero(flip)):
+            assert margin_of(b, a) <= 1e-4, (b, a, margin_of(b, a))
+    ok = ~flip
     rel = np.abs(net - ref_net) / np.maximum(np.abs(ref_net), 1e-2)
-    assert rel.max() <= 1e-4, rel.max()
-    assert np.array_equal(steps, ref_steps)
-    assert np.abs(values - ref_values).max() <= 1e-4 * np.maximum(np.abs(ref_values).max(), 1.0)
+    assert rel[ok].max() <= 1e-4, rel[ok].max()
+    assert np.abs(values - ref_values)[ok].max() <= 1e-4 * np.maximum(np.abs(ref_values).max(), 1.0)
     for b in np.nonzero(best != ref_best)[0]:        # documented near-tie rule
+        if flip[b].any():
+            continue
         v = ref_values[b]
         assert abs(v[best[b]] - v[ref_best[b]]) <= 1e-4 * max(abs(v[ref_best[b]]), 1e-3), (b, best[b], ref_best[b])
-    return rel.max()
+    return rel[ok].max()
 
 
 @pytest.mark.parametrize("tag", DECISIONS)
@@ -257,3 +269,59 @@ def test_decide_step_host_matches_device_pipeline(engine, oracle, actions):
     assert np.array_equal(inf, info[np.arange(B), chosen])
     assert np.array_equal(reward, rew[np.arange(B), chosen]) or np.abs(reward - rew[np.arange(B), chosen]).max() < 1e-12
     assert np.array_equal(done, (inf >= 2).astype(np.int32))
+
+
+def test_error_paths_and_empty_batches(engine, actions):
+    """argument validation of the C ABI: errors are reported, nothing is silently computed"""
+    from aemcarl_b200._lib import AemError
+    from aemcarl_b200.engine import Engine
+    W = wts.synthetic_weights(0)
+    engine.load_weights(W)
+    with pytest.raises(AemError, match="113752"):
+        engine.load_weights(W[:-1])
+    humans = torch.zeros((2, 33, 8), dtype=torch.float64, device="cuda")       # n > AEM_MAX_HUMANS
+    robot = torch.zeros((2, 9), dtype=torch.float64, device="cuda")
+    with pytest.raises(AemError, match="bad B / n"):
+        engine.orca(humans, robot)
+    # B = 0 is a no-op, not an error
+    h0 = torch.zeros((0, 5, 8), dtype=torch.float64, device="cuda")
+    r0 = torch.zeros((0, 9), dtype=torch.float64, device="cuda")
+    assert engine.orca(h0, r0).shape == (0, 5, 2)
+    fresh = Engine(0)
+    with pytest.raises(AemError, match="aem_set_env_params"):
+        fresh.orca(humans[:, :5].contiguous(), robot)
+    fresh.set_env_params(make_env_params())
+    with pytest.raises(AemError, match="aem_set_action_space"):
+        fresh.env_lookahead(robot, humans[:, :5].contiguous(), torch.zeros((2, 5, 2), dtype=torch.float64, device="cuda"),
+                            torch.zeros(2, dtype=torch.float64, device="cuda"))
+    with pytest.raises((AemError, KeyError)):
+        fresh.set_precision(7)
+    fresh.close()
+
+
+def test_precisions_agree_at_full_bench_size(engine, oracle, actions):
+    """size-independent property at the BASELINE configuration (4096 envs x 5 humans x 81 actions): the tensor-core
+    variants and the FP32 kernel agree within the stated tolerance, ACT counts are identical, argmax differs only on
+    near-ties; also checks determinism (two launches give bit-identical outputs)."""
+    from aemcarl_b200 import scenarios
+    if engine.precision_name == "fp32":
+        pytest.skip("reference run is the fp32 kernel itself")
+    B, n = 4096, 5
+    W = wts.synthetic_weights(0)
+    engine.load_weights(W)
+    robot, humans = scenarios.generate_pool("train", 0, B, n, "circle_crossing")
+    rng = np.random.RandomState(0)
+    humans[:, :, 2:4] = rng.uniform(-0.7, 0.7, (B, n, 2))
+    robot[:, 0:2] += rng.uniform(-1, 1, (B, 2))
+    hnext = np.concatenate([humans[:, :, 0:2] + 0.2 * humans[:, :, 2:4], humans[:, :, 2:5]], axis=2)
+    rewards = rng.uniform(-0.05, 0, (B, 81))
+    args = (dev(robot), dev(hnext), dev(rewards), pow(0.9, 0.2))
+    v1, n1, b1, s1 = [t.clone() for t in engine.lookahead(*args)]
+    v2, n2, b2, s2 = engine.lookahead(*args)
+    assert torch.equal(n1, n2) and torch.equal(b1, b2) and torch.equal(s1, s2)          # deterministic
+    engine.set_precision("fp32")
+    vr, nr, br, sr = engine.lookahead(*args)
+    engine.set_precision(engine.precision_name)
+    margin = lambda b, a: oracle.act_margin(W, oracle.rotated_state(robot[b], hnext[b], actions[a]))
+    check_values(n1.cpu().numpy(), nr.cpu().numpy(), s1.cpu().numpy(), sr.cpu().numpy(), v1.cpu().numpy(),
+                 vr.cpu().numpy(), b1.cpu().numpy(), br.cpu().numpy(), margin_of=margin)
