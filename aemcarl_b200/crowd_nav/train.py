@@ -1,0 +1,143 @@
+"""Training entry point mirroring crowd_nav/train.py:20-246 for the actenvcarl policy on the CUDA hot path.
+
+    python -m aemcarl_b200.crowd_nav.train --output_dir data/output [--il_episodes 200] [--train_episodes N] ...
+    torchrun --nproc-per-node N -m aemcarl_b200.crowd_nav.train ...     (data parallel: env shards + grad all-reduce)
+
+Flow (same order as the reference): imitation learning with the ORCA teacher (safety_space from train.config) ->
+Trainer.optimize_epoch -> il_model.pth -> target model -> RL loop with the linear epsilon schedule, one sampled episode
+per step, optimize_batch, periodic target update / validation / checkpoints (rl_model_{ep}.pth, state_dict keys of the
+reference).  Data parallelism: every rank plays its own cases (rank-strided case counters) and the flat gradient is
+all-reduced between backward() and step() (crowd_nav/utils/trainer.py).
+"""
+import argparse
+import copy
+import logging
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from aemcarl_b200.crowd_nav.default_configs import env_config, policy_config, train_config
+from aemcarl_b200.crowd_nav.policy.policy_factory import policy_factory
+from aemcarl_b200.crowd_nav.utils.explorer import Explorer
+from aemcarl_b200.crowd_nav.utils.memory import ReplayMemory
+from aemcarl_b200.crowd_nav.utils.trainer import Trainer, broadcast_parameters
+from aemcarl_b200.crowd_sim import make
+from aemcarl_b200.crowd_sim.envs.utils.robot import Robot
+
+
+def build(args, device):
+    ecfg = env_config(sim__human_num=args.human_num)
+    for k in ("agent_timestep", "human_timestep", "reward_increment", "position_variance", "direction_variance"):
+        ecfg.set("reward", k, str(getattr(args, k)))
+    pcfg = policy_config(act_fixed=args.act_fixed, act_steps=args.act_steps)
+    tcfg = train_config()
+    policy = policy_factory["actenvcarl"]()
+    policy.configure(pcfg)
+    policy.set_device(device)
+    env = make("CrowdSim-v0")
+    env.configure(ecfg)
+    robot = Robot(ecfg, "robot")
+    env.set_robot(robot)
+    return ecfg, pcfg, tcfg, policy, env, robot
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser("Parse configuration file")
+    ap.add_argument("--output_dir", default="data/output")
+    ap.add_argument("--human_num", type=int, default=5)
+    ap.add_argument("--optimizer", default="Adam")
+    ap.add_argument("--il_episodes", type=int, default=200)           # the reference hard-codes 200 (train.py:196)
+    ap.add_argument("--il_epochs", type=int, default=None)
+    ap.add_argument("--train_episodes", type=int, default=None)
+    ap.add_argument("--agent_timestep", type=float, default=0.4)
+    ap.add_argument("--human_timestep", type=float, default=0.5)
+    ap.add_argument("--reward_increment", type=float, default=2.0)
+    ap.add_argument("--position_variance", type=float, default=2.0)
+    ap.add_argument("--direction_variance", type=float, default=2.0)
+    ap.add_argument("--act_steps", type=int, default=1)
+    ap.add_argument("--act_fixed", default=False, action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args(argv)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=device)
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s, %(levelname)s: %(message)s",
+                        datefmt="%Y-%m-%d %H:%M:%S")
+    os.makedirs(args.output_dir, exist_ok=True)
+    torch.manual_seed(args.seed)
+    ecfg, pcfg, tcfg, policy, env, robot = build(args, device)
+    model = policy.get_model()
+    broadcast_parameters(model, 0)
+
+    batch_size = tcfg.getint("trainer", "batch_size")
+    memory = ReplayMemory(tcfg.getint("train", "capacity"))
+    trainer = Trainer(model, memory, device, batch_size)
+    explorer = Explorer(env, robot, device, memory, policy.gamma, target_policy=policy)
+
+    # ---- imitation learning (train.py:171-204)
+    il_policy = policy_factory[tcfg.get("imitation_learning", "il_policy")]()
+    il_policy.multiagent_training = policy.multiagent_training
+    il_policy.safety_space = tcfg.getfloat("imitation_learning", "safety_space")
+    robot.set_policy(il_policy)
+    policy.set_env(env)
+    policy.time_step = env.time_step
+    trainer.set_learning_rate(tcfg.getfloat("imitation_learning", "il_learning_rate"), args.optimizer)
+    env.case_counter["train"] = rank                      # rank-strided cases
+    stride_cases(env, world)
+    explorer.run_k_episodes(args.il_episodes, "train", update_memory=True, imitation_learning=True)
+    il_epochs = args.il_epochs or tcfg.getint("imitation_learning", "il_epochs")
+    loss = trainer.optimize_epoch(il_epochs) if len(memory) >= batch_size else float("nan")
+    logging.info("Finish imitation learning. Experience set size: %d/%d, loss %.3e", len(memory), memory.capacity, loss)
+    if rank == 0:
+        torch.save(model.state_dict(), os.path.join(args.output_dir, "il_model.pth"))
+    explorer.update_target_model(model)
+
+    # ---- reinforcement learning (train.py:206-246)
+    robot.set_policy(policy)
+    policy.set_env(env)
+    trainer.set_learning_rate(tcfg.getfloat("train", "rl_learning_rate"), args.optimizer)
+    train_episodes = args.train_episodes if args.train_episodes is not None else tcfg.getint("train", "train_episodes")
+    eps_start, eps_end = tcfg.getfloat("train", "epsilon_start"), tcfg.getfloat("train", "epsilon_end")
+    eps_decay = tcfg.getfloat("train", "epsilon_decay")
+    episode = 0
+    while episode < train_episodes:
+        epsilon = eps_start + (eps_end - eps_start) / eps_decay * episode if episode < eps_decay else eps_end
+        policy.set_epsilon(epsilon)
+        if episode % tcfg.getint("train", "evaluation_interval") == 0 and episode > 0:
+            explorer.run_k_episodes(env.case_size["val"], "val", episode=episode)
+        explorer.run_k_episodes(tcfg.getint("train", "sample_episodes"), "train", update_memory=True, episode=episode)
+        trainer.optimize_batch(tcfg.getint("train", "train_batches"))
+        episode += 1
+        if episode % tcfg.getint("train", "target_update_interval") == 0:
+            explorer.update_target_model(model)
+        if episode != 0 and episode % tcfg.getint("train", "checkpoint_interval") == 0 and rank == 0:
+            torch.save(model.state_dict(), os.path.join(args.output_dir, "rl_model_%d.pth" % episode))
+    if rank == 0:
+        torch.save(model.state_dict(), os.path.join(args.output_dir, "rl_model.pth"))
+    return dict(loss=loss, memory=len(memory), model=model, explorer=explorer, policy=policy, env=env, robot=robot)
+
+
+def stride_cases(env, world):
+    """data parallel: rank r plays cases r, r + world, ... (the reference's counter advances by one)"""
+    if world <= 1:
+        return
+    orig = env.reset
+
+    def reset(phase="test", test_case=None):
+        ob = orig(phase, test_case)
+        if env.case_counter[phase] >= 0:
+            env.case_counter[phase] = (env.case_counter[phase] + world - 1) % env.case_size[phase]
+        return ob
+    env.reset = reset
+
+
+if __name__ == "__main__":
+    main()
