@@ -29,6 +29,15 @@ def allreduce_gradients(model):
     return flat.numel()
 
 
+def min_over_ranks(value, device):
+    """ranks own different amounts of experience: every rank must run the same number of all-reduced steps"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item())
+
+
 def broadcast_parameters(model, src=0):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         for p in model.state_dict().values():
@@ -71,9 +80,12 @@ class Trainer(object):
         if self.data_loader is None:
             self.data_loader = DataLoader(self.memory, self.batch_size, shuffle=True, drop_last=True)
         average_epoch_loss = 0
+        steps_per_epoch = min_over_ranks(len(self.data_loader), self.device)
         for epoch in range(num_epochs):
             epoch_loss = 0
-            for inputs, values in self.data_loader:
+            for i, (inputs, values) in enumerate(self.data_loader):
+                if i >= steps_per_epoch:
+                    break
                 epoch_loss += self._step(inputs, values)
             average_epoch_loss = epoch_loss / len(self.memory)
             logging.debug("Average loss in epoch %d: %.2E", epoch, average_epoch_loss)

@@ -204,7 +204,7 @@ class CrowdSim(object):
         from aemcarl_b200.engine import get_engine
         if not isinstance(action, ActionXY):
             raise NotImplementedError("holonomic ActionXY only (the reference's step() is broken for ActionRot)")
-        eng = get_engine(role="env")
+        eng = get_engine(torch.cuda.current_device(), role="env")
         eng.set_action_space(np.array([[action.vx, action.vy]], dtype=np.float64))
         _, hnext, rewards, info, dmin, nv = self.lookahead_all(eng)
         reward = float(rewards[0, 0].item())

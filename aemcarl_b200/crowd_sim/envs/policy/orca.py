@@ -33,7 +33,7 @@ class ORCA(Policy):
         """orca.py:82-132: agent 0 = self (goal, v_pref), the others are observable states with zero preferred
         velocity; only agent 0's new velocity is read."""
         from aemcarl_b200.engine import get_engine, make_env_params
-        eng = get_engine(role="orca")
+        eng = get_engine(torch.cuda.current_device(), role="orca")
         s = state.self_state
         m = len(state.human_states)
         humans = np.zeros((1, m + 1, 8), dtype=np.float64)

@@ -254,7 +254,7 @@ __global__ void env_apply_kernel(int B, int n, int A, double *__restrict__ robot
     global_time[b] += time_step;
 }
 
-static int g_tile_cap = 0;
+static int g_tile_cap[64] = {0};     // per device: cudaFuncSetAttribute is a per-device setting
 
 cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const double *humans,
                                     const double *new_vel, const double *global_time, const double *actions,
@@ -266,11 +266,13 @@ cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const
     const int tile_cap = side * side;
     const size_t smem = (size_t)(tile_cap + ENV_THREADS + 8 + AEM_MAX_ACTIONS + AEM_MAX_HUMANS * 8 + 9 + 1) * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    if (tile_cap > g_tile_cap) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (tile_cap > g_tile_cap[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(env_lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
-        g_tile_cap = tile_cap;
+        g_tile_cap[dev & 63] = tile_cap;
     }
     env_lookahead_kernel<<<B, ENV_THREADS, smem, st>>>(B, n, A, robot, humans, new_vel, global_time, actions, lut, p,
                                                        amax, tile_cap, rewards, info, dmin, humans_next);
