@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--humans", type=int, default=5)
+    ap.add_argument("--rule", default="circle_crossing", choices=["circle_crossing", "square_crossing"])
+    ap.add_argument("--pool", type=int, default=0, help="scenario pool size (default min(envs, 8192))")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-envs", type=int, default=256, help="--impl reference: envs per step (bounded sample)")
     ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3"],
@@ -202,8 +204,8 @@ def main():
     W = wts.synthetic_weights(0)
     eng.load_weights(W)
     eng.set_precision(args.precision)
-    env = VecCrowdSim(eng, B, n, "circle_crossing", "train", first_case=rank * B, pool_size=B,
-                      case_stride=world * B)
+    pool = args.pool or min(B, 8192)
+    env = VecCrowdSim(eng, B, n, args.rule, "train", first_case=rank * pool, pool_size=pool, case_stride=world * B)
     gbar = env.gamma_bar()
     dev = eng.device
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -306,8 +308,9 @@ def main():
             chosen, reward, done, info, _ = eng.decide_step_host(robot_h, humans_h, time_h, gbar)
             d = done != 0
             if d.any():                            # host-side re-seed of finished episodes (inside the timed region)
-                robot_h[d] = env.pool_robot_h[d]
-                humans_h[d] = env.pool_humans_h[d]
+                src = np.nonzero(d)[0] % pool
+                robot_h[d] = env.pool_robot_h[src]
+                humans_h[d] = env.pool_humans_h[src]
                 time_h[d] = 0.0
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
@@ -333,8 +336,8 @@ def main():
                          "fp32": "f32"}[args.precision],
                "data": "synthetic",
                "config": {"workload": "batched lookahead inference: %d envs x %d humans x 81 actions per GPU, "
-                                      "random-init weights (synthetic_weights seed 0), circle_crossing train-stream "
-                                      "scenarios, predict + step" % (B, n),
+                                      "random-init weights (synthetic_weights seed 0), %s train-stream "
+                                      "scenarios, predict + step" % (B, n, args.rule),
                           "envs_per_gpu": B, "humans": n, "actions": 81, "l2": "flushed between timed iterations "
                           "(256 MB memset outside the event pairs)", "parallelism": "env-sharded x%d" % world},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
