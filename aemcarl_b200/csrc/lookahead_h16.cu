@@ -13,6 +13,7 @@
 //   * weight images img[k/8][n][8] (fp16, hi and lo) stream through a 3 x 16 KB bulk-TMA ring.
 // Layout of every layer (N / K permutation and padding) is defined in capi.cu pack_h16.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "aem_common.cuh"
 #include "tc_common.cuh"
@@ -338,6 +339,9 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     }
     __syncthreads();
     int nev = 0;
+    // the two CTAs of an SM run identical work: offset the second one so that its epilogues fall into the first one's
+    // MMA / commit waits instead of colliding with its epilogues
+    if ((int)blockIdx.x >= (int)gridDim.x / 2 && args.stagger_ns > 0) __nanosleep((unsigned)args.stagger_ns);
 
 #define GROUP_BARRIER()                     \
     do {                                    \
@@ -833,7 +837,14 @@ cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStrea
     if (ntiles <= 0) return cudaSuccess;
     const int maxgrid = 2 * h->num_sms;        // two CTAs (two tiles in flight) per SM
     const int grid = ntiles < maxgrid ? ntiles : maxgrid;
-    h16::lookahead_h16_kernel<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(a);
+    LookaheadArgs b = a;
+    static int stagger = -1;
+    if (stagger < 0) {
+        const char *e = getenv("AEM_H16_STAGGER_NS");
+        stagger = e ? atoi(e) : 0;
+    }
+    b.stagger_ns = stagger;
+    h16::lookahead_h16_kernel<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
     return cudaGetLastError();
 }
 

@@ -70,7 +70,7 @@ class Engine:
 
     def set_precision(self, precision):
         """'fp32' (FFMA kernel, default), 'tf32x3' (tcgen05, one tile / SM) or 'fp16x3' (tcgen05, two tiles / SM)"""
-        mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2, 0: 0, 1: 1, 2: 2}[precision]
+        mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2, "fp16x3q": 3, 0: 0, 1: 1, 2: 2, 3: 3}[precision]
         check(self.lib.aem_set_precision(self.h, mode))
         self.precision = mode
 

@@ -32,7 +32,7 @@ def actions():
     return np.load(os.path.join(GOLDEN, "action_rotate.npz"))["actions"]
 
 
-@pytest.fixture(scope="session", params=["fp32", "tf32x3", "fp16x3"])
+@pytest.fixture(scope="session", params=["fp32", "tf32x3", "fp16x3", "fp16x3q"])
 def engine(actions, request):
     import torch
     if not torch.cuda.is_available():
