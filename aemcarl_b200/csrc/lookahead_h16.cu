@@ -13,7 +13,10 @@
 //   * weight images img[k/8][n][8] (fp16, hi and lo) stream through a 3 x 16 KB bulk-TMA ring.
 // Layout of every layer (N / K permutation and padding) is defined in capi.cu pack_h16.
 #include <cuda_fp16.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
+#include <unistd.h>
 
 #include "aem_common.cuh"
 #include "tc_common.cuh"
@@ -171,18 +174,21 @@ __device__ __forceinline__ void rotate13(const float *s, float *o)   // cadrl.py
 }
 
 // ------------------------------------------------------------------------------------------------
-// issuer (thread 0 for the bulk copies / commits; warp 0 issues MMAs warp-uniformly)
+// weight ring: consumer = warp 0 (issues the MMAs), producer = lane 0 of warp 1 (requests the bulk copies)
 // ------------------------------------------------------------------------------------------------
-struct LayerInfo { int off_hi, off_lo, bytes, nsplit; };      // 16 B per layer, kept in shared memory
+// Neither role works between a group barrier and the group's first MMA: the ring read position travels in registers
+// (IssReg) while a group is issued and at every commit lane 0 publishes how many chunks the committed MMAs cover; the
+// producer, after waiting on an event like every other thread, releases exactly those slots and requests the next chunks
+// from a flat table of {offset, bytes} built once per CTA.
 struct Issuer {
-    uint8_t *wbuf;
-    uint64_t *wfull;
-    const __half *img;
-    const LayerInfo *layers;
-    int nloaded, nused, nfree;
-    int pf_stage, pf_idx, pf_part;
+    int used_ev[NEV];               // consumer -> producer: chunks consumed when event e was committed, at [e % NEV]
+    int nused, ubuf, upar;          // consumer: running chunk count, ring slot and mbarrier parity of the next chunk
+    int nloaded, nfree, lbuf;       // producer: chunks requested / released, ring slot of the next request
+    int pf_cur, pf_end, pf_stage;   // producer: cursor into the chunk table; stage -1 = waiting for the ACT decision, -2 = done
     int tiles_left;
 };
+struct IssReg { uint32_t buf, par, n; };
+constexpr int MAX_CHUNKS = 128;
 __device__ __forceinline__ int stage_len(int st) { return st == 0 ? 3 : (st == 1 ? 5 : 23); }
 __device__ __forceinline__ int layer_at(int st, int idx)
 {
@@ -190,38 +196,50 @@ __device__ __forceinline__ int layer_at(int st, int idx)
     if (st == 1) return idx == 0 ? TL_Z1 : (idx == 1 ? TL_Z2 : (idx == 2 ? TL_R1 : (idx == 3 ? TL_R2 : TL_Q)));
     return idx < 21 ? TL_ENC + idx : (idx == 21 ? TL_A0 : TL_A2);
 }
-__device__ __noinline__ void prefetch(Issuer *s)
+// chunk table entry: offset into the image in units of 8 halves (16 B) | bytes / 16 << 20
+__device__ void build_chunk_table(const TcLayer *layers, uint32_t *chunks, int *stage_beg)
 {
-    while (s->pf_stage >= 0 && s->nloaded - s->nfree < NBUF) {
-        const LayerInfo L = s->layers[layer_at(s->pf_stage, s->pf_idx)];
-        const int nsplit = L.nsplit;                   // number of k-halves per image (1 or 2)
-        const int part = s->pf_part / nsplit, sub = s->pf_part - part * nsplit;
-        const int bytes = L.bytes / nsplit;
-        const int buf = s->nloaded % NBUF;
-        mbar_expect_tx(&s->wfull[buf], (uint32_t)bytes);
-        bulk_g2s(s->wbuf + (size_t)buf * WBUF_BYTES, s->img + (part ? L.off_lo : L.off_hi) + sub * (bytes / 2),
-                 (uint32_t)bytes, &s->wfull[buf]);
-        ++s->nloaded;
-        if (++s->pf_part == 2 * nsplit) {
-            s->pf_part = 0;
-            if (++s->pf_idx == stage_len(s->pf_stage)) {
-                s->pf_idx = 0;
-                if (s->pf_stage == 2) {
-                    if (s->tiles_left > 0) { --s->tiles_left; s->pf_stage = 0; } else s->pf_stage = -2;
-                } else {
-                    s->pf_stage = -1;
-                }
-            }
+    int n = 0;
+    for (int st = 0; st < 3; ++st) {
+        stage_beg[st] = n;
+        for (int i = 0; i < stage_len(st); ++i) {
+            const TcLayer L = layers[layer_at(st, i)];
+            const int nsplit = L.bias_off;                 // h16 tables carry the k-split count in this field
+            const int bytes = L.bytes / nsplit;
+            for (int part = 0; part < 2; ++part)
+                for (int sub = 0; sub < nsplit; ++sub)
+                    chunks[n++] = (uint32_t)(((part ? L.off_lo : L.off_hi) + sub * (bytes / 2)) >> 3) | ((uint32_t)(bytes >> 4) << 20);
         }
     }
+    stage_beg[3] = n;
 }
-__device__ __noinline__ uint32_t take_chunk_addr(Issuer *s)
+__device__ __forceinline__ void set_stage(Issuer *s, const int *stage_beg, int st)
 {
-    while (s->nloaded <= s->nused) prefetch(s);
-    const int buf = s->nused % NBUF;
-    mbar_wait(&s->wfull[buf], (uint32_t)((s->nused / NBUF) & 1));
-    ++s->nused;
-    return smem_u32(s->wbuf + (size_t)buf * WBUF_BYTES);
+    s->pf_stage = st;
+    if (st >= 0) { s->pf_cur = stage_beg[st]; s->pf_end = stage_beg[st + 1]; }
+}
+// request as many chunks as the ring has room for (producer thread only)
+__device__ __forceinline__ void prefetch(Issuer *s, const uint32_t *chunks, const int *stage_beg, uint8_t *wbuf, uint64_t *wfull,
+                                         const __half *img)
+{
+    int stage = s->pf_stage;
+    int nloaded = s->nloaded;
+    int room = NBUF - (nloaded - s->nfree);
+    if (stage < 0 || room <= 0) return;
+    int cur = s->pf_cur, end = s->pf_end, lbuf = s->lbuf, tiles_left = s->tiles_left;
+    while (room > 0) {
+        const uint32_t c = chunks[cur];
+        const uint32_t bytes = (c >> 20) << 4;
+        mbar_expect_tx(&wfull[lbuf], bytes);
+        bulk_g2s(wbuf + (size_t)lbuf * WBUF_BYTES, img + (size_t)(c & 0xFFFFFu) * 8, bytes, &wfull[lbuf]);
+        ++nloaded; --room;
+        if (++lbuf == NBUF) lbuf = 0;
+        if (++cur == end) {
+            if (stage == 2 && tiles_left > 0) { --tiles_left; stage = 0; cur = stage_beg[0]; end = stage_beg[1]; }
+            else { stage = (stage == 2) ? -2 : -1; break; }
+        }
+    }
+    s->nloaded = nloaded; s->lbuf = lbuf; s->pf_cur = cur; s->pf_end = end; s->pf_stage = stage; s->tiles_left = tiles_left;
 }
 __device__ __forceinline__ bool elect_one()
 {
@@ -244,7 +262,8 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 //   a_base + HSTRIDE * (ks / KSH) + 8 * (ks % KSH), lo part LO columns further.  SPECIAL: step-1 images use the
 //   k-steps {1, 3} of A1 (the x slots).
 template <int N, int KS, int KSH, int HSTRIDE, int LO, bool SPECIAL, int SPLIT>
-__device__ __forceinline__ void issue_t(Issuer *iss, int lane, uint32_t tm, uint32_t a_base, uint32_t d, bool accumulate)
+__device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t ring, uint32_t tm, uint32_t a_base, uint32_t d,
+                                        bool accumulate)
 {
     constexpr uint32_t LBO = (uint32_t)N * 16;
     constexpr uint64_t DHI = ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
@@ -256,10 +275,10 @@ __device__ __forceinline__ void issue_t(Issuer *iss, int lane, uint32_t tm, uint
     for (int part = 0; part < 2; ++part) {               // part 0: W_hi (A_hi and A_lo passes), part 1: W_lo (A_hi pass)
 #pragma unroll
         for (int sub = 0; sub < SPLIT; ++sub) {
-            uint32_t wa = 0;
-            if (lane == 0) wa = take_chunk_addr(iss);
-            wa = __shfl_sync(0xffffffffu, wa, 0);
-            const uint32_t base = (wa & 0x3FFFFu) >> 4;
+            mbar_wait(&wfull[r.buf], r.par);         // all lanes, uniform
+            const uint32_t base = ((ring + r.buf * (uint32_t)WBUF_BYTES) & 0x3FFFFu) >> 4;
+            if (++r.buf == (uint32_t)NBUF) { r.buf = 0; r.par ^= 1u; }
+            ++r.n;
 #pragma unroll
             for (int kk = 0; kk < KSS; ++kk) {
                 const int ks = sub * KSS + kk;
@@ -280,10 +299,10 @@ __device__ __forceinline__ void issue_t(Issuer *iss, int lane, uint32_t tm, uint
 }
 // shorthand for the three operand layouts
 // (images larger than one ring slot -- N * K = 8192 -- are streamed as two k-halves: SPLIT = 2)
-#define ISSUE_K64(N, a, d, acc) issue_t<N, 4, 4, 0, 32, false, ((N) * 64 > 6144 ? 2 : 1)>(iss_p, lane, tm, a, d, acc)
-#define ISSUE_K64S(N, a, d) issue_t<N, 2, 4, 0, 32, true, 1>(iss_p, lane, tm, a, d, false)        /* step-1 images   */
-#define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 32, false, 2>(iss_p, lane, tm, a, d, false)      /* in-place [64|64] */
-#define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 24, false, 1>(iss_p, lane, tm, a, d, acc)    /* in-place [48|48] */
+#define ISSUE_K64(N, a, d, acc) issue_t<N, 4, 4, 0, 32, false, ((N) * 64 > 6144 ? 2 : 1)>(ir, wfull, ring, tm, a, d, acc)
+#define ISSUE_K64S(N, a, d) issue_t<N, 2, 4, 0, 32, true, 1>(ir, wfull, ring, tm, a, d, false)        /* step-1 images   */
+#define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 32, false, 2>(ir, wfull, ring, tm, a, d, false)      /* in-place [64|64] */
+#define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 24, false, 1>(ir, wfull, ring, tm, a, d, acc)    /* in-place [48|48] */
 
 __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArgs args)
 {
@@ -300,7 +319,8 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     uint64_t *evb = wfull + NBUF;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(evb + NEV);
     __shared__ Issuer s_iss;
-    __shared__ LayerInfo s_layers[TL_NUM];     // a global-memory table would cost an L2 round trip per prefetched chunk
+    __shared__ uint32_t s_chunks[MAX_CHUNKS];
+    __shared__ int s_stage_beg[4];
 
     const NetParams &net = args.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -317,24 +337,23 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     }
     if (warp == 0) tmem_alloc(tmem_slot, 256);
     for (int i = tid; i < net.h16_pblk_floats; i += NT) pblk[i] = net.h16_pblk[i];
-    if (tid < TL_NUM) {
-        const TcLayer L = net.h16_layers_d[tid];
-        s_layers[tid].off_hi = L.off_hi; s_layers[tid].off_lo = L.off_lo; s_layers[tid].bytes = L.bytes;
-        s_layers[tid].nsplit = L.bias_off;     // h16 tables carry the k-split count in this field
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = *tmem_slot;
     const uint32_t tl = tm + lane_base;
-    Issuer *iss_p = &s_iss;
-    if (tid == 0) {
-        s_iss.wbuf = wbuf; s_iss.wfull = wfull; s_iss.img = net.h16_img; s_iss.layers = s_layers;
-        s_iss.nloaded = s_iss.nused = s_iss.nfree = 0;
-        s_iss.pf_stage = -2; s_iss.pf_idx = 0; s_iss.pf_part = 0; s_iss.tiles_left = 0;
+    const uint32_t ring = smem_u32(wbuf);
+    if (tid == 32) {
+        build_chunk_table(net.h16_layers_d, s_chunks, s_stage_beg);
+        for (int i = 0; i < NEV; ++i) s_iss.used_ev[i] = 0;
+        s_iss.nused = s_iss.ubuf = s_iss.upar = 0;
+        s_iss.nloaded = s_iss.nfree = s_iss.lbuf = 0;
+        s_iss.pf_cur = s_iss.pf_end = 0; s_iss.tiles_left = 0;
+        s_iss.pf_stage = -2;
         if ((int)blockIdx.x < ntiles) {
-            s_iss.pf_stage = 0;
             s_iss.tiles_left = (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x;
+            set_stage(&s_iss, s_stage_beg, 0);
+            prefetch(&s_iss, s_chunks, s_stage_beg, wbuf, wfull, net.h16_img);
         }
     }
     __syncthreads();
@@ -356,15 +375,28 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         mbar_wait(&evb[(e) % NEV], (uint32_t)(((e) / NEV) & 1));        \
         tc_fence_after();                                               \
     } while (0)
-#define ISSUER_DRAIN(e)                                                 \
-    do {                                                                \
-        prefetch(iss_p);                                                \
-        mbar_wait(&evb[(e) % NEV], (uint32_t)(((e) / NEV) & 1));        \
-        s_iss.nfree = s_iss.nused;                                      \
-        prefetch(iss_p);                                                \
+#define ISSUE_BEGIN() \
+    IssReg ir;        \
+    ir.buf = (uint32_t)s_iss.ubuf; ir.par = (uint32_t)s_iss.upar; ir.n = (uint32_t)s_iss.nused
+#define ISSUE_COMMIT(e)                                                         \
+    do {                                                                        \
+        if (lane == 0) { s_iss.used_ev[(e) % NEV] = (int)ir.n; __threadfence_block(); COMMIT(e); } /* publish BEFORE the commit */ \
+        __syncwarp();                                                           \
+    } while (0)
+#define ISSUE_END() \
+    do { if (lane == 0) { s_iss.nused = (int)ir.n; s_iss.ubuf = (int)ir.buf; s_iss.upar = (int)ir.par; } } while (0)
+// after an event has been waited on: the producer releases the ring slots its MMAs read and requests the next chunks
+#define PRODUCE(e)                                                                    \
+    do {                                                                              \
+        if (tid == 32) {                                                              \
+            s_iss.nfree = s_iss.used_ev[(e) % NEV];                                   \
+            prefetch(&s_iss, s_chunks, s_stage_beg, wbuf, wfull, net.h16_img);        \
+        }                                                                             \
+        __syncwarp();                                                                 \
     } while (0)
 
     const float *PB = pblk;
+#define MARK() do { if (args.dbg && (tid == 0 || tid == 32)) { ((volatile long long *)args.dbg)[2 * blockIdx.x + (tid == 32)] = __LINE__ + 10000ll * tile; __threadfence_system(); } } while (0)
 
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -437,25 +469,31 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         for (int step = 1; step <= max_steps; ++step) {
             const bool kfull = step > 1;
             // ---- z1 -> in place A2
-            GROUP_BARRIER();
+            MARK(); GROUP_BARRIER();
             const int e_z1 = nev++;
             if (warp == 0) {
+                ISSUE_BEGIN();
                 if (kfull) ISSUE_K64(128, A1, D1, false);
                 else ISSUE_K64S(128, A1, D1);
-                if (lane == 0) { COMMIT(e_z1); ISSUER_DRAIN(e_z1); }
+                ISSUE_COMMIT(e_z1);
+                ISSUE_END();
             }
             __syncwarp();
-            WAIT_EVENT(e_z1);
+            MARK(); WAIT_EVENT(e_z1); MARK();
+            PRODUCE(e_z1); MARK();
             relu_inplace<64>(tl + D1 + 64 * half, PB + PB_Z1 + 64 * half);
             // ---- z
-            GROUP_BARRIER();
+            MARK(); GROUP_BARRIER();
             const int e_z2 = nev++;
             if (warp == 0) {
+                ISSUE_BEGIN();
                 ISSUE_K128(64, D1, D2);
-                if (lane == 0) { COMMIT(e_z2); ISSUER_DRAIN(e_z2); }
+                ISSUE_COMMIT(e_z2);
+                ISSUE_END();
             }
             __syncwarp();
-            WAIT_EVENT(e_z2);
+            MARK(); WAIT_EVENT(e_z2); MARK();
+            PRODUCE(e_z2); MARK();
             {
                 const float *b = PB + PB_Z2 + 32 * half;
                 float v[32];
@@ -467,23 +505,29 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             }
             if (kfull) {
                 // ---- r1 -> in place A2, r, [r*h ; x] -> A3
-                GROUP_BARRIER();
+                MARK(); GROUP_BARRIER();
                 const int e_r1 = nev++;
                 if (warp == 0) {
+                    ISSUE_BEGIN();
                     ISSUE_K64(128, A1, D1, false);
-                    if (lane == 0) { COMMIT(e_r1); ISSUER_DRAIN(e_r1); }
+                    ISSUE_COMMIT(e_r1);
+                    ISSUE_END();
                 }
                 __syncwarp();
-                WAIT_EVENT(e_r1);
+                MARK(); WAIT_EVENT(e_r1); MARK();
+                PRODUCE(e_r1); MARK();
                 relu_inplace<64>(tl + D1 + 64 * half, PB + PB_R1 + 64 * half);
-                GROUP_BARRIER();
+                MARK(); GROUP_BARRIER();
                 const int e_r2 = nev++;
                 if (warp == 0) {
+                    ISSUE_BEGIN();
                     ISSUE_K128(64, D1, D2);
-                    if (lane == 0) { COMMIT(e_r2); ISSUER_DRAIN(e_r2); }
+                    ISSUE_COMMIT(e_r2);
+                    ISSUE_END();
                 }
                 __syncwarp();
-                WAIT_EVENT(e_r2);
+                MARK(); WAIT_EVENT(e_r2); MARK();
+                PRODUCE(e_r2); MARK();
                 {
                     const float *b = PB + PB_R2 + 32 * half;
 #pragma unroll
@@ -502,15 +546,18 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 }
             }
             // ---- q, h = (1 - z) h + z q
-            GROUP_BARRIER();
+            MARK(); GROUP_BARRIER();
             const int e_q = nev++;
             if (warp == 0) {
+                ISSUE_BEGIN();
                 if (kfull) ISSUE_K64(64, A3, D2, false);
                 else ISSUE_K64S(64, A1, D2);
-                if (lane == 0) { COMMIT(e_q); ISSUER_DRAIN(e_q); }
+                ISSUE_COMMIT(e_q);
+                ISSUE_END();
             }
             __syncwarp();
-            WAIT_EVENT(e_q);
+            MARK(); WAIT_EVENT(e_q); MARK();
+            PRODUCE(e_q); MARK();
             {
                 const float *b = PB + PB_Q + 32 * half;
                 const float *pw = PB + PB_PW + 25 * half;
@@ -564,13 +611,14 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 __syncthreads();
                 cont = s_flag[0] && step < max_steps;
             }
-            if (tid == 0 && s_iss.pf_stage == -1) {
+            if (tid == 32 && s_iss.pf_stage == -1) {
                 int ns;
                 if (cont) ns = 1;
                 else if (args.mode == 2) {
                     if (s_iss.tiles_left > 0) { --s_iss.tiles_left; ns = 0; } else ns = -2;
                 } else ns = 2;
-                s_iss.pf_stage = ns; s_iss.pf_idx = 0; s_iss.pf_part = 0;
+                set_stage(&s_iss, s_stage_beg, ns);
+                prefetch(&s_iss, s_chunks, s_stage_beg, wbuf, wfull, net.h16_img);
             }
             if (!cont) break;
         }
@@ -605,15 +653,18 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         for (int l = 0; l < 3; ++l) {
             const int PBL = PB_ENC + PB_ENC_STRIDE * l;
             const float *LN = PB + PB_LN + l * 200 + 25 * half;
-            GROUP_BARRIER();
+            MARK(); GROUP_BARRIER();
             const int e_in = nev++;
             if (warp == 0) {
+                ISSUE_BEGIN();
                 ISSUE_K64(96, AE, DIN, false);
                 ISSUE_K64(96, AE, DIN + 96, false);
-                if (lane == 0) { COMMIT(e_in); ISSUER_DRAIN(e_in); }
+                ISSUE_COMMIT(e_in);
+                ISSUE_END();
             }
             __syncwarp();
-            WAIT_EVENT(e_in);
+            MARK(); WAIT_EVENT(e_in); MARK();
+            PRODUCE(e_in); MARK();
             float o[32];
             {
                 float qh[25];
@@ -670,14 +721,17 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             }
             st_pack<32>(tl + AATT + 16 * half, tl + AATT + 32 + 16 * half, o);
             // ---- out_proj + residual + LayerNorm1
-            GROUP_BARRIER();
+            MARK(); GROUP_BARRIER();
             const int e_out = nev++;
             if (warp == 0) {
+                ISSUE_BEGIN();
                 ISSUE_K64(64, AATT, DOUT, false);
-                if (lane == 0) { COMMIT(e_out); ISSUER_DRAIN(e_out); }
+                ISSUE_COMMIT(e_out);
+                ISSUE_END();
             }
             __syncwarp();
-            WAIT_EVENT(e_out);
+            MARK(); WAIT_EVENT(e_out); MARK();
+            PRODUCE(e_out); MARK();
             {
                 const float *b = PB + PBL + PBE_OUT + 32 * half;
                 float s = 0.0f;
@@ -708,32 +762,43 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, a);
             }
             // ---- FFN in two hidden chunks, converted in place
-            GROUP_BARRIER();
+            MARK(); GROUP_BARRIER();
             const int e_f1a = nev++;
             const int e_f1b = nev++;
             if (warp == 0) {
+                ISSUE_BEGIN();
                 ISSUE_K64(96, AE, DF1A, false);
-                if (lane == 0) COMMIT(e_f1a);
-                __syncwarp();
+                ISSUE_COMMIT(e_f1a);
                 ISSUE_K64(96, AE, DF1B, false);
-                if (lane == 0) { COMMIT(e_f1b); ISSUER_DRAIN(e_f1b); }
+                ISSUE_COMMIT(e_f1b);
+                ISSUE_END();
             }
             __syncwarp();
-            WAIT_EVENT(e_f1a);
+            MARK(); WAIT_EVENT(e_f1a); MARK();
+            PRODUCE(e_f1a); MARK();
             relu_inplace<48>(tl + DF1A + 48 * half, PB + PBL + PBE_F1A + 48 * half);
-            GROUP_BARRIER();       // F1B has completed as well (drained above): AE is dead, D_F2 may overwrite it
-            if (warp == 0) ISSUE_K96(64, DF1A, DF2, false);
+            MARK(); GROUP_BARRIER();
+            if (warp == 0) {
+                WAIT_EVENT(e_f1b);     // F1B reads AE, which D_F2 aliases: it must have completed before linear2 starts
+                ISSUE_BEGIN();
+                ISSUE_K96(64, DF1A, DF2, false);
+                ISSUE_END();
+            }
             __syncwarp();
-            WAIT_EVENT(e_f1b);
+            MARK(); WAIT_EVENT(e_f1b); MARK();
+            PRODUCE(e_f1b); MARK();
             relu_inplace<48>(tl + DF1B + 48 * half, PB + PBL + PBE_F1B + 48 * half);
-            GROUP_BARRIER();
+            MARK(); GROUP_BARRIER();
             const int e_f2 = nev++;
             if (warp == 0) {
+                ISSUE_BEGIN();
                 ISSUE_K96(64, DF1B, DF2, true);
-                if (lane == 0) { COMMIT(e_f2); ISSUER_DRAIN(e_f2); }
+                ISSUE_COMMIT(e_f2);
+                ISSUE_END();
             }
             __syncwarp();
-            WAIT_EVENT(e_f2);
+            MARK(); WAIT_EVENT(e_f2); MARK();
+            PRODUCE(e_f2); MARK();
             {
                 const float *b = PB + PBL + PBE_F2 + 32 * half;
                 float s = 0.0f;
@@ -768,23 +833,29 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         }
 
         // ---------------- phase 3: action_mlp ----------------
-        GROUP_BARRIER();
+        MARK(); GROUP_BARRIER();
         const int e_a0 = nev++;
         if (warp == 0) {
+            ISSUE_BEGIN();
             ISSUE_K64(128, AE, DA0, false);
-            if (lane == 0) { COMMIT(e_a0); ISSUER_DRAIN(e_a0); }
+            ISSUE_COMMIT(e_a0);
+            ISSUE_END();
         }
         __syncwarp();
-        WAIT_EVENT(e_a0);
+        MARK(); WAIT_EVENT(e_a0); MARK();
+        PRODUCE(e_a0); MARK();
         relu_inplace<64>(tl + DA0 + 64 * half, PB + PB_A0 + 64 * half);
-        GROUP_BARRIER();
+        MARK(); GROUP_BARRIER();
         const int e_a2 = nev++;
         if (warp == 0) {
+            ISSUE_BEGIN();
             ISSUE_K128(64, DA0, DA2);
-            if (lane == 0) { COMMIT(e_a2); ISSUER_DRAIN(e_a2); }
+            ISSUE_COMMIT(e_a2);
+            ISSUE_END();
         }
         __syncwarp();
-        WAIT_EVENT(e_a2);
+        MARK(); WAIT_EVENT(e_a2); MARK();
+        PRODUCE(e_a2); MARK();
         {
             const float *b = PB + PB_A2 + 32 * half;
             const float *w4 = PB + PB_A4 + 25 * half;
@@ -811,15 +882,20 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         __syncthreads();
     }
 
+    { const int tile = -1; MARK(); }
     tmem_wait_st();
     tmem_wait_ld();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tm, 256);
+    { const int tile = -2; MARK(); }
 #undef GROUP_BARRIER
 #undef COMMIT
 #undef WAIT_EVENT
-#undef ISSUER_DRAIN
+#undef ISSUE_BEGIN
+#undef ISSUE_COMMIT
+#undef ISSUE_END
+#undef PRODUCE
 }
 
 }  // namespace h16
@@ -844,6 +920,25 @@ cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStrea
         stagger = e ? atoi(e) : 0;
     }
     b.stagger_ns = stagger;
+    if (getenv("AEM_H16_WATCHDOG")) {       // debug: report where CTA 0 is stuck instead of hanging
+        long long *host = nullptr;
+        cudaHostAlloc((void **)&host, 16 * 1024, cudaHostAllocMapped);
+        for (int i = 0; i < 2048; ++i) host[i] = 0;
+        b.dbg = host;
+        h16::lookahead_h16_kernel<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
+        for (int i = 0; i < 300; ++i) {
+            if (cudaStreamQuery(st) != cudaErrorNotReady) { cudaFreeHost(host); return cudaGetLastError(); }
+            struct timespec ts = {0, 10000000};
+            nanosleep(&ts, nullptr);
+        }
+        for (int c = 0; c < grid && c < 1024; ++c) {
+            const long long a0 = ((volatile long long *)host)[2 * c], a1 = ((volatile long long *)host)[2 * c + 1];
+            if (a0 / 10000 != -2 || a1 / 10000 != -2)
+                fprintf(stderr, "h16 watchdog: CTA %d stuck: thread 0 tile %lld line %lld, thread 32 tile %lld line %lld\n", c,
+                        a0 / 10000, a0 % 10000, a1 / 10000, a1 % 10000);
+        }
+        _exit(3);
+    }
     h16::lookahead_h16_kernel<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
     return cudaGetLastError();
 }

@@ -146,14 +146,19 @@ __device__ __forceinline__ void rotate13(const float *s, float *o)   // cadrl.py
 // issuer
 // ------------------------------------------------------------------------------------------------
 struct LayerInfo { int off_hi, off_lo, bytes, nsplit; };
-// Weight ring bookkeeping.  Lives in shared memory and is touched by lane 0 of warp 0 only, always while the tensor
-// pipe is busy (right after a commit) or at the ACT decision, never between the group barrier and the first MMA:
-// the read position of the ring travels in registers (IssReg) while a group is issued.
+// Weight ring bookkeeping (shared memory).  Two single-thread roles, neither on the path between a group barrier and the
+// group's first MMA:
+//   consumer = warp 0: the ring read position travels in registers (IssReg) while a group is issued; after the commit
+//              lane 0 publishes the running chunk count in used[group & 1];
+//   producer = lane 0 of warp 1: after each group barrier it releases the slots of all PREVIOUS groups (complete: every
+//              thread waited on their events before the barrier) and requests the next chunks, in parallel with warp 0
+//              issuing and the tensor pipe working; it also switches stages at the ACT decision.
 struct Issuer {
-    int nused, nloaded, nfree;      // chunks consumed by issued MMAs / requested from L2 / released for refill
-    int lbuf;                       // ring slot of the next request
-    int ubuf, upar;                 // ring slot and mbarrier parity of the next chunk to consume
-    int pf_cur, pf_end, pf_stage;   // cursor into the chunk table; stage -1 = waiting for the ACT decision, -2 = done
+    int used[2];                    // consumer -> producer: chunks consumed up to and including group e, at [e & 1]
+    int ubuf, upar;                 // consumer: ring slot and mbarrier parity of the next chunk to consume
+    int nloaded, nfree;             // producer: chunks requested from L2 / released for refill
+    int lbuf;                       // producer: ring slot of the next request
+    int pf_cur, pf_end, pf_stage;   // producer: cursor into the chunk table; stage -1 = waiting for the ACT decision, -2 = done
     int tiles_left;
 };
 struct IssReg { uint32_t buf, par, n; };
@@ -312,9 +317,9 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
     const uint32_t tm = *tmem_slot;
     const uint32_t tl = tm + lane_base;
     const uint32_t ring = smem_u32(wbuf);
-    if (tid == 0) {
+    if (tid == 32) {
         build_chunk_table(s_layers, s_chunks, s_stage_beg);
-        s_iss.nloaded = s_iss.nused = s_iss.nfree = 0;
+        s_iss.nloaded = s_iss.nfree = s_iss.used[0] = s_iss.used[1] = 0;
         s_iss.lbuf = s_iss.ubuf = s_iss.upar = 0;
         s_iss.pf_cur = s_iss.pf_end = 0; s_iss.tiles_left = 0;
         s_iss.pf_stage = -2;
@@ -355,13 +360,18 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
         if (lane == 0) {                                                              \
             TS();                                                                     \
             COMMIT(e);                                                                \
-            const int used0 = s_iss.nused;                                            \
-            s_iss.nfree = used0;                                                      \
-            s_iss.nused = used0 + (int)ir.n;                                          \
+            s_iss.used[(e) & 1] = s_iss.used[((e) & 1) ^ 1] + (int)ir.n;              \
             s_iss.ubuf = (int)ir.buf; s_iss.upar = (int)ir.par;                       \
-            prefetch(&s_iss, s_chunks, s_stage_beg, wbuf, wfull, net.q16_img);        \
             TS();                                                                     \
         }                                                                             \
+    } while (0)
+#define PRODUCE(e)                                                                    \
+    do {                                                                              \
+        if (tid == 32) {                                                              \
+            s_iss.nfree = s_iss.used[((e) & 1) ^ 1];                                  \
+            prefetch(&s_iss, s_chunks, s_stage_beg, wbuf, wfull, net.q16_img);        \
+        }                                                                             \
+        __syncwarp();                                                                 \
     } while (0)
 
     const float *PB = pblk;
@@ -457,6 +467,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
             // ---- z1 | r1 (one N = 256 group; step 1 needs z1 only)
             GROUP_BARRIER();
             const int e_1 = nev++;
+            PRODUCE(e_1);
             if (warp == 0) {
                 ISSUE_BEGIN();
                 if (kfull) ISSUE_K64(256, A1, D1);
@@ -470,6 +481,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
             // ---- z2 and r2 together
             GROUP_BARRIER();
             const int e_2 = nev++;
+            PRODUCE(e_2);
             if (warp == 0) {
                 ISSUE_BEGIN();
                 ISSUE_K128(64, D1, D2Z);
@@ -504,6 +516,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
             // ---- q, h = (1 - z) h + z q
             GROUP_BARRIER();
             const int e_q = nev++;
+            PRODUCE(e_q);
             if (warp == 0) {
                 ISSUE_BEGIN();
                 ISSUE_K64(64, kfull ? A3 : A1, D2Z);
@@ -566,7 +579,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
                 __syncthreads();
                 cont = s_flag[0] && step < max_steps;
             }
-            if (tid == 0 && s_iss.pf_stage == -1) {
+            if (tid == 32 && s_iss.pf_stage == -1) {
                 int ns;
                 if (cont) ns = 1;
                 else if (args.mode == 2) {
@@ -611,6 +624,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
             const float *LN = PB + PB_LN + l * 200 + Q0;
             GROUP_BARRIER();
             const int e_in = nev++;
+            PRODUCE(e_in);
             if (warp == 0) {
                 ISSUE_BEGIN();
                 ISSUE_K64(192, AE, DIN);
@@ -684,6 +698,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
             // ---- out_proj + residual + LayerNorm1
             GROUP_BARRIER();
             const int e_out = nev++;
+            PRODUCE(e_out);
             if (warp == 0) {
                 ISSUE_BEGIN();
                 ISSUE_K64(64, AATT, DOUT);
@@ -697,6 +712,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
                     // ---- FFN: linear1 (one N = 192 group, converted in place), linear2, residual + LayerNorm2
                     GROUP_BARRIER();
                     const int e_f1 = nev++;
+                    PRODUCE(e_f1);
                     if (warp == 0) {
                         ISSUE_BEGIN();
                         ISSUE_K64(192, AE, DF1);
@@ -707,6 +723,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
                     relu_inplace<48>(tl + DF1 + 48 * qd, PB + PBL + PBE_F1 + 48 * qd);
                     GROUP_BARRIER();
                     const int e_f2 = nev++;
+                    PRODUCE(e_f2);
                     if (warp == 0) {
                         ISSUE_BEGIN();
                         ISSUE_K192(64, DF1, DF2);
@@ -764,6 +781,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
         // ---------------- phase 3: action_mlp ----------------
         GROUP_BARRIER();
         const int e_a0 = nev++;
+        PRODUCE(e_a0);
         if (warp == 0) {
             ISSUE_BEGIN();
             ISSUE_K64(128, AE, DA0);
@@ -774,6 +792,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
         relu_inplace<32>(tl + DA0 + 32 * qd, PB + PB_A0 + 32 * qd);
         GROUP_BARRIER();
         const int e_a2 = nev++;
+        PRODUCE(e_a2);
         if (warp == 0) {
             ISSUE_BEGIN();
             ISSUE_K128(64, DA0, DA2);
@@ -816,6 +835,7 @@ __global__ void __launch_bounds__(NT, 1) lookahead_q16_kernel(const LookaheadArg
 #undef WAIT_EVENT
 #undef ISSUE_BEGIN
 #undef ISSUE_END
+#undef PRODUCE
 }
 
 }  // namespace q16

@@ -69,7 +69,8 @@ class Engine:
         check(self.lib.aem_set_act_mode(self.h, int(bool(act_fixed)), int(act_steps)))
 
     def set_precision(self, precision):
-        """'fp32' (FFMA kernel, default), 'tf32x3' (tcgen05, one tile / SM) or 'fp16x3' (tcgen05, two tiles / SM)"""
+        """'fp32' (FFMA kernel, default), 'tf32x3' (tcgen05, one tile / SM), 'fp16x3' (tcgen05, two tiles / SM, two threads per
+        row) or 'fp16x3q' (tcgen05, one tile / SM, four threads per row: the fastest)"""
         mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2, "fp16x3q": 3, 0: 0, 1: 1, 2: 2, 3: 3}[precision]
         check(self.lib.aem_set_precision(self.h, mode))
         self.precision = mode

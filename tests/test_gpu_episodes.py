@@ -39,7 +39,7 @@ def oracle_episodes(po, W, actions, robot, humans, max_steps=110):
     return codes, length
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16x3q"])
 def test_500_test_cases_outcomes_match_oracle(oracle, actions, precision):
     eng = Engine(0)
     eng.set_action_space(actions)
