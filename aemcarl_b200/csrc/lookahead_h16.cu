@@ -197,7 +197,7 @@ __device__ __forceinline__ int layer_at(int st, int idx)
     return idx < 21 ? TL_ENC + idx : (idx == 21 ? TL_A0 : TL_A2);
 }
 // chunk table entry: offset into the image in units of 8 halves (16 B) | bytes / 16 << 20
-__device__ void build_chunk_table(const TcLayer *layers, uint32_t *chunks, int *stage_beg)
+__device__ __noinline__ void build_chunk_table(const TcLayer *layers, uint32_t *chunks, int *stage_beg)
 {
     int n = 0;
     for (int st = 0; st < 3; ++st) {
@@ -219,7 +219,7 @@ __device__ __forceinline__ void set_stage(Issuer *s, const int *stage_beg, int s
     if (st >= 0) { s->pf_cur = stage_beg[st]; s->pf_end = stage_beg[st + 1]; }
 }
 // request as many chunks as the ring has room for (producer thread only)
-__device__ __forceinline__ void prefetch(Issuer *s, const uint32_t *chunks, const int *stage_beg, uint8_t *wbuf, uint64_t *wfull,
+__device__ __noinline__ void prefetch(Issuer *s, const uint32_t *chunks, const int *stage_beg, uint8_t *wbuf, uint64_t *wfull,
                                          const __half *img)
 {
     int stage = s->pf_stage;
@@ -396,7 +396,11 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     } while (0)
 
     const float *PB = pblk;
+#ifdef AEM_H16_MARKS
 #define MARK() do { if (args.dbg && (tid == 0 || tid == 32)) { ((volatile long long *)args.dbg)[2 * blockIdx.x + (tid == 32)] = __LINE__ + 10000ll * tile; __threadfence_system(); } } while (0)
+#else
+#define MARK() do { } while (0)
+#endif
 
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {

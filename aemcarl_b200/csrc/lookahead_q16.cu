@@ -171,7 +171,7 @@ __device__ __forceinline__ int layer_at(int st, int idx)
     return idx < 12 ? QL_ENC + idx : (idx == 12 ? QL_A0 : QL_A2);
 }
 // chunk table: the {offset in halves, bytes} of every ring chunk of the three stages, in consumption order
-__device__ void build_chunk_table(const LayerInfo *layers, int2 *chunks, int *stage_beg)
+__device__ __noinline__ void build_chunk_table(const LayerInfo *layers, int2 *chunks, int *stage_beg)
 {
     int n = 0;
     for (int st = 0; st < 3; ++st) {
@@ -191,7 +191,7 @@ __device__ __forceinline__ void set_stage(Issuer *s, const int *stage_beg, int s
     if (st >= 0) { s->pf_cur = stage_beg[st]; s->pf_end = stage_beg[st + 1]; }
 }
 // request as many chunks as the ring has room for (lane 0 of warp 0)
-__device__ __forceinline__ void prefetch(Issuer *s, const int2 *chunks, const int *stage_beg, uint8_t *wbuf, uint64_t *wfull,
+__device__ __noinline__ void prefetch(Issuer *s, const int2 *chunks, const int *stage_beg, uint8_t *wbuf, uint64_t *wfull,
                                          const __half *img)
 {
     int stage = s->pf_stage;
