@@ -122,32 +122,28 @@ __device__ __forceinline__ void ld8_unpack(uint32_t hi_addr, uint32_t lo_addr, f
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
-// In-place ReLU conversion of this thread's W accumulator columns [base, base + W) into its operand block:
-// hi columns [base, base + W/2), lo columns [base + W/2, base + W).  W = 64 or 48.  The upper half of the accumulators
-// is buffered in registers first because the lo columns overwrite it.
+// In-place ReLU conversion of this thread's W accumulator columns [base, base + W) into its operand block, 16 columns
+// at a time: accumulators [16c, 16c + 16) -> hi columns [16c, 16c + 8), lo columns [16c + 8, 16c + 16).  Every chunk is
+// read completely before it is overwritten and touches no other chunk, so the loop stays rolled (instruction-cache
+// footprint) and needs no staging registers.  k-step ks of the operand = chunk ks: hi at 16 ks, lo at 16 ks + 8.
 template <int W>
 __device__ __forceinline__ void relu_inplace(uint32_t base, const float *__restrict__ bias)
 {
-    constexpr int NB = W / 16;            // chunks of 8 that must be buffered (upper half)
-    float buf[NB * 8];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) ld8f(base + W / 2 + 8 * c, buf + 8 * c);
-    tmem_wait_ld();
-#pragma unroll
-    for (int c = 0; c < NB; ++c) {        // lower half: read chunk, write hi [4c,4c+4) and lo [W/2+4c, ..)
-        float v[8];
-        ld8f(base + 8 * c, v);
+#pragma unroll 1
+    for (int c = 0; c < W / 16; ++c) {
+        float v[16];
+        ld8f(base + 16 * c, v);
+        ld8f(base + 16 * c + 8, v + 8);
         tmem_wait_ld();
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias + 16 * c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + bias[8 * c + j], 0.0f);
-        st8_pack(base + 4 * c, base + W / 2 + 4 * c, v);
-    }
-#pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        float *v = buf + 8 * c;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + bias[W / 2 + 8 * c + j], 0.0f);
-        st8_pack(base + W / 4 + 4 * c, base + W / 2 + W / 4 + 4 * c, v);
+        for (int q = 0; q < 4; ++q) {
+            const float4 bb = b4[q];
+            v[4 * q] = fmaxf(v[4 * q] + bb.x, 0.0f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + bb.y, 0.0f);
+            v[4 * q + 2] = fmaxf(v[4 * q + 2] + bb.z, 0.0f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + bb.w, 0.0f);
+        }
+        st8_pack(base + 16 * c, base + 16 * c + 8, v);
+        st8_pack(base + 16 * c + 4, base + 16 * c + 12, v + 8);
     }
 }
 
@@ -259,9 +255,9 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 }
 
 // One layer: KS k-steps (16 K values = 8 operand columns each) per pass.  Operand column of k-step ks:
-//   a_base + HSTRIDE * (ks / KSH) + 8 * (ks % KSH), lo part LO columns further.  SPECIAL: step-1 images use the
+//   a_base + HSTRIDE * (ks / KSH) + KSTR * (ks % KSH), lo part LO columns further.  SPECIAL: step-1 images use the
 //   k-steps {1, 3} of A1 (the x slots).
-template <int N, int KS, int KSH, int HSTRIDE, int LO, bool SPECIAL, int SPLIT>
+template <int N, int KS, int KSH, int HSTRIDE, int KSTR, int LO, bool SPECIAL, int SPLIT>
 __device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t ring, uint32_t tm, uint32_t a_base, uint32_t d,
                                         bool accumulate)
 {
@@ -283,7 +279,7 @@ __device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t rin
             for (int kk = 0; kk < KSS; ++kk) {
                 const int ks = sub * KSS + kk;
                 const uint32_t acol = SPECIAL ? (uint32_t)(8 * (2 * ks + 1))
-                                              : (uint32_t)(HSTRIDE * (ks / KSH) + 8 * (ks % KSH));
+                                              : (uint32_t)(HSTRIDE * (ks / KSH) + KSTR * (ks % KSH));
                 const uint64_t bd = DHI | (uint64_t)(base + kk * ((2 * LBO) >> 4));
                 if (leader) {
                     if (part == 0) {
@@ -299,10 +295,10 @@ __device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t rin
 }
 // shorthand for the three operand layouts
 // (images larger than one ring slot -- N * K = 8192 -- are streamed as two k-halves: SPLIT = 2)
-#define ISSUE_K64(N, a, d, acc) issue_t<N, 4, 4, 0, 32, false, ((N) * 64 > 6144 ? 2 : 1)>(ir, wfull, ring, tm, a, d, acc)
-#define ISSUE_K64S(N, a, d) issue_t<N, 2, 4, 0, 32, true, 1>(ir, wfull, ring, tm, a, d, false)        /* step-1 images   */
-#define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 32, false, 2>(ir, wfull, ring, tm, a, d, false)      /* in-place [64|64] */
-#define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 24, false, 1>(ir, wfull, ring, tm, a, d, acc)    /* in-place [48|48] */
+#define ISSUE_K64(N, a, d, acc) issue_t<N, 4, 4, 0, 8, 32, false, ((N) * 64 > 6144 ? 2 : 1)>(ir, wfull, ring, tm, a, d, acc)
+#define ISSUE_K64S(N, a, d) issue_t<N, 2, 4, 0, 8, 32, true, 1>(ir, wfull, ring, tm, a, d, false)        /* step-1 images   */
+#define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 16, 8, false, 2>(ir, wfull, ring, tm, a, d, false)   /* in-place 2 x 4 x [8|8] */
+#define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 16, 8, false, 1>(ir, wfull, ring, tm, a, d, acc) /* in-place 2 x 3 x [8|8] */
 
 __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArgs args)
 {
@@ -472,67 +468,44 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #pragma unroll 1
         for (int step = 1; step <= max_steps; ++step) {
             const bool kfull = step > 1;
-            // ---- z1 -> in place A2
-            MARK(); GROUP_BARRIER();
-            const int e_z1 = nev++;
-            if (warp == 0) {
-                ISSUE_BEGIN();
-                if (kfull) ISSUE_K64(128, A1, D1, false);
-                else ISSUE_K64S(128, A1, D1);
-                ISSUE_COMMIT(e_z1);
-                ISSUE_END();
-            }
-            __syncwarp();
-            MARK(); WAIT_EVENT(e_z1); MARK();
-            PRODUCE(e_z1); MARK();
-            relu_inplace<64>(tl + D1 + 64 * half, PB + PB_Z1 + 64 * half);
-            // ---- z
-            MARK(); GROUP_BARRIER();
-            const int e_z2 = nev++;
-            if (warp == 0) {
-                ISSUE_BEGIN();
-                ISSUE_K128(64, D1, D2);
-                ISSUE_COMMIT(e_z2);
-                ISSUE_END();
-            }
-            __syncwarp();
-            MARK(); WAIT_EVENT(e_z2); MARK();
-            PRODUCE(e_z2); MARK();
-            {
-                const float *b = PB + PB_Z2 + 32 * half;
-                float v[32];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) ld8f(tl + D2 + 32 * half + 8 * c, v + 8 * c);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 25; ++j) z[j] = sigmoidf_(fmaxf(v[j] + b[j], 0.0f));
-            }
-            if (kfull) {
-                // ---- r1 -> in place A2, r, [r*h ; x] -> A3
+            // ---- the two gates share one copy of the code (instruction-cache footprint): gate 0 = z, gate 1 = r
+            //      layer 1 -> in place A2 (K = 128), layer 2 -> z, or r and [r*h ; x] -> A3.  The ring delivers the weight
+            //      images in the order Z1, Z2, R1, R2; step 1 has h = 0 and needs z only.
+#pragma unroll 1
+            for (int gate = 0; gate < (kfull ? 2 : 1); ++gate) {
                 MARK(); GROUP_BARRIER();
-                const int e_r1 = nev++;
+                const int e_g1 = nev++;
                 if (warp == 0) {
                     ISSUE_BEGIN();
-                    ISSUE_K64(128, A1, D1, false);
-                    ISSUE_COMMIT(e_r1);
+                    if (kfull) ISSUE_K64(128, A1, D1, false);
+                    else ISSUE_K64S(128, A1, D1);
+                    ISSUE_COMMIT(e_g1);
                     ISSUE_END();
                 }
                 __syncwarp();
-                MARK(); WAIT_EVENT(e_r1); MARK();
-                PRODUCE(e_r1); MARK();
-                relu_inplace<64>(tl + D1 + 64 * half, PB + PB_R1 + 64 * half);
+                MARK(); WAIT_EVENT(e_g1); MARK();
+                PRODUCE(e_g1); MARK();
+                relu_inplace<64>(tl + D1 + 64 * half, PB + (gate ? PB_R1 : PB_Z1) + 64 * half);
                 MARK(); GROUP_BARRIER();
-                const int e_r2 = nev++;
+                const int e_g2 = nev++;
                 if (warp == 0) {
                     ISSUE_BEGIN();
                     ISSUE_K128(64, D1, D2);
-                    ISSUE_COMMIT(e_r2);
+                    ISSUE_COMMIT(e_g2);
                     ISSUE_END();
                 }
                 __syncwarp();
-                MARK(); WAIT_EVENT(e_r2); MARK();
-                PRODUCE(e_r2); MARK();
-                {
+                MARK(); WAIT_EVENT(e_g2); MARK();
+                PRODUCE(e_g2); MARK();
+                if (gate == 0) {
+                    const float *b = PB + PB_Z2 + 32 * half;
+                    float v[32];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ld8f(tl + D2 + 32 * half + 8 * c, v + 8 * c);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 25; ++j) z[j] = sigmoidf_(fmaxf(v[j] + b[j], 0.0f));
+                } else {
                     const float *b = PB + PB_R2 + 32 * half;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -661,8 +634,8 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             const int e_in = nev++;
             if (warp == 0) {
                 ISSUE_BEGIN();
-                ISSUE_K64(96, AE, DIN, false);
-                ISSUE_K64(96, AE, DIN + 96, false);
+#pragma unroll 1
+                for (int hd = 0; hd < 2; ++hd) ISSUE_K64(96, AE, DIN + 96 * hd, false);
                 ISSUE_COMMIT(e_in);
                 ISSUE_END();
             }
@@ -696,27 +669,21 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #pragma unroll
                 for (int j = 0; j < 32; ++j) o[j] = 0.0f;
                 if (samp >= 0) {
-                    const float *base = kv + (samp * T) * KV_PITCH + 50 * half;
-                    float m = -INFINITY;
-                    for (int j = 0; j < T; ++j) {
-                        const float *kp = base + j * KV_PITCH;
+                    // one pass over the T keys of the sample with a running maximum (streaming softmax)
+                    const float *kp = kv + (samp * T) * KV_PITCH + 50 * half;
+                    float m = -INFINITY, sum = 0.0f;
+                    for (int j = 0; j < T; ++j, kp += KV_PITCH) {
                         float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
                         for (int c = 0; c < 24; c += 2) { d0 = fmaf(qh[c], kp[c], d0); d1 = fmaf(qh[c + 1], kp[c + 1], d1); }
                         d0 = fmaf(qh[24], kp[24], d0);
-                        m = fmaxf(m, (d0 + d1) * 0.2f);
-                    }
-                    float sum = 0.0f;
-                    for (int j = 0; j < T; ++j) {
-                        const float *kp = base + j * KV_PITCH;
-                        float d0 = 0.0f, d1 = 0.0f;
+                        const float sc = (d0 + d1) * 0.2f;
+                        const float mn = fmaxf(m, sc);
+                        const float rescale = __expf(m - mn), p = __expf(sc - mn);
+                        m = mn;
+                        sum = fmaf(sum, rescale, p);
 #pragma unroll
-                        for (int c = 0; c < 24; c += 2) { d0 = fmaf(qh[c], kp[c], d0); d1 = fmaf(qh[c + 1], kp[c + 1], d1); }
-                        d0 = fmaf(qh[24], kp[24], d0);
-                        const float p = __expf((d0 + d1) * 0.2f - m);
-                        sum += p;
-#pragma unroll
-                        for (int c = 0; c < 25; ++c) o[c] = fmaf(p, kp[25 + c], o[c]);
+                        for (int c = 0; c < 25; ++c) o[c] = fmaf(p, kp[25 + c], o[c] * rescale);
                     }
                     const float inv = __fdividef(1.0f, sum);
 #pragma unroll
@@ -736,80 +703,50 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             __syncwarp();
             MARK(); WAIT_EVENT(e_out); MARK();
             PRODUCE(e_out); MARK();
-            {
-                const float *b = PB + PBL + PBE_OUT + 32 * half;
-                float s = 0.0f;
-                {
-                    float v[32];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) ld8f(tl + DOUT + 32 * half + 8 * c, v + 8 * c);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 25; ++j) { xres[j] += v[j] + b[j]; s += xres[j]; }
+            // pass 0: out_proj + residual + LayerNorm1; pass 1: FFN + residual + LayerNorm2 (one copy of the LayerNorm code)
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1) {
+                    // ---- FFN in two hidden chunks, converted in place; linear2 accumulates the two K = 96 halves
+                    MARK(); GROUP_BARRIER();
+                    const int e_f1 = nev;          // chunk c completes on event e_f1 + c
+                    const int e_f2 = nev + 2;
+                    nev += 3;
+                    if (warp == 0) {
+                        ISSUE_BEGIN();
+                        ISSUE_K64(96, AE, DF1A, false);
+                        ISSUE_COMMIT(e_f1);
+                        ISSUE_K64(96, AE, DF1B, false);
+                        ISSUE_COMMIT(e_f1 + 1);
+                        ISSUE_END();
+                    }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        MARK(); WAIT_EVENT(e_f1 + c); MARK();
+                        PRODUCE(e_f1 + c); MARK();
+                        relu_inplace<48>(tl + (c ? DF1B : DF1A) + 48 * half, PB + PBL + (c ? PBE_F1B : PBE_F1A) + 48 * half);
+                        MARK(); GROUP_BARRIER();
+                        if (warp == 0) {
+                            if (c == 0) WAIT_EVENT(e_f1 + 1);   // F1B reads AE, which D_F2 aliases: complete before linear2 starts
+                            ISSUE_BEGIN();
+                            ISSUE_K96(64, c ? DF1B : DF1A, DF2, c != 0);
+                            if (c) ISSUE_COMMIT(e_f2);
+                            ISSUE_END();
+                        }
+                        __syncwarp();
+                    }
+                    MARK(); WAIT_EVENT(e_f2); MARK();
+                    PRODUCE(e_f2); MARK();
                 }
-                const float mh = s * 0.04f;
-                float ss = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 25; ++j) { const float dd = xres[j] - mh; ss = fmaf(dd, dd, ss); }
-                sx[half * 128 + row] = s;
-                sx[256 + half * 128 + row] = ss;
-                pair_sync(q4);
-                const float so = sx[(half ^ 1) * 128 + row], sso = sx[256 + (half ^ 1) * 128 + row];
-                const float mean = (s + so) * 0.02f;
-                const float dm = (s - so) * 0.04f;
-                const float rstd = rsqrtf((ss + sso + dm * dm * 12.5f) * 0.02f + 1e-5f);
-                float a[32];
-#pragma unroll
-                for (int j = 0; j < 25; ++j) { xres[j] = (xres[j] - mean) * rstd * LN[j] + LN[50 + j]; a[j] = xres[j]; }
-#pragma unroll
-                for (int j = 25; j < 32; ++j) a[j] = 0.0f;
-                st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, a);
-            }
-            // ---- FFN in two hidden chunks, converted in place
-            MARK(); GROUP_BARRIER();
-            const int e_f1a = nev++;
-            const int e_f1b = nev++;
-            if (warp == 0) {
-                ISSUE_BEGIN();
-                ISSUE_K64(96, AE, DF1A, false);
-                ISSUE_COMMIT(e_f1a);
-                ISSUE_K64(96, AE, DF1B, false);
-                ISSUE_COMMIT(e_f1b);
-                ISSUE_END();
-            }
-            __syncwarp();
-            MARK(); WAIT_EVENT(e_f1a); MARK();
-            PRODUCE(e_f1a); MARK();
-            relu_inplace<48>(tl + DF1A + 48 * half, PB + PBL + PBE_F1A + 48 * half);
-            MARK(); GROUP_BARRIER();
-            if (warp == 0) {
-                WAIT_EVENT(e_f1b);     // F1B reads AE, which D_F2 aliases: it must have completed before linear2 starts
-                ISSUE_BEGIN();
-                ISSUE_K96(64, DF1A, DF2, false);
-                ISSUE_END();
-            }
-            __syncwarp();
-            MARK(); WAIT_EVENT(e_f1b); MARK();
-            PRODUCE(e_f1b); MARK();
-            relu_inplace<48>(tl + DF1B + 48 * half, PB + PBL + PBE_F1B + 48 * half);
-            MARK(); GROUP_BARRIER();
-            const int e_f2 = nev++;
-            if (warp == 0) {
-                ISSUE_BEGIN();
-                ISSUE_K96(64, DF1B, DF2, true);
-                ISSUE_COMMIT(e_f2);
-                ISSUE_END();
-            }
-            __syncwarp();
-            MARK(); WAIT_EVENT(e_f2); MARK();
-            PRODUCE(e_f2); MARK();
-            {
-                const float *b = PB + PBL + PBE_F2 + 32 * half;
+                const float *b = PB + PBL + (pass ? PBE_F2 : PBE_OUT) + 32 * half;
+                const float *g = LN + 100 * pass;
                 float s = 0.0f;
                 {
                     float v[32];
+                    const uint32_t dcol = tl + (pass ? DF2 : DOUT) + 32 * half;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) ld8f(tl + DF2 + 32 * half + 8 * c, v + 8 * c);
+                    for (int c = 0; c < 4; ++c) ld8f(dcol + 8 * c, v + 8 * c);
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 25; ++j) { xres[j] += v[j] + b[j]; s += xres[j]; }
@@ -821,17 +758,17 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 sx[half * 128 + row] = s;
                 sx[256 + half * 128 + row] = ss;
                 tc_fence_before();
-                pair_sync(q4);      // also: the partner has finished reading its D_F2 columns (AE overwrites them)
+                pair_sync(q4);      // pass 1 also: the partner has finished reading its D_F2 columns (AE overwrites them)
                 const float so = sx[(half ^ 1) * 128 + row], sso = sx[256 + (half ^ 1) * 128 + row];
                 const float mean = (s + so) * 0.02f;
                 const float dm = (s - so) * 0.04f;
                 const float rstd = rsqrtf((ss + sso + dm * dm * 12.5f) * 0.02f + 1e-5f);
                 float a[32];
 #pragma unroll
-                for (int j = 0; j < 25; ++j) { xres[j] = (xres[j] - mean) * rstd * LN[100 + j] + LN[150 + j]; a[j] = xres[j]; }
+                for (int j = 0; j < 25; ++j) { xres[j] = (xres[j] - mean) * rstd * g[j] + g[50 + j]; a[j] = xres[j]; }
 #pragma unroll
                 for (int j = 25; j < 32; ++j) a[j] = 0.0f;
-                if (l == 2) { a[25] = selfs[0]; a[26] = selfs[1]; a[27] = selfs[2]; }     // joint = [self_state ; env]
+                if (pass == 1 && l == 2) { a[25] = selfs[0]; a[26] = selfs[1]; a[27] = selfs[2]; }     // joint = [self_state ; env]
                 st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, a);
             }
         }
