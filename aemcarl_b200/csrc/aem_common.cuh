@@ -65,7 +65,7 @@ enum { TL_Z1S = 0, TL_QS = 1, TL_Z1 = 2, TL_Z2 = 3, TL_R1 = 4, TL_R2 = 5, TL_Q =
        TL_ENC = 7,      // + 7 * l : INA, INB, OUT, F1A, F1B, F2A, F2B
        TL_A0 = 28, TL_A2 = 29, TL_NUM = 30 };
 constexpr int TC_PBLK_FLOATS = 3200;
-constexpr int H16_PBLK_FLOATS = 2880;
+constexpr int H16_PBLK_FLOATS = 704;       // LayerNorm 600, ponder 51, action_mlp.4 51 (biases ride in the weight images)
 constexpr int Q16_PBLK_FLOATS = 2880;
 // layers of lookahead_q16.cu (four threads per row)
 enum { QL_Z1 = 0, QL_Z1R1 = 1, QL_Z2 = 2, QL_R2 = 3, QL_Q = 4, QL_ENC = 5 /* + 4 * l : IN, OUT, F1, F2 */, QL_A0 = 17,

@@ -158,6 +158,33 @@ struct H16Pack {
     std::vector<__half> img;
     std::vector<float> pblk;
     aem::TcLayer layers[aem::TL_NUM];
+    // The bias rides in the weights: K slot `bias_k` of every operand layout is a padding slot that the kernel keeps at
+    // exactly 1.0, so column `bias_k` of the image holds the bias (hi/lo split like every weight).  Layers whose
+    // accumulators are converted in place into the next operand get a padding neuron `one_c` whose only non-zero weight is
+    // 1.0 at `bias_k`: it evaluates to relu(1) = 1 and becomes the next layer's constant slot.
+    template <class OM, class IM>
+    void add(int id, const float *W, int in_dim, const float *bias, int N, int K, OM om, IM im, int bias_k, int one_c)
+    {
+        aem::TcLayer &L = layers[id];
+        L.N = N; L.ksteps = K / 16; L.bytes = N * K * 2;
+        L.off_hi = (int)img.size();
+        img.resize(img.size() + (size_t)2 * N * K, __float2half(0.0f));
+        L.off_lo = L.off_hi + N * K;
+        if (im(bias_k) >= 0 || (one_c >= 0 && om(one_c) >= 0)) { fprintf(stderr, "pack_h16: slot clash at layer %d\n", id); abort(); }
+        for (int c = 0; c < N; ++c)
+            for (int k = 0; k < K; ++k) {
+                const int o = om(c), i = im(k);
+                float w = (o >= 0 && i >= 0) ? W[(size_t)o * in_dim + i] : 0.0f;
+                if (k == bias_k) w = (o >= 0 && bias) ? bias[o] : (c == one_c ? 1.0f : 0.0f);
+                const __half hi = __float2half_rn(w);
+                const __half lo = __float2half_rn(w - __half2float(hi));
+                const size_t at = ((size_t)(k / 8) * N + c) * 8 + (k % 8);
+                img[L.off_hi + at] = hi;
+                img[L.off_lo + at] = lo;
+            }
+        L.bias_off = (N * K * 2 > 12288) ? 2 : 1;     // h16 tables: k-halves per image (ring slots are 12 KB)
+    }
+    // layout with a separate bias block in the parameter block (lookahead_q16.cu)
     template <class OM, class IM>
     void add(int id, const float *W, int in_dim, const float *bias, int N, int K, OM om, IM im, int expect_bias_off)
     {
@@ -191,33 +218,30 @@ void pack_h16(const float *w, H16Pack &P)
 {
     using namespace aem;
     auto step1 = [](int k) { return in_hx(k < 16 ? 16 + k : 48 + (k - 16)); };     // A1 slots {16..31, 48..63}
-    P.add(TL_Z1, w + OFF_Z1W, HXD, w + OFF_Z1B, 128, 64, out100w, in_hx, 0);
-    P.add(TL_Z2, w + OFF_Z2W, 100, w + OFF_Z2B, 64, 128, out50, in100w, 128);
-    P.add(TL_R1, w + OFF_R1W, HXD, w + OFF_R1B, 128, 64, out100w, in_hx, 192);
-    P.add(TL_R2, w + OFF_R2W, 100, w + OFF_R2B, 64, 128, out50, in100w, 320);
-    P.add(TL_Q, w + OFF_QW, HXD, w + OFF_QB, 64, 64, out50, in_hx, 384);
-    P.add(TL_Z1S, w + OFF_Z1W, HXD, nullptr, 128, 32, out100w, step1, -1);
-    P.add(TL_QS, w + OFF_QW, HXD, nullptr, 64, 32, out50, step1, -1);
+    P.add(TL_Z1, w + OFF_Z1W, HXD, w + OFF_Z1B, 128, 64, out100w, in_hx, 63, 127);
+    P.add(TL_Z2, w + OFF_Z2W, 100, w + OFF_Z2B, 64, 128, out50, in100w, 127, -1);
+    P.add(TL_R1, w + OFF_R1W, HXD, w + OFF_R1B, 128, 64, out100w, in_hx, 63, 127);
+    P.add(TL_R2, w + OFF_R2W, 100, w + OFF_R2B, 64, 128, out50, in100w, 127, -1);
+    P.add(TL_Q, w + OFF_QW, HXD, w + OFF_QB, 64, 64, out50, in_hx, 63, -1);
+    P.add(TL_Z1S, w + OFF_Z1W, HXD, w + OFF_Z1B, 128, 32, out100w, step1, 31, 127);
+    P.add(TL_QS, w + OFF_QW, HXD, w + OFF_QB, 64, 32, out50, step1, 31, -1);
     for (int l = 0; l < 3; ++l) {
         const float *E = w + OFF_ENC + l * ENC_SIZE;
-        const int LB = TL_ENC + 7 * l, PBL = 448 + 512 * l;
+        const int LB = TL_ENC + 7 * l;
         for (int hd = 0; hd < 2; ++hd)
             P.add(LB + hd, E + ENC_INW, HID, E + ENC_INB, 96, 64,
-                  [hd](int c) { int sidx = c / 32, j = c % 32; return j < 25 ? sidx * 50 + 25 * hd + j : -1; }, in50w,
-                  PBL + 96 * hd);
-        P.add(LB + 2, E + ENC_OW, HID, E + ENC_OB, 64, 64, out50, in50w, PBL + 192);
+                  [hd](int c) { int sidx = c / 32, j = c % 32; return j < 25 ? sidx * 50 + 25 * hd + j : -1; }, in50w, 63, -1);
+        P.add(LB + 2, E + ENC_OW, HID, E + ENC_OB, 64, 64, out50, in50w, 63, -1);
         for (int ch = 0; ch < 2; ++ch)
             P.add(LB + 3 + ch, E + ENC_L1W, HID, E + ENC_L1B, 96, 64,
-                  [ch](int c) { int u = unit75(c / 48, c % 48); return u >= 0 ? 75 * ch + u : -1; }, in50w,
-                  PBL + 256 + 96 * ch);
-        for (int ch = 0; ch < 2; ++ch)
+                  [ch](int c) { int u = unit75(c / 48, c % 48); return u >= 0 ? 75 * ch + u : -1; }, in50w, 63, 95);
+        for (int ch = 0; ch < 2; ++ch)       // linear2 accumulates the two chunks; the bias rides in chunk b
             P.add(LB + 5 + ch, E + ENC_L2W, 150, ch == 1 ? E + ENC_L2B : nullptr, 64, 96, out50,
-                  [ch](int k) { int u = unit75(k / 48, k % 48); return u >= 0 ? 75 * ch + u : -1; },
-                  ch == 1 ? PBL + 448 : -1);
+                  [ch](int k) { int u = unit75(k / 48, k % 48); return u >= 0 ? 75 * ch + u : -1; }, 95, -1);
     }
-    P.add(TL_A0, w + OFF_A0W, 56, w + OFF_A0B, 128, 64, out100w, in_jointw, 1984);
-    P.add(TL_A2, w + OFF_A2W, 100, w + OFF_A2B, 64, 128, out50, in100w, 2112);
-    // LayerNorm (3 x 200), ponder (50 + 1), last action layer (50 + 1)
+    P.add(TL_A0, w + OFF_A0W, 56, w + OFF_A0B, 128, 64, out100w, in_jointw, 63, 127);
+    P.add(TL_A2, w + OFF_A2W, 100, w + OFF_A2B, 64, 128, out50, in100w, 127, -1);
+    // parameter block: LayerNorm (3 x 200), ponder (50 + 1), last action layer (50 + 1)
     for (int l = 0; l < 3; ++l) {
         const float *E = w + OFF_ENC + l * ENC_SIZE;
         P.pblk.insert(P.pblk.end(), E + ENC_N1G, E + ENC_N1G + 200);

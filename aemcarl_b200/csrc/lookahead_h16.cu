@@ -29,7 +29,7 @@ using namespace aemtc;
 constexpr int NT = 256;
 constexpr int NBUF = 4;                 // a two-layer issue group (in_proj heads, linear1 chunks) holds 4 chunks at once
 constexpr int WBUF_BYTES = 12288;       // 16 KB images (N*K = 8192 fp16) are streamed as two 8 KB k-halves
-constexpr int KV_PITCH = 101;
+constexpr int KV_PITCH = 116;           // [k head 0 (28) | k head 1 (28) | v head 0 (28) | v head 1 (28)] + 4: float4 access, conflict-free
 constexpr int NEV = 4;
 constexpr int PBLK_MAX = H16_PBLK_FLOATS;
 
@@ -47,10 +47,10 @@ constexpr uint32_t DF2 = 0;             // linear2 accumulators N = 64 (aliases 
 constexpr uint32_t DA0 = 64;            // action_mlp.0 accumulators N = 128, converted in place
 constexpr uint32_t DA2 = 192;           // action_mlp.2 accumulators N = 64
 
-// parameter block offsets (floats) -- fixed by the layer order of capi.cu pack_h16 (asserted there)
-constexpr int PB_Z1 = 0, PB_Z2 = 128, PB_R1 = 192, PB_R2 = 320, PB_Q = 384, PB_ENC = 448, PB_ENC_STRIDE = 512;
-constexpr int PBE_INA = 0, PBE_OUT = 192, PBE_F1A = 256, PBE_F1B = 352, PBE_F2 = 448;   // INB = INA + 96
-constexpr int PB_A0 = 1984, PB_A2 = 2112, PB_LN = 2176, PB_PW = 2776, PB_A4 = 2827;
+// parameter block offsets (floats): LayerNorm 3 x [g1 b1 g2 b2], ponder weights + bias, action_mlp.4 weights + bias.
+// The biases of the MMA layers ride in the weight images (capi.cu pack_h16): every operand keeps one padding K slot
+// (slot 31 of half 1) at exactly 1.0.
+constexpr int PB_LN = 0, PB_PW = 600, PB_A4 = 651;
 static_assert(PB_A4 + 51 <= H16_PBLK_FLOATS, "parameter block");
 
 constexpr size_t SMEM_BYTES = (size_t)NBUF * WBUF_BYTES + 128 * KV_PITCH * 4 + PBLK_MAX * 4 + 4 * 128 * 4 +
@@ -122,12 +122,20 @@ __device__ __forceinline__ void ld8_unpack(uint32_t hi_addr, uint32_t lo_addr, f
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
+// ReLU + fp16 hi/lo split of a pair: hi = relu(a) rounded TOWARDS ZERO, so the residual of a positive value is never
+// negative and the ReLU can ride in both conversions (a negative value gives hi = 0, residual a < 0 -> lo = 0).
+__device__ __forceinline__ void split2_relu(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - f.y), "f"(a - f.x));
+}
 // In-place ReLU conversion of this thread's W accumulator columns [base, base + W) into its operand block, 16 columns
 // at a time: accumulators [16c, 16c + 16) -> hi columns [16c, 16c + 8), lo columns [16c + 8, 16c + 16).  Every chunk is
 // read completely before it is overwritten and touches no other chunk, so the loop stays rolled (instruction-cache
 // footprint) and needs no staging registers.  k-step ks of the operand = chunk ks: hi at 16 ks, lo at 16 ks + 8.
 template <int W>
-__device__ __forceinline__ void relu_inplace(uint32_t base, const float *__restrict__ bias)
+__device__ __forceinline__ void relu_inplace(uint32_t base)
 {
 #pragma unroll 1
     for (int c = 0; c < W / 16; ++c) {
@@ -135,15 +143,13 @@ __device__ __forceinline__ void relu_inplace(uint32_t base, const float *__restr
         ld8f(base + 16 * c, v);
         ld8f(base + 16 * c + 8, v + 8);
         tmem_wait_ld();
-        const float4 *b4 = reinterpret_cast<const float4 *>(bias + 16 * c);
+        uint32_t h[8], l[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 bb = b4[q];
-            v[4 * q] = fmaxf(v[4 * q] + bb.x, 0.0f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + bb.y, 0.0f);
-            v[4 * q + 2] = fmaxf(v[4 * q + 2] + bb.z, 0.0f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + bb.w, 0.0f);
-        }
-        st8_pack(base + 16 * c, base + 16 * c + 8, v);
-        st8_pack(base + 16 * c + 4, base + 16 * c + 12, v + 8);
+        for (int i = 0; i < 8; ++i) split2_relu(v[2 * i], v[2 * i + 1], h[i], l[i]);
+        st4u(base + 16 * c, h);
+        st4u(base + 16 * c + 4, h + 4);
+        st4u(base + 16 * c + 8, l);
+        st4u(base + 16 * c + 12, l + 4);
     }
 }
 
@@ -453,7 +459,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 7; ++i) xh[i] = half ? (i < 6 ? o[7 + (i < 6 ? i : 0)] : 0.0f) : o[i];
+            for (int i = 0; i < 7; ++i) xh[i] = half ? (i < 6 ? o[7 + (i < 6 ? i : 0)] : 1.0f) : o[i];   // slot 31 of half 1 = 1 (bias)
             float v[32];
 #pragma unroll
             for (int j = 0; j < 25; ++j) v[j] = 0.0f;
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 __syncwarp();
                 MARK(); WAIT_EVENT(e_g1); MARK();
                 PRODUCE(e_g1); MARK();
-                relu_inplace<64>(tl + D1 + 64 * half, PB + (gate ? PB_R1 : PB_Z1) + 64 * half);
+                relu_inplace<64>(tl + D1 + 64 * half);
                 MARK(); GROUP_BARRIER();
                 const int e_g2 = nev++;
                 if (warp == 0) {
@@ -498,15 +504,13 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 MARK(); WAIT_EVENT(e_g2); MARK();
                 PRODUCE(e_g2); MARK();
                 if (gate == 0) {
-                    const float *b = PB + PB_Z2 + 32 * half;
                     float v[32];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) ld8f(tl + D2 + 32 * half + 8 * c, v + 8 * c);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 25; ++j) z[j] = sigmoidf_(fmaxf(v[j] + b[j], 0.0f));
+                    for (int j = 0; j < 25; ++j) z[j] = sigmoidf_(fmaxf(v[j], 0.0f));
                 } else {
-                    const float *b = PB + PB_R2 + 32 * half;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float v[8];
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int s = 8 * c + j;
-                            if (s < 25) v[j] = __fmul_rn(sigmoidf_(fmaxf(v[j] + b[s], 0.0f)), hn[s]);
+                            if (s < 25) v[j] = __fmul_rn(sigmoidf_(fmaxf(v[j], 0.0f)), hn[s]);
                             else v[j] = xh[s - 25];
                         }
                         st8_pack(tl + A3 + 16 * half + 4 * c, tl + A3 + 32 + 16 * half + 4 * c, v);
@@ -536,7 +540,6 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             MARK(); WAIT_EVENT(e_q); MARK();
             PRODUCE(e_q); MARK();
             {
-                const float *b = PB + PB_Q + 32 * half;
                 const float *pw = PB + PB_PW + 25 * half;
                 float pd = 0.0f;
 #pragma unroll
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     for (int j = 0; j < 8; ++j) {
                         const int s = 8 * c + j;
                         if (s < 25) {
-                            const float qv = tanhf_(v[j] + b[s]);
+                            const float qv = tanhf_(v[j]);
                             hn[s] = __fadd_rn(__fmul_rn(1.0f - z[s], hn[s]), __fmul_rn(z[s], qv));
                             pd = fmaf(hn[s], pw[s], pd);
                             v[j] = hn[s];
@@ -622,13 +625,13 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = j < 25 ? xres[j] : 0.0f;
+            if (half) v[31] = 1.0f;                                   // constant slot (bias)
             st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, v);
         }
 
         // ---------------- phase 2: 3 x post-norm encoder layer ----------------
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
-            const int PBL = PB_ENC + PB_ENC_STRIDE * l;
             const float *LN = PB + PB_LN + l * 200 + 25 * half;
             MARK(); GROUP_BARRIER();
             const int e_in = nev++;
@@ -644,23 +647,27 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             PRODUCE(e_in); MARK();
             float o[32];
             {
-                float qh[25];
-                const float *b = PB + PBL + PBE_INA + 96 * half;
-                float *dst = kv + row * KV_PITCH + 50 * half;
+                // q stays in registers (28 slots, the last 3 zero); k and v of this head go to shared memory as 7 float4
+                // each: row = [k head 0 (28) | k head 1 (28) | v head 0 (28) | v head 1 (28)].  Accumulator columns 25..31
+                // of every block are padding neurons and exactly zero.
+                float qh[28];
+                {
+                    float4 *dst = reinterpret_cast<float4 *>(kv + row * KV_PITCH + 28 * half);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {          // q | k | v blocks of 32 columns each
-                    float a[8], k[8], v[8];
-                    ld8f(tl + DIN + 96 * half + 8 * c, a);
-                    ld8f(tl + DIN + 96 * half + 32 + 8 * c, k);
-                    ld8f(tl + DIN + 96 * half + 64 + 8 * c, v);
-                    tmem_wait_ld();
+                    for (int c = 0; c < 4; ++c) {          // q | k | v blocks of 32 columns each
+                        float a[8], k[8], v[8];
+                        ld8f(tl + DIN + 96 * half + 8 * c, a);
+                        ld8f(tl + DIN + 96 * half + 32 + 8 * c, k);
+                        ld8f(tl + DIN + 96 * half + 64 + 8 * c, v);
+                        tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int s = 8 * c + j;
-                        if (s < 25) {
-                            qh[s] = a[j] + b[s];
-                            dst[s] = k[j] + b[32 + s];
-                            dst[25 + s] = v[j] + b[64 + s];
+                        for (int j = 0; j < 8; ++j)
+                            if (8 * c + j < 28) qh[8 * c + j] = a[j] * 0.2f;       // 1 / sqrt(head_dim = 25)
+                        dst[2 * c] = make_float4(k[0], k[1], k[2], k[3]);
+                        dst[14 + 2 * c] = make_float4(v[0], v[1], v[2], v[3]);
+                        if (c < 3) {
+                            dst[2 * c + 1] = make_float4(k[4], k[5], k[6], k[7]);
+                            dst[14 + 2 * c + 1] = make_float4(v[4], v[5], v[6], v[7]);
                         }
                     }
                 }
@@ -670,26 +677,35 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 for (int j = 0; j < 32; ++j) o[j] = 0.0f;
                 if (samp >= 0) {
                     // one pass over the T keys of the sample with a running maximum (streaming softmax)
-                    const float *kp = kv + (samp * T) * KV_PITCH + 50 * half;
+                    const float *kb = kv + (samp * T) * KV_PITCH + 28 * half;
                     float m = -INFINITY, sum = 0.0f;
-                    for (int j = 0; j < T; ++j, kp += KV_PITCH) {
-                        float d0 = 0.0f, d1 = 0.0f;
+                    for (int j = 0; j < T; ++j, kb += KV_PITCH) {
+                        const float4 *kp = reinterpret_cast<const float4 *>(kb);
+                        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
 #pragma unroll
-                        for (int c = 0; c < 24; c += 2) { d0 = fmaf(qh[c], kp[c], d0); d1 = fmaf(qh[c + 1], kp[c + 1], d1); }
-                        d0 = fmaf(qh[24], kp[24], d0);
-                        const float sc = (d0 + d1) * 0.2f;
+                        for (int c = 0; c < 7; ++c) {
+                            const float4 k4 = kp[c];
+                            d0 = fmaf(qh[4 * c], k4.x, d0); d1 = fmaf(qh[4 * c + 1], k4.y, d1);
+                            d2 = fmaf(qh[4 * c + 2], k4.z, d2); d3 = fmaf(qh[4 * c + 3], k4.w, d3);
+                        }
+                        const float sc = (d0 + d1) + (d2 + d3);
                         const float mn = fmaxf(m, sc);
                         const float rescale = __expf(m - mn), p = __expf(sc - mn);
                         m = mn;
                         sum = fmaf(sum, rescale, p);
 #pragma unroll
-                        for (int c = 0; c < 25; ++c) o[c] = fmaf(p, kp[25 + c], o[c] * rescale);
+                        for (int c = 0; c < 7; ++c) {
+                            const float4 v4 = kp[14 + c];
+                            o[4 * c] = fmaf(p, v4.x, o[4 * c] * rescale); o[4 * c + 1] = fmaf(p, v4.y, o[4 * c + 1] * rescale);
+                            o[4 * c + 2] = fmaf(p, v4.z, o[4 * c + 2] * rescale); o[4 * c + 3] = fmaf(p, v4.w, o[4 * c + 3] * rescale);
+                        }
                     }
                     const float inv = __fdividef(1.0f, sum);
 #pragma unroll
                     for (int c = 0; c < 25; ++c) o[c] *= inv;
                 }
             }
+            if (half) o[31] = 1.0f;                                       // constant slot (bias)
             st_pack<32>(tl + AATT + 16 * half, tl + AATT + 32 + 16 * half, o);
             // ---- out_proj + residual + LayerNorm1
             MARK(); GROUP_BARRIER();
@@ -725,7 +741,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     for (int c = 0; c < 2; ++c) {
                         MARK(); WAIT_EVENT(e_f1 + c); MARK();
                         PRODUCE(e_f1 + c); MARK();
-                        relu_inplace<48>(tl + (c ? DF1B : DF1A) + 48 * half, PB + PBL + (c ? PBE_F1B : PBE_F1A) + 48 * half);
+                        relu_inplace<48>(tl + (c ? DF1B : DF1A) + 48 * half);
                         MARK(); GROUP_BARRIER();
                         if (warp == 0) {
                             if (c == 0) WAIT_EVENT(e_f1 + 1);   // F1B reads AE, which D_F2 aliases: complete before linear2 starts
@@ -739,7 +755,6 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     MARK(); WAIT_EVENT(e_f2); MARK();
                     PRODUCE(e_f2); MARK();
                 }
-                const float *b = PB + PBL + (pass ? PBE_F2 : PBE_OUT) + 32 * half;
                 const float *g = LN + 100 * pass;
                 float s = 0.0f;
                 {
@@ -749,7 +764,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     for (int c = 0; c < 4; ++c) ld8f(dcol + 8 * c, v + 8 * c);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 25; ++j) { xres[j] += v[j] + b[j]; s += xres[j]; }
+                    for (int j = 0; j < 25; ++j) { xres[j] += v[j]; s += xres[j]; }
                 }
                 const float mh = s * 0.04f;
                 float ss = 0.0f;
@@ -769,6 +784,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #pragma unroll
                 for (int j = 25; j < 32; ++j) a[j] = 0.0f;
                 if (pass == 1 && l == 2) { a[25] = selfs[0]; a[26] = selfs[1]; a[27] = selfs[2]; }     // joint = [self_state ; env]
+                if (half) a[31] = 1.0f;                                   // constant slot (bias)
                 st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, a);
             }
         }
@@ -785,7 +801,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         __syncwarp();
         MARK(); WAIT_EVENT(e_a0); MARK();
         PRODUCE(e_a0); MARK();
-        relu_inplace<64>(tl + DA0 + 64 * half, PB + PB_A0 + 64 * half);
+        relu_inplace<64>(tl + DA0 + 64 * half);
         MARK(); GROUP_BARRIER();
         const int e_a2 = nev++;
         if (warp == 0) {
@@ -798,7 +814,6 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         MARK(); WAIT_EVENT(e_a2); MARK();
         PRODUCE(e_a2); MARK();
         {
-            const float *b = PB + PB_A2 + 32 * half;
             const float *w4 = PB + PB_A4 + 25 * half;
             float pd = 0.0f;
 #pragma unroll
@@ -808,7 +823,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (8 * c + j < 25) pd = fmaf(fmaxf(v[j] + b[8 * c + j], 0.0f), w4[8 * c + j], pd);
+                    if (8 * c + j < 25) pd = fmaf(fmaxf(v[j], 0.0f), w4[8 * c + j], pd);
             }
             sx[half * 128 + row] = pd;
             pair_sync(q4);
@@ -823,13 +838,17 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         __syncthreads();
     }
 
+#ifdef AEM_H16_MARKS
     { const int tile = -1; MARK(); }
+#endif
     tmem_wait_st();
     tmem_wait_ld();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tm, 256);
+#ifdef AEM_H16_MARKS
     { const int tile = -2; MARK(); }
+#endif
 #undef GROUP_BARRIER
 #undef COMMIT
 #undef WAIT_EVENT
