@@ -94,7 +94,10 @@ int aem_set_act_mode(aem_handle h, int act_fixed, int act_steps);
 /* Arithmetic of the value-network GEMMs inside aem_lookahead / aem_value_forward / aem_gru_act:
  *   0 = FP32 FFMA (k-ascending accumulation, the order of the CPU oracle)            [default]
  *   1 = tcgen05 tensor cores, 3xTF32 split with FP32 accumulation in tensor memory (~1e-6 relative of mode 0)
- *   2 = tcgen05 tensor cores, FP16 hi/lo split (3 MMAs per product, FP32 accumulation), two tiles in flight per SM. */
+ *   2 = tcgen05 tensor cores, FP16 hi/lo split (3 MMAs per product, FP32 accumulation), two tiles in flight per SM
+ *       (the fastest; what bench.py measures)
+ *   3 = same arithmetic as 2, four threads per token row, one tile per SM (experimental).
+ * Every mode is held to the same parity bar (tests/test_gpu_parity.py). */
 int aem_set_precision(aem_handle h, int precision);
 
 /* ---- device-pointer entry points ---- */
