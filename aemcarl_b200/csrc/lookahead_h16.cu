@@ -424,8 +424,10 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #pragma unroll
             for (int i = 0; i < 3; ++i) selfs[i] = 0.0f;
             if (row < nrows) {
-                samp = row / T;
-                tok = row - samp * T;
+                // row order inside a tile: the token-0 (robot) rows of all samples first, then the human tokens sample by
+                // sample -- the last encoder layer and the action MLP only need token 0, i.e. the leading warps
+                if (row < nsamp) { samp = row; tok = 0; }
+                else { const int r2 = row - nsamp; samp = r2 / (T - 1); tok = 1 + r2 - samp * (T - 1); }
                 const int gs = s0 + samp;
                 if (args.mode == 0) {
                     const int b = gs / args.A, a = gs - b * args.A;
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         }
         if (args.mode == 2) {
             if (row < nrows) {
-                float *dst = args.gru_out + ((size_t)s0 * T + row) * HID + 25 * half;
+                float *dst = args.gru_out + ((size_t)(s0 + samp) * T + tok) * HID + 25 * half;
 #pragma unroll
                 for (int j = 0; j < 25; ++j) dst[j] = xres[j];
                 if (args.steps && half == 0 && tok == 0) args.steps[s0 + samp] = (uint8_t)s_cnt[samp];
@@ -645,6 +647,9 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             __syncwarp();
             MARK(); WAIT_EVENT(e_in); MARK();
             PRODUCE(e_in); MARK();
+            // exact saving: the last layer needs k / v of every token but q, out_proj, FFN and LayerNorm of
+            // token 0 only: warps without a token-0 row skip those epilogues (their MMA rows compute garbage nobody reads)
+            const bool live = l < 2 || q4 * 32 < nsamp;
             float o[32];
             {
                 // q stays in registers (28 slots, the last 3 zero); k and v of this head go to shared memory as 7 float4
@@ -675,11 +680,13 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 __syncthreads();       // every thread has consumed D_IN and published k / v
 #pragma unroll
                 for (int j = 0; j < 32; ++j) o[j] = 0.0f;
-                if (samp >= 0) {
-                    // one pass over the T keys of the sample with a running maximum (streaming softmax)
-                    const float *kb = kv + (samp * T) * KV_PITCH + 28 * half;
+                if (samp >= 0 && live) {
+                    // one pass over the T keys of the sample with a running maximum (streaming softmax);
+                    // key 0 is the sample's token-0 row, keys 1.. are its block of human rows
+                    const float *kb = kv + samp * KV_PITCH + 28 * half;
+                    const float *kb_rest = kv + (nsamp + samp * (T - 1)) * KV_PITCH + 28 * half;
                     float m = -INFINITY, sum = 0.0f;
-                    for (int j = 0; j < T; ++j, kb += KV_PITCH) {
+                    for (int j = 0; j < T; ++j, kb = (j == 1 ? kb_rest : kb + KV_PITCH)) {
                         const float4 *kp = reinterpret_cast<const float4 *>(kb);
                         float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
 #pragma unroll
@@ -706,7 +713,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 }
             }
             if (half) o[31] = 1.0f;                                       // constant slot (bias)
-            st_pack<32>(tl + AATT + 16 * half, tl + AATT + 32 + 16 * half, o);
+            if (live) st_pack<32>(tl + AATT + 16 * half, tl + AATT + 32 + 16 * half, o);
             // ---- out_proj + residual + LayerNorm1
             MARK(); GROUP_BARRIER();
             const int e_out = nev++;
@@ -741,7 +748,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     for (int c = 0; c < 2; ++c) {
                         MARK(); WAIT_EVENT(e_f1 + c); MARK();
                         PRODUCE(e_f1 + c); MARK();
-                        relu_inplace<48>(tl + (c ? DF1B : DF1A) + 48 * half);
+                        if (live) relu_inplace<48>(tl + (c ? DF1B : DF1A) + 48 * half);
                         MARK(); GROUP_BARRIER();
                         if (warp == 0) {
                             if (c == 0) WAIT_EVENT(e_f1 + 1);   // F1B reads AE, which D_F2 aliases: complete before linear2 starts
@@ -755,6 +762,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     MARK(); WAIT_EVENT(e_f2); MARK();
                     PRODUCE(e_f2); MARK();
                 }
+                if (!live) continue;
                 const float *g = LN + 100 * pass;
                 float s = 0.0f;
                 {
@@ -801,7 +809,8 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         __syncwarp();
         MARK(); WAIT_EVENT(e_a0); MARK();
         PRODUCE(e_a0); MARK();
-        relu_inplace<64>(tl + DA0 + 64 * half);
+        const bool live_a = q4 * 32 < nsamp;      // only token-0 rows feed the value head
+        if (live_a) relu_inplace<64>(tl + DA0 + 64 * half);
         MARK(); GROUP_BARRIER();
         const int e_a2 = nev++;
         if (warp == 0) {
@@ -813,7 +822,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         __syncwarp();
         MARK(); WAIT_EVENT(e_a2); MARK();
         PRODUCE(e_a2); MARK();
-        {
+        if (live_a) {
             const float *w4 = PB + PB_A4 + 25 * half;
             float pd = 0.0f;
 #pragma unroll
