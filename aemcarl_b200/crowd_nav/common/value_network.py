@@ -111,6 +111,16 @@ class ValueNetworkTransformerAndGRU(nn.Module):
     def get_step_cnt(self):
         return self.step_cnt
 
+    def __deepcopy__(self, memo):
+        """Explorer.update_target_model deep-copies the network (explorer.py:18-19); the copy must not share (or try to
+        pickle) the ctypes engine handle -- it uploads its own weights on first use."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in ("_engine", "_loaded_version") else copy.deepcopy(v, memo)
+        return new
+
     # ---- flat blob <-> parameters ---------------------------------------------------------------
     def flat_weights(self):
         return wts.flatten_state_dict(self.state_dict())

@@ -60,6 +60,13 @@ def main(argv=None):
     ap.add_argument("--act_steps", type=int, default=1)
     ap.add_argument("--act_fixed", default=False, action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--vectorised", type=int, default=0, metavar="B",
+                    help="RL phase on B environments in lock-step (VecExplorer + on-device replay memory); 0 = the "
+                         "reference's one-episode-at-a-time loop")
+    ap.add_argument("--updates_per_wave", type=int, default=None,
+                    help="optimizer steps after each wave of B episodes (default: train_batches x B, the reference's ratio)")
+    ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3", "fp16x3q"],
+                    help="arithmetic of the lookahead kernel in the vectorised RL phase")
     args = ap.parse_args(argv)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -108,6 +115,9 @@ def main(argv=None):
     eps_start, eps_end = tcfg.getfloat("train", "epsilon_start"), tcfg.getfloat("train", "epsilon_end")
     eps_decay = tcfg.getfloat("train", "epsilon_decay")
     episode = 0
+    if args.vectorised > 0:
+        episode = vectorised_rl(args, tcfg, policy, env, model, memory, trainer, explorer, train_episodes,
+                                (eps_start, eps_end, eps_decay), rank, world, device)
     while episode < train_episodes:
         epsilon = eps_start + (eps_end - eps_start) / eps_decay * episode if episode < eps_decay else eps_end
         policy.set_epsilon(epsilon)
@@ -123,6 +133,44 @@ def main(argv=None):
     if rank == 0:
         torch.save(model.state_dict(), os.path.join(args.output_dir, "rl_model.pth"))
     return dict(loss=loss, memory=len(memory), model=model, explorer=explorer, policy=policy, env=env, robot=robot)
+
+
+def vectorised_rl(args, tcfg, policy, env, model, memory, trainer, explorer, train_episodes, eps_sched, rank, world, device):
+    """RL phase of train.py:206-246 with waves of B episodes per rank: same epsilon schedule (evaluated at the episode
+    counter of the wave), same sample : update ratio, same target-update / validation / checkpoint intervals (triggered
+    when a wave crosses a multiple).  Experience lives in a DeviceReplayMemory seeded with the imitation data."""
+    from aemcarl_b200.crowd_nav.utils.vec_explorer import DeviceReplayMemory, VecExplorer
+    B = args.vectorised
+    n = args.human_num
+    dmem = DeviceReplayMemory(memory.capacity, n, device)
+    if len(memory):
+        dmem.push_batch(torch.stack([m[0] for m in memory.memory]), torch.stack([m[1] for m in memory.memory]))
+    trainer.memory, trainer.data_loader = dmem, None
+    policy.engine().set_precision(args.precision)
+    vec = VecExplorer(policy, B, env.env_params(), dmem, policy.gamma, human_num=n, rule=env.train_val_sim,
+                      seed=args.seed * 1000 + rank)
+    vec.update_target_model(model)
+    eps_start, eps_end, eps_decay = eps_sched
+    base_case = env.case_counter["train"]
+    updates = args.updates_per_wave or tcfg.getint("train", "train_batches") * B // tcfg.getint("train", "sample_episodes")
+    every = lambda key, before, after: after // tcfg.getint("train", key) > before // tcfg.getint("train", key)
+    episode, wave = 0, 0
+    while episode < train_episodes:
+        epsilon = eps_start + (eps_end - eps_start) / eps_decay * episode if episode < eps_decay else eps_end
+        policy.set_epsilon(epsilon)
+        stats = vec.run_k_episodes(B, "train", update_memory=True, episode=episode, epsilon=epsilon,
+                                   first_case=base_case + (wave * world + rank) * B)
+        if len(dmem) >= trainer.batch_size:
+            trainer.optimize_batch(updates)
+        before, episode, wave = episode, episode + B * world, wave + 1
+        if every("target_update_interval", before, episode):
+            vec.update_target_model(model)
+        if every("evaluation_interval", before, episode) and episode < train_episodes:
+            vec.run_k_episodes(env.case_size["val"], "val", episode=episode, first_case=0)
+        if every("checkpoint_interval", before, episode) and rank == 0:
+            torch.save(model.state_dict(), os.path.join(args.output_dir, "rl_model_%d.pth" % episode))
+    explorer.vec, explorer.device_memory, explorer.vec_stats = vec, dmem, stats
+    return episode
 
 
 def stride_cases(env, world):

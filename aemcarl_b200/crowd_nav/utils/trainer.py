@@ -74,16 +74,23 @@ class Trainer(object):
         self.optimizer.step()
         return loss.data.item()
 
+    def _device_memory(self):
+        """DeviceReplayMemory (utils/vec_explorer.py): mini-batches are gathered on the device, no DataLoader"""
+        return hasattr(self.memory, "sample") and hasattr(self.memory, "epoch_batches")
+
     def optimize_epoch(self, num_epochs):
         if self.optimizer is None:
             raise ValueError("Learning rate is not set!")
-        if self.data_loader is None:
+        fast = self._device_memory()
+        if not fast and self.data_loader is None:
             self.data_loader = DataLoader(self.memory, self.batch_size, shuffle=True, drop_last=True)
         average_epoch_loss = 0
-        steps_per_epoch = min_over_ranks(len(self.data_loader), self.device)
+        n_batches = len(self.memory) // self.batch_size if fast else len(self.data_loader)
+        steps_per_epoch = min_over_ranks(n_batches, self.device)
         for epoch in range(num_epochs):
             epoch_loss = 0
-            for i, (inputs, values) in enumerate(self.data_loader):
+            batches = self.memory.epoch_batches(self.batch_size, drop_last=True) if fast else self.data_loader
+            for i, (inputs, values) in enumerate(batches):
                 if i >= steps_per_epoch:
                     break
                 epoch_loss += self._step(inputs, values)
@@ -94,11 +101,12 @@ class Trainer(object):
     def optimize_batch(self, num_batches):
         if self.optimizer is None:
             raise ValueError("Learning rate is not set!")
-        if self.data_loader is None:
+        fast = self._device_memory()
+        if not fast and self.data_loader is None:
             self.data_loader = DataLoader(self.memory, self.batch_size, shuffle=True)
         losses = 0
         for _ in range(num_batches):
-            inputs, values = next(iter(self.data_loader))
+            inputs, values = self.memory.sample(self.batch_size) if fast else next(iter(self.data_loader))
             losses += self._step(inputs, values)
         average_loss = losses / num_batches
         logging.debug("Average loss : %.2E", average_loss)

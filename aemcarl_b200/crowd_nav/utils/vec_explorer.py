@@ -1,0 +1,270 @@
+"""Vectorised Explorer with an on-device replay memory.
+
+The reference's Explorer (crowd_nav/utils/explorer.py:22-151) plays one episode at a time and, for every
+success / collision episode, pushes one (rotated state, target value) pair per step into a Python list.  Here B
+episodes run in lock-step on a VecCrowdSim (one fused lookahead + step launch sequence per step for all of them), the
+trajectories stay in HBM, the target values of all finished episodes are computed by ONE batched aem_value_forward
+on the target network, and the pairs land in a ring buffer that is itself a pair of device tensors.
+
+Semantics kept from the reference:
+  * a step stores last_state = transform(state BEFORE the action) (multi_human_rl.py:385-386, explorer.py:53);
+  * only episodes that end in ReachGoal or Collision are stored (explorer.py:78-80);
+  * RL target (explorer.py:132-139): value_i = r_i + gamma^(dt * v_pref) * V_target(state_{i+1}), last step value = r;
+  * IL target (explorer.py:126-130): value_i = sum_{s >= i} gamma^((s - i) * dt * v_pref) * r_s;
+  * the statistics and the log line of run_k_episodes (explorer.py:82-108).
+Differences (documented, unavoidable in a vectorised run): episodes finish out of case order, so the ORDER of the pairs
+in the ring differs (the multiset per episode is identical -- tests/test_gpu_explorer.py); epsilon-greedy draws come from
+a seeded torch.Generator on the device instead of the global numpy stream.
+"""
+import logging
+
+import numpy as np
+import torch
+
+from aemcarl_b200.crowd_nav.utils.explorer import average
+
+INFO_DANGER, INFO_REACHGOAL, INFO_COLLISION, INFO_TIMEOUT = 1, 2, 3, 4
+
+
+class DeviceReplayMemory(object):
+    """Replay ring buffer (crowd_nav/utils/memory.py:4-28) held as two tensors on `device`:
+    states [capacity, n, 13] f32 and values [capacity, 1] f32.  Works on any torch device (the ring logic is tested
+    on the CPU); push() keeps the reference's overwrite-oldest order."""
+
+    def __init__(self, capacity, human_num, device):
+        self.capacity = int(capacity)
+        self.device = torch.device(device)
+        self.states = torch.zeros((self.capacity, human_num, 13), dtype=torch.float32, device=self.device)
+        self.values = torch.zeros((self.capacity, 1), dtype=torch.float32, device=self.device)
+        self.position = 0
+        self.size = 0
+
+    def push(self, item):
+        state, value = item
+        self.push_batch(state.unsqueeze(0), value.reshape(1, 1))
+
+    def push_batch(self, states, values):
+        """append m pairs in order; like m successive push() calls"""
+        m = int(states.shape[0])
+        if m == 0:
+            return
+        states = states.to(self.device, torch.float32)
+        values = values.to(self.device, torch.float32).reshape(m, 1)
+        if m >= self.capacity:                      # only the last `capacity` survive
+            first_kept = m - self.capacity
+            end = (self.position + m) % self.capacity
+            idx = (torch.arange(self.capacity, device=self.device) + end) % self.capacity
+            self.states[idx] = states[first_kept:]
+            self.values[idx] = values[first_kept:]
+        else:
+            idx = (torch.arange(m, device=self.device) + self.position) % self.capacity
+            self.states[idx] = states
+            self.values[idx] = values
+        self.position = (self.position + m) % self.capacity
+        self.size = min(self.capacity, self.size + m)
+
+    def is_full(self):
+        return self.size == self.capacity
+
+    def __len__(self):
+        return self.size
+
+    def __getitem__(self, item):
+        if item >= self.size:
+            raise IndexError(item)
+        return self.states[item], self.values[item]
+
+    def clear(self):
+        self.position = 0
+        self.size = 0
+
+    def sample(self, batch_size, generator=None):
+        """one shuffled mini-batch without replacement (what next(iter(DataLoader(shuffle=True))) yields)"""
+        k = min(int(batch_size), self.size)
+        perm = torch.randperm(self.size, device=self.device, generator=generator)[:k]
+        return self.states[perm], self.values[perm]
+
+    def epoch_batches(self, batch_size, drop_last=True, generator=None):
+        perm = torch.randperm(self.size, device=self.device, generator=generator)
+        stop = self.size - (self.size % batch_size if drop_last else 0)
+        for i in range(0, stop, batch_size):
+            idx = perm[i:i + batch_size]
+            yield self.states[idx], self.values[idx]
+
+
+class VecExplorer(object):
+    """run_k_episodes for a batch of environments.  `policy` is the ACTENVCARL policy (its engine drives the lookahead),
+    `num_envs` episodes are in flight at once."""
+
+    def __init__(self, policy, num_envs, env_params, memory=None, gamma=None, human_num=5, rule="circle_crossing",
+                 seed=0, scenario_kw=None):
+        self.policy = policy
+        self.env_params = env_params          # aem_env_params of the configured CrowdSim (env.env_params())
+        self.B = int(num_envs)
+        self.n = int(human_num)
+        self.rule = rule
+        self.memory = memory
+        self.gamma = policy.gamma if gamma is None else gamma
+        self.device = policy.device
+        self.target_model = None
+        self.scenario_kw = scenario_kw
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(seed))
+        self.case_counter = {"train": 0, "val": 0, "test": 0}
+        self.last_stats = None
+        self._target_engine = None
+
+    def update_target_model(self, target_model):
+        import copy
+        self.target_model = copy.deepcopy(target_model)
+
+    def _target_values(self, states):
+        """V_target of rotated states [m, n, 13] with one batched kernel launch (explorer.py:137, batch-1 there)"""
+        from aemcarl_b200.engine import get_engine
+        if self.target_model is None:
+            raise ValueError("update_target_model() has not been called")
+        if self._target_engine is None:
+            self._target_engine = get_engine(self.device.index or 0, role="target")
+        eng = self.target_model.sync_engine(self._target_engine)
+        eng.set_precision(getattr(self.policy.engine(), "precision", 0))
+        v, _ = eng.value_forward(states.contiguous())
+        return v.reshape(-1)
+
+    def run_k_episodes(self, k, phase, update_memory=False, imitation_learning=False, episode=None, epsilon=None,
+                       first_case=None, print_failure=False):
+        from aemcarl_b200.vec_env import VecCrowdSim
+        if imitation_learning:
+            raise NotImplementedError("the ORCA teacher of the imitation phase runs through the serial Explorer")
+        if update_memory and (self.memory is None or self.gamma is None):
+            raise ValueError("Memory or gamma value is not set!")
+        pol = self.policy
+        pol.set_phase(phase)
+        eng = pol.engine()
+        eng.set_env_params(self.env_params)
+        first = self.case_counter[phase] if first_case is None else int(first_case)
+        B = min(self.B, int(k))
+        env = VecCrowdSim(eng, B, human_num=self.n, rule=self.rule, phase=phase, first_case=first, pool_size=int(k),
+                          gamma=self.gamma, scenario_kw=self.scenario_kw)
+        if pol.action_space is None:
+            pol.build_action_space(float(env.pool_robot_h[0, 7]))
+            eng = pol.engine()
+        dev = self.device
+        dt = eng.params.time_step
+        v_pref = float(env.pool_robot_h[0, 7])
+        gbar = pow(self.gamma, dt * v_pref)
+        tmax = int(round(eng.params.time_limit / dt)) + 2
+        eps = float(epsilon if epsilon is not None else (pol.epsilon or 0.0)) if phase == "train" else 0.0
+
+        traj_s = torch.zeros((B, tmax, self.n, 13), dtype=torch.float32, device=dev)
+        traj_r = torch.zeros((B, tmax), dtype=torch.float64, device=dev)
+        step_idx = torch.zeros((B,), dtype=torch.int64, device=dev)
+        rows = torch.arange(B, device=dev)
+        case_of_env = np.arange(B)                   # pool index each env is playing
+        active = np.ones(B, dtype=bool)
+        next_case = B
+        codes = np.full(k, -1, dtype=np.int64)
+        nav_time = np.zeros(k)
+        cum_reward = np.zeros(k)
+        too_close, min_dist = 0, []
+        disc = torch.pow(torch.tensor(gbar, dtype=torch.float64, device=dev),
+                         torch.arange(tmax, device=dev, dtype=torch.float64))
+        env_steps = 0
+        pushed = 0
+
+        while active.any():
+            cur = eng.transform(env.robot, env.humans)                      # last_state of every env
+            best = env.lookahead()
+            if eps > 0.0:
+                explore = torch.rand((B,), device=dev, generator=self.gen) < eps
+                rnd = torch.randint(0, eng.A, (B,), device=dev, generator=self.gen, dtype=torch.int32)
+                # the goal short-circuit (action 0 inside the goal disc) precedes the epsilon draw (multi_human_rl.py:321)
+                at_goal = torch.linalg.norm(env.robot[:, 0:2] - env.robot[:, 5:7], dim=1) < env.robot[:, 4]
+                best = torch.where(explore & ~at_goal, rnd, best)
+            reward, done, info, dmin = env.apply(best, auto_reset=False)
+            traj_s[rows, step_idx] = cur
+            traj_r[rows, step_idx] = reward
+            step_idx += 1
+            step_idx.clamp_(max=tmax - 1)               # envs without a case left keep stepping harmlessly
+            done_h = done.cpu().numpy() != 0
+            info_h = info.cpu().numpy()
+            act_idx = np.nonzero(active)[0]
+            env_steps += len(act_idx)
+            danger = active & (info_h == INFO_DANGER)
+            if danger.any():
+                too_close += int(danger.sum())
+                min_dist.extend(dmin.cpu().numpy()[danger].tolist())
+            fin = np.nonzero(active & done_h)[0]
+            if len(fin) == 0:
+                continue
+            fin_t = torch.from_numpy(fin).to(dev)
+            lens = step_idx[fin_t]
+            live_steps = torch.arange(tmax, device=dev).unsqueeze(0) < lens.unsqueeze(1)
+            cr = (traj_r[fin_t] * disc.unsqueeze(0) * live_steps).sum(dim=1).cpu().numpy()
+            gt_h = env.global_time[fin_t].cpu().numpy()
+            cases = case_of_env[fin]
+            codes[cases] = info_h[fin]
+            nav_time[cases] = gt_h
+            cum_reward[cases] = cr
+            store = fin[np.isin(info_h[fin], (INFO_REACHGOAL, INFO_COLLISION))]
+            if update_memory and len(store):
+                pushed += self._store(traj_s, traj_r, step_idx, store, gbar)
+            # next cases for the finished envs
+            for b in fin:
+                if next_case < k:
+                    case_of_env[b] = next_case
+                    next_case += 1
+                else:
+                    active[b] = False
+            reload = np.array([b for b in fin if active[b]], dtype=np.int64)
+            if len(reload):
+                rb = torch.from_numpy(reload).to(dev)
+                cb = torch.from_numpy(case_of_env[reload]).to(dev)
+                env.robot[rb] = env.pool_robot[cb]
+                env.humans[rb] = env.pool_humans[cb]
+                env.global_time[rb] = 0.0
+            step_idx[fin_t] = 0
+
+        self.case_counter[phase] = (first + k) % max(1, self._case_size(phase))
+        success = int((codes == INFO_REACHGOAL).sum())
+        collision = int((codes == INFO_COLLISION).sum())
+        timeout = int((codes == INFO_TIMEOUT).sum())
+        assert success + collision + timeout == k
+        time_limit = eng.params.time_limit
+        s_times = nav_time[codes == INFO_REACHGOAL]
+        avg_nav_time = float(s_times.mean()) if len(s_times) else time_limit
+        extra = "" if episode is None else "in episode {} ".format(episode)
+        logging.info("{:<5} {}has success rate: {:.2f}, collision rate: {:.2f}, nav time: {:.2f}, total reward: {:.4f}"
+                     .format(phase.upper(), extra, success / k, collision / k, avg_nav_time, average(list(cum_reward))))
+        if phase in ["val", "test"]:
+            total_time = (nav_time[codes != INFO_TIMEOUT].sum() + time_limit * timeout) * dt
+            logging.info("Frequency of being in danger: %.2f and average min separate distance in danger: %.2f",
+                         too_close / total_time, average(min_dist))
+        if print_failure:
+            logging.info("Collision cases: " + " ".join(str(x) for x in np.nonzero(codes == INFO_COLLISION)[0]))
+            logging.info("Timeout cases: " + " ".join(str(x) for x in np.nonzero(codes == INFO_TIMEOUT)[0]))
+        self.last_stats = dict(success=success, collision=collision, timeout=timeout, too_close=too_close,
+                               avg_nav_time=avg_nav_time, cumulative_rewards=list(cum_reward), codes=codes,
+                               env_steps=env_steps, pushed=pushed)
+        return self.last_stats
+
+    def _case_size(self, phase):
+        return {"train": np.iinfo(np.uint32).max - 2000, "val": 100, "test": 500}[phase]
+
+    def _store(self, traj_s, traj_r, step_idx, envs, gbar):
+        """RL targets of the finished episodes `envs` (explorer.py:132-139) -> replay memory, one batched target forward"""
+        dev = self.device
+        eb = torch.from_numpy(np.asarray(envs)).to(dev)
+        lens = step_idx[eb]
+        tmax = traj_s.shape[1]
+        t = torch.arange(tmax, device=dev).unsqueeze(0)
+        valid = t < lens.unsqueeze(1)                          # [m, tmax] steps of each episode
+        has_next = t < (lens - 1).unsqueeze(1)
+        states = traj_s[eb]                                    # [m, tmax, n, 13]
+        rewards = traj_r[eb]
+        values = rewards.clone()
+        if has_next.any():
+            nxt = torch.roll(states, -1, dims=1)[has_next]     # state_{i+1} of every non-final step
+            v = self._target_values(nxt).to(torch.float64)
+            values[has_next] = rewards[has_next] + gbar * v
+        self.memory.push_batch(states[valid], values[valid].to(torch.float32))
+        return int(valid.sum().item())

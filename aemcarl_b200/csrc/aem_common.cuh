@@ -154,6 +154,7 @@ cudaError_t launch_lookahead(aem_handle h, const LookaheadArgs &a, cudaStream_t 
 cudaError_t launch_lookahead_tc(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
 cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
 cudaError_t launch_lookahead_q16(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
+cudaError_t launch_transform(const double *robot, const double *humans, int B, int n, float *out, cudaStream_t st);
 cudaError_t launch_select(const double *values, const double *robot, int B, int A, int32_t *best, cudaStream_t st);
 cudaError_t launch_orca(int B, int n, const double *humans, const double *robot, const aem_env_params &p,
                         double *new_vel, cudaStream_t st);

@@ -673,6 +673,18 @@ int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *
     return AEM_OK;
 }
 
+int aem_transform(aem_handle h, int B, int n, const double *robot_d, const double *humans_d, float *states_d, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (B == 0) return AEM_OK;
+    if (!robot_d || !humans_d || !states_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_transform(robot_d, humans_d, B, n, states_d, as_stream(stream)));
+    h->launches += 1;
+    return AEM_OK;
+}
+
 int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint8_t *steps_d, void *stream)
 {
     if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");

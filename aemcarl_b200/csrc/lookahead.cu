@@ -593,6 +593,35 @@ __global__ void select_kernel(const double *__restrict__ values, const double *_
     }
 }
 
+// MultiHumanRL.transform (multi_human_rl.py:423-438): rotate() of the CURRENT joint state -> the replay-memory sample
+// [n][13] of every environment.  One thread per (env, human); same rotate13 as the lookahead kernel.
+__global__ void transform_kernel(const double *__restrict__ robot, const double *__restrict__ humans, int B, int n,
+                                 float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * n) return;
+    const int b = i / n;
+    const double *rb = robot + (size_t)b * 9;
+    const double *hb = humans + (size_t)i * 8;
+    float in14[14], o[XD];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) in14[k] = (float)rb[k];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) in14[9 + k] = (float)hb[k];
+    rotate13(in14, o);
+    float *dst = out + (size_t)i * XD;
+#pragma unroll
+    for (int k = 0; k < XD; ++k) dst[k] = o[k];
+}
+
+cudaError_t launch_transform(const double *robot, const double *humans, int B, int n, float *out, cudaStream_t st)
+{
+    if (B <= 0) return cudaSuccess;
+    const int threads = 128;
+    transform_kernel<<<(B * n + threads - 1) / threads, threads, 0, st>>>(robot, humans, B, n, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lookahead(aem_handle h, const LookaheadArgs &a, cudaStream_t st)
 {
     static bool attr_set[64] = {false};

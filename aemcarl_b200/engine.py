@@ -70,7 +70,7 @@ class Engine:
 
     def set_precision(self, precision):
         """'fp32' (FFMA kernel, default), 'tf32x3' (tcgen05, one tile / SM), 'fp16x3' (tcgen05, two tiles / SM, two threads per
-        row) or 'fp16x3q' (tcgen05, one tile / SM, four threads per row: the fastest)"""
+        row: the fastest) or 'fp16x3q' (tcgen05, one tile / SM, four threads per row: experimental)"""
         mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2, "fp16x3q": 3, 0: 0, 1: 1, 2: 2, 3: 3}[precision]
         check(self.lib.aem_set_precision(self.h, mode))
         self.precision = mode
@@ -160,6 +160,14 @@ class Engine:
         steps = torch.empty((S,), dtype=U8, device=self.device)
         check(self.lib.aem_gru_act(self.h, S, T, _ptr(x), _ptr(out), _ptr(steps), self._stream()))
         return out, steps
+
+    def transform(self, robot, humans, out=None):
+        """MultiHumanRL.transform of every env: robot [B,9] f64, humans [B,n,8] f64 -> rotated states [B,n,13] f32"""
+        B, n, _ = humans.shape
+        self._chk(robot, F64); self._chk(humans, F64)
+        out = torch.empty((B, n, 13), dtype=F32, device=self.device) if out is None else out
+        check(self.lib.aem_transform(self.h, B, n, _ptr(robot), _ptr(humans), _ptr(out), self._stream()))
+        return out
 
     # ---- host-buffer call (the e2e path) -------------------------------------------------------
     def decide_step_host(self, robot, humans, global_time, gamma_bar, want_values=False):

@@ -16,6 +16,7 @@
  *   aem_env_reset_done  <- CrowdSim.reset for finished episodes of a batch (crowd_sim.py:486-552, explorer.py:44-47)
  *   aem_value_forward   <- model(state) on already rotated states (explorer.py:137, trainer.py:52,75)
  *   aem_gru_act         <- ATCBasic.forward components.py:107-137 (fused GRU-cell / adaptive-computation-time)
+ *   aem_transform       <- MultiHumanRL.transform multi_human_rl.py:423-438 (replay-memory sample of the current state)
  *   aem_decide_step_host<- Robot.act + CrowdSim.step through HOST buffers (explorer.py:51-53), the e2e call
  *
  * Conventions: plain pointers and sizes only; `*_d` = device pointer, `*_h` = host pointer; all device entry
@@ -135,6 +136,10 @@ int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *
 
 /* x_d [S*T][13] f32, rows grouped in samples of T tokens -> out_d [S*T][50] f32, steps_d [S] u8 (may be NULL) */
 int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint8_t *steps_d, void *stream);
+
+/* MultiHumanRL.transform (multi_human_rl.py:423-438): rotate() of the current joint state of every environment, the
+ * sample Explorer stores in the replay memory.  robot_d [B][9] f64, humans_d [B][n][8] f64 -> states_d [B][n][13] f32 */
+int aem_transform(aem_handle h, int B, int n, const double *robot_d, const double *humans_d, float *states_d, void *stream);
 
 /* ---- host-buffer call: one full env-step (predict + step) for B environments ----
  * In/out (updated in place): robot_h [B][9], humans_h [B][n][8], global_time_h [B].

@@ -1,0 +1,106 @@
+"""GPU: the vectorised Explorer / on-device replay memory against the serial drop-in Explorer
+(crowd_nav/utils/explorer.py:22-151 mirror, itself pinned to the reference's recorded episodes in test_gpu_api.py)
+and against the oracle's rotate()."""
+import numpy as np
+import pytest
+import torch
+
+from aemcarl_b200.crowd_nav.utils.explorer import Explorer
+from aemcarl_b200.crowd_nav.utils.memory import ReplayMemory
+from aemcarl_b200.crowd_nav.utils.trainer import Trainer
+from aemcarl_b200.crowd_nav.utils.vec_explorer import DeviceReplayMemory, VecExplorer
+from test_gpu_api import setup
+
+pytestmark = pytest.mark.gpu
+
+
+def test_transform_matches_oracle_rotate(oracle):
+    """aem_transform = MultiHumanRL.transform (multi_human_rl.py:423-438): bit-exact with the oracle's rotate()"""
+    from aemcarl_b200 import scenarios
+    from aemcarl_b200.engine import Engine
+    eng = Engine(0)
+    B, n = 64, 7
+    robot, humans = scenarios.generate_pool("train", 11, B, n, "circle_crossing")
+    rng = np.random.RandomState(3)
+    robot[:, 2:4] = rng.uniform(-1, 1, (B, 2))            # moving robot, theta
+    robot[:, 8] = rng.uniform(-3, 3, B)
+    humans[:, :, 2:4] = rng.uniform(-1, 1, (B, n, 2))
+    out = eng.transform(torch.from_numpy(robot).cuda(), torch.from_numpy(humans).cuda()).cpu().numpy()
+    in14 = np.zeros((B, n, 14), dtype=np.float32)
+    in14[:, :, :9] = robot[:, None, :].astype(np.float32)
+    in14[:, :, 9:] = humans[:, :, :5].astype(np.float32)
+    ref = oracle.rotate(in14.reshape(-1, 14)).reshape(B, n, 13)
+    assert np.array_equal(out, ref)
+    eng.close()
+
+
+def _sorted_pairs(states, values):
+    states = np.asarray(states, dtype=np.float64).reshape(len(values), -1)
+    values = np.asarray(values, dtype=np.float64).reshape(-1)
+    key = np.lexsort(np.concatenate([states.T[::-1], values[None]], axis=0))
+    return states[key], values[key]
+
+
+def test_vectorised_explorer_reproduces_the_serial_explorer():
+    """Same policy, same target network, same 8 training cases, epsilon = 0: the (state, value) pairs pushed by the
+    vectorised explorer are the pairs the serial one pushes (order aside), and the statistics agree."""
+    env, robot, policy = setup()
+    dev = torch.device("cuda:0")
+    policy.set_phase("train")
+    policy.set_epsilon(0.0)
+    k = 8
+    mem = ReplayMemory(100000)
+    serial = Explorer(env, robot, dev, mem, policy.gamma, policy)
+    serial.update_target_model(policy.get_model())
+    env.case_counter["train"] = 0
+    s_stats = serial.run_k_episodes(k, "train", update_memory=True)
+    s_states = [m[0].cpu().numpy() for m in mem.memory]
+    s_values = [m[1].item() for m in mem.memory]
+
+    dmem = DeviceReplayMemory(100000, 5, dev)
+    vec = VecExplorer(policy, 5, env.env_params(), dmem, policy.gamma, human_num=5)     # 5 envs < 8 cases: refills
+    vec.update_target_model(policy.get_model())
+    v_stats = vec.run_k_episodes(k, "train", update_memory=True, epsilon=0.0, first_case=0)
+    for key in ("success", "collision", "timeout", "too_close"):
+        assert v_stats[key] == s_stats[key], key
+    assert v_stats["avg_nav_time"] == pytest.approx(s_stats["avg_nav_time"], abs=1e-9)
+    assert np.allclose(sorted(v_stats["cumulative_rewards"]), sorted(s_stats["cumulative_rewards"]), atol=1e-9)
+    assert len(dmem) == len(mem) == v_stats["pushed"] and len(mem) > 20
+    a_s, a_v = _sorted_pairs(s_states, s_values)
+    b_s, b_v = _sorted_pairs(dmem.states[:len(dmem)].cpu().numpy(), dmem.values[:len(dmem)].cpu().numpy())
+    assert np.allclose(a_s, b_s, atol=2e-6), np.abs(a_s - b_s).max()
+    assert np.allclose(a_v, b_v, atol=5e-6), np.abs(a_v - b_v).max()
+    assert vec.case_counter["train"] == k
+
+
+def test_epsilon_greedy_and_training_on_the_device_memory():
+    env, robot, policy = setup()
+    dev = torch.device("cuda:0")
+    dmem = DeviceReplayMemory(5000, 5, dev)
+    vec = VecExplorer(policy, 16, env.env_params(), dmem, policy.gamma, human_num=5, seed=1)
+    vec.update_target_model(policy.get_model())
+    greedy = vec.run_k_episodes(16, "train", update_memory=False, epsilon=0.0, first_case=100)
+    noisy = vec.run_k_episodes(16, "train", update_memory=True, epsilon=0.5, first_case=100)
+    assert noisy["env_steps"] != greedy["env_steps"] or noisy["cumulative_rewards"] != greedy["cumulative_rewards"]
+    assert len(dmem) == noisy["pushed"] > 0
+    trainer = Trainer(policy.get_model(), dmem, dev, batch_size=32)
+    trainer.set_learning_rate(1e-3, "Adam")
+    policy.get_model().train()
+    l0 = trainer.optimize_batch(3)
+    l1 = trainer.optimize_epoch(1)
+    policy.get_model().eval()
+    assert np.isfinite(l0) and np.isfinite(l1)
+
+
+def test_train_entry_point_with_the_vectorised_rl_phase(tmp_path):
+    """train.py --vectorised B: imitation data moves into the device memory, waves of B episodes add to it, the
+    optimizer runs on device-gathered mini-batches, the target network is refreshed across a wave boundary."""
+    from aemcarl_b200.crowd_nav import train
+    out = train.main(["--output_dir", str(tmp_path), "--il_episodes", "6", "--il_epochs", "2", "--train_episodes", "64",
+                      "--vectorised", "32", "--updates_per_wave", "4"])
+    ex = out["explorer"]
+    assert len(ex.device_memory) > out["memory"] > 50          # RL experience was added to the imitation data
+    assert ex.vec_stats["success"] + ex.vec_stats["collision"] + ex.vec_stats["timeout"] == 32
+    assert ex.vec.case_counter["train"] > 0
+    assert (tmp_path / "rl_model.pth").exists()
+    assert all(torch.isfinite(p).all() for p in out["model"].parameters())

@@ -153,3 +153,31 @@ def test_no_cpu_fallback():
     from aemcarl_b200.engine import Engine
     with pytest.raises(AemError, match="no CPU fallback"):
         Engine(0)
+
+
+def test_device_replay_memory_ring_matches_reference_ring():
+    """DeviceReplayMemory (utils/vec_explorer.py) keeps the ring semantics of memory.py:4-28, also for batched pushes
+    that wrap around or exceed the capacity"""
+    import torch
+    from aemcarl_b200.crowd_nav.utils.memory import ReplayMemory
+    from aemcarl_b200.crowd_nav.utils.vec_explorer import DeviceReplayMemory
+    cap, n = 7, 2
+    ref, dev = ReplayMemory(cap), DeviceReplayMemory(cap, n, "cpu")
+    counter = 0
+    for m in (3, 2, 4, 1, 9, 7, 16, 5):
+        st = torch.arange(counter, counter + m, dtype=torch.float32).reshape(m, 1, 1).expand(m, n, 13).contiguous()
+        va = torch.arange(counter, counter + m, dtype=torch.float32).reshape(m, 1) * 0.5
+        counter += m
+        for i in range(m):
+            ref.push((st[i], va[i]))
+        dev.push_batch(st, va)
+        assert len(dev) == len(ref) and dev.position == ref.position and dev.is_full() == ref.is_full()
+        for i in range(len(ref)):
+            assert torch.equal(dev[i][0], ref[i][0]) and torch.equal(dev[i][1], ref[i][1])
+    g = torch.Generator().manual_seed(0)
+    xs, vs = dev.sample(4, g)
+    assert xs.shape == (4, n, 13) and vs.shape == (4, 1) and len(set(vs.reshape(-1).tolist())) == 4
+    seen = torch.cat([v for _, v in dev.epoch_batches(3, drop_last=True, generator=g)])
+    assert seen.numel() == 6 and len(set(seen.reshape(-1).tolist())) == 6
+    dev.clear()
+    assert len(dev) == 0
