@@ -143,7 +143,7 @@ def run_reference(args, rank, world):
     total = float(np.sum(times))
     value = ns * args.steps / total
     sample = "%d envs per step (bounded sample of the %d-env workload), all %d host threads" % (ns, args.envs, cores)
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    out = {"impl": "reference", "metric": METRIC.replace("5 humans", "%d humans" % args.humans), "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "batched lookahead inference: %d envs x %d humans x 81 actions, random-init weights"
@@ -330,7 +330,7 @@ def main():
         cpu = cpu_baseline(snap[0], snap[1], snap[2], W, actions, gbar)
 
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        out = {"metric": METRIC.replace("5 humans", "%d humans" % args.humans), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None,
                "dtype": {"tf32x3": "tf32x3 (fp32-equivalent split, fp32 accumulate)",
