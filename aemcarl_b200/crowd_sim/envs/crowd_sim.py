@@ -109,23 +109,28 @@ class CrowdSim(object):
         return human
 
     def generate_random_human_position(self, human_num, rule):
-        if rule not in ("square_crossing", "circle_crossing"):
-            if rule == "mixed":
-                raise NotImplementedError("the 'mixed' rule is listed under 'next' in DESIGN.md")
+        if rule not in ("square_crossing", "circle_crossing", "mixed"):
             raise ValueError("Rule doesn't exist")
         self.humans = []
-        agents = [scenarios._Agent(self.robot.px, self.robot.py, self.robot.gx, self.robot.gy, self.robot.radius,
-                                   self.robot.v_pref)]
-        for _ in range(human_num):
+        robot = scenarios._Agent(self.robot.px, self.robot.py, self.robot.gx, self.robot.gy, self.robot.radius,
+                                 self.robot.v_pref)
+        agents = [robot]
+        proto = self._new_human()
+        if rule == "mixed":        # crowd_sim.py:337-386: also redraws self.human_num
+            self.human_num, drawn = scenarios._mixed_humans(np.random, robot, human_num, self.circle_radius,
+                                                            self.square_width, self.discomfort_dist, proto.radius,
+                                                            proto.v_pref, self.randomize_attributes)
+        else:
+            drawn = []
+            for _ in range(human_num):
+                make = scenarios._circle_human if rule == "circle_crossing" else scenarios._square_human
+                extent = self.circle_radius if rule == "circle_crossing" else self.square_width
+                drawn.append(make(np.random, agents, extent, self.discomfort_dist, proto.radius, proto.v_pref,
+                                  self.randomize_attributes))
+                agents.append(drawn[-1])
+        for a in drawn:
             human = self._new_human()
-            if rule == "circle_crossing":
-                a = scenarios._circle_human(np.random, agents, self.circle_radius, self.discomfort_dist, human.radius,
-                                            human.v_pref, self.randomize_attributes)
-            else:
-                a = scenarios._square_human(np.random, agents, self.square_width, self.discomfort_dist, human.radius,
-                                            human.v_pref, self.randomize_attributes)
             human.set(a.px, a.py, a.gx, a.gy, 0, 0, 0, radius=a.radius, v_pref=a.v_pref)
-            agents.append(a)
             self.humans.append(human)
 
     # ------------------------------------------------------------------ reset (crowd_sim.py:486-552)

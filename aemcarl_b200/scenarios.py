@@ -79,13 +79,55 @@ def _square_human(rs, agents, square_width, discomfort_dist, radius, v_pref, ran
     return _Agent(px, py, gx, gy, radius, v_pref)
 
 
+# 'mixed' rule (crowd_sim.py:337-386): with probability 0.2 a static scene, otherwise a dynamic one; the number of
+# humans is drawn from a fixed distribution per kind.
+_STATIC_COUNT_P = ((0, 0.05), (1, 0.2), (2, 0.2), (3, 0.3), (4, 0.1), (5, 0.15))
+_DYNAMIC_COUNT_P = ((1, 0.3), (2, 0.3), (3, 0.2), (4, 0.1), (5, 0.1))
+
+
+def _mixed_humans(rs, robot, human_num, circle_radius, square_width, discomfort_dist, radius, v_pref, randomize):
+    """Returns (human_num of the episode, list of agents).  A static scene with zero humans still carries one dummy
+    human parked at (0, -10) (crowd_sim.py:355-358); static humans have goal = start."""
+    static = rs.random_sample() < 0.2
+    prob = rs.random_sample()
+    for count, p in (_STATIC_COUNT_P if static else _DYNAMIC_COUNT_P):
+        if prob - p <= 0:
+            human_num = count
+            break
+        prob -= p
+    agents = [robot]
+    if static:
+        width, height = 4, 8
+        if human_num == 0:
+            agents.append(_Agent(0, -10, 0, -10, radius, v_pref))
+        for _ in range(human_num):
+            sign = -1 if rs.random_sample() > 0.5 else 1
+            while True:
+                px = rs.random_sample() * width * 0.5 * sign
+                py = (rs.random_sample() - 0.5) * height
+                if all(_norm(px - a.px, py - a.py) >= radius + a.radius + discomfort_dist for a in agents):
+                    break
+            agents.append(_Agent(px, py, px, py, radius, v_pref))
+    else:
+        for i in range(human_num):       # the first two cross the circle, the others the square
+            make = _circle_human if i < 2 else _square_human
+            extent = circle_radius if i < 2 else square_width
+            agents.append(make(rs, agents, extent, discomfort_dist, radius, v_pref, randomize))
+    return human_num, agents[1:]
+
+
 def generate_case(phase, case, human_num, rule, circle_radius=4.0, square_width=10.0, discomfort_dist=0.2,
                   robot_radius=0.3, robot_v_pref=1.0, human_radius=0.3, human_v_pref=1.0, randomize_attributes=False):
     """One scenario: (robot[9], humans[human_num][8]) float64, laid out as include/aemcarl_b200.h documents."""
     rs = np.random.RandomState(case_seed(phase, case))
     robot = _Agent(0.0, -circle_radius, 0.0, circle_radius, robot_radius, robot_v_pref)   # crowd_sim.py:512
     agents = [robot]
-    for i in range(human_num):
+    if rule == "mixed":        # the number of humans is part of the draw: the result has len(humans) rows
+        _, hs_list = _mixed_humans(rs, robot, human_num, circle_radius, square_width, discomfort_dist, human_radius,
+                                   human_v_pref, randomize_attributes)
+        agents += hs_list
+        human_num = len(hs_list)
+    for i in range(0 if rule == "mixed" else human_num):
         if rule == "circle_crossing":
             h = _circle_human(rs, agents, circle_radius, discomfort_dist, human_radius, human_v_pref,
                               randomize_attributes)
@@ -102,6 +144,9 @@ def generate_case(phase, case, human_num, rule, circle_radius=4.0, square_width=
 
 def generate_pool(phase, first_case, count, human_num, rule, **kw):
     """Scenarios first_case .. first_case+count-1 stacked: robot [count][9], humans [count][n][8]."""
+    if rule == "mixed":
+        raise NotImplementedError("'mixed' draws a different number of humans per case; batches need one n "
+                                  "(play mixed scenes through the serial CrowdSim)")
     robots = np.empty((count, 9), dtype=np.float64)
     humans = np.empty((count, human_num, 8), dtype=np.float64)
     for i in range(count):

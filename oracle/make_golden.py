@@ -213,6 +213,24 @@ def gen_scenarios():
                 env.reset(phase, case)
                 res.append([[h.px, h.py, h.gx, h.gy] for h in env.humans])
             out["%s_%s" % (tag, phase)] = np.array(res, dtype=np.float64)
+    # the 'mixed' rule (variable human count per case) and randomize_attributes: rows padded to 6 humans,
+    # columns px, py, gx, gy, radius, v_pref; *_count = len(env.humans), *_human_num = env.human_num after reset
+    for tag, sim, rand, ncase in (("mixed5", "mixed", False, 96), ("mixed5_rand", "mixed", True, 48),
+                                  ("circle5_rand", "circle_crossing", True, 32), ("square5_rand", "square_crossing", True, 32)):
+        env, robot, _ = ref_shim.make_env(human_num=5, test_sim=sim)
+        env.randomize_attributes = rand
+        policy = ref_shim.make_policy(seed=0)
+        robot.set_policy(policy)
+        rows = np.zeros((ncase, 6, 6), dtype=np.float64)
+        count = np.zeros(ncase, dtype=np.int64)
+        hnum = np.zeros(ncase, dtype=np.int64)
+        for case in range(ncase):
+            env.human_num = 5
+            env.reset("test", case)
+            count[case], hnum[case] = len(env.humans), env.human_num
+            for i, h in enumerate(env.humans):
+                rows[case, i] = [h.px, h.py, h.gx, h.gy, h.radius, h.v_pref]
+        out[tag + "_rows"], out[tag + "_count"], out[tag + "_human_num"] = rows, count, hnum
     np.savez_compressed(os.path.join(OUT, "scenarios.npz"), **out)
 
 

@@ -198,3 +198,21 @@ def test_train_entry_point_il_and_rl(tmp_path):
     policy.configure(policy_config())
     policy.get_model().load_state_dict(sd)
     assert np.isfinite(out["loss"]) and out["loss"] < 1.0
+
+
+def test_mixed_rule_episodes_run_with_a_varying_number_of_humans(golden_dir):
+    """'mixed' scenes (crowd_sim.py:337-386) through the drop-in CrowdSim: the human count of every case equals the
+    reference's and the episodes run to an outcome on the CUDA path (n changes from episode to episode)."""
+    g = np.load(os.path.join(golden_dir, "scenarios.npz"))
+    env, robot, policy = setup(5, "mixed")
+    seen = set()
+    for case in (2, 3, 4, 12):
+        ob = env.reset("test", case)
+        assert len(env.humans) == len(ob) == g["mixed5_count"][case] and env.human_num == g["mixed5_human_num"][case]
+        seen.add(len(ob))
+        done, steps = False, 0
+        while not done and steps < 130:
+            ob, reward, done, info = env.step(robot.act(ob))
+            steps += 1
+        assert done and isinstance(info, (ReachGoal, Collision, Timeout))
+    assert len(seen) >= 3

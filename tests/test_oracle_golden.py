@@ -109,3 +109,26 @@ def test_episode_replay_matches_reference(oracle, golden_dir, actions):
                 break
         assert code == outcome and step + 1 == nsteps
         assert mismatch <= 1
+
+
+@pytest.mark.parametrize("tag,rule,rand", [("mixed5", "mixed", False), ("mixed5_rand", "mixed", True),
+                                           ("circle5_rand", "circle_crossing", True),
+                                           ("square5_rand", "square_crossing", True)])
+def test_mixed_rule_and_randomized_attributes_match_reference(golden_dir, tag, rule, rand):
+    """crowd_sim.py:337-386 ('mixed': static / dynamic scenes with a drawn human count, dummy human for an empty static
+    scene) and Agent.sample_random_attributes (agent.py:39-45): start, goal, radius and v_pref of every human of every
+    recorded case are bit-identical to the unmodified reference."""
+    from aemcarl_b200 import scenarios
+    g = np.load(os.path.join(golden_dir, "scenarios.npz"))
+    rows, count, hnum = g[tag + "_rows"], g[tag + "_count"], g[tag + "_human_num"]
+    assert len(set(count.tolist())) > (3 if rule == "mixed" else 0)
+    for case in range(len(count)):
+        rb, hs = scenarios.generate_case("test", case, 5, rule, randomize_attributes=rand)
+        assert hs.shape == (count[case], 8)
+        got = hs[:, [0, 1, 5, 6, 4, 7]]
+        assert np.array_equal(got, rows[case, :count[case]]), (tag, case)
+        if rule == "mixed":        # an empty static scene keeps human_num = 0 but carries the parked dummy human
+            assert hnum[case] == (0 if (count[case] == 1 and hs[0, 1] == -10 and hs[0, 0] == 0) else count[case])
+    if rule == "mixed":
+        with pytest.raises(NotImplementedError):
+            scenarios.generate_pool("test", 0, 4, 5, "mixed")
