@@ -61,6 +61,8 @@ SYMBOLS = {
     "aem_value_forward": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),
     "aem_gru_act": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),
     "aem_decide_step_host": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [_VP] * 8),
+    "aem_env_step_xy": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, ctypes.c_double, _VP, _VP, _VP,
+                                       _VP, _VP, _VP]),
     "aem_transform": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),
     "aem_launch_count": (ctypes.c_longlong, [_VP]),
 }

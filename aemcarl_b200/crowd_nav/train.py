@@ -85,7 +85,12 @@ def main(argv=None):
     broadcast_parameters(model, 0)
 
     batch_size = tcfg.getint("trainer", "batch_size")
-    memory = ReplayMemory(tcfg.getint("train", "capacity"))
+    vec = None
+    if args.vectorised > 0:      # experience lives in HBM from the start (utils/vec_explorer.py)
+        from aemcarl_b200.crowd_nav.utils.vec_explorer import DeviceReplayMemory, VecExplorer
+        memory = DeviceReplayMemory(tcfg.getint("train", "capacity"), args.human_num, device)
+    else:
+        memory = ReplayMemory(tcfg.getint("train", "capacity"))
     trainer = Trainer(model, memory, device, batch_size)
     explorer = Explorer(env, robot, device, memory, policy.gamma, target_policy=policy)
 
@@ -97,9 +102,20 @@ def main(argv=None):
     policy.set_env(env)
     policy.time_step = env.time_step
     trainer.set_learning_rate(tcfg.getfloat("imitation_learning", "il_learning_rate"), args.optimizer)
-    env.case_counter["train"] = rank                      # rank-strided cases
-    stride_cases(env, world)
-    explorer.run_k_episodes(args.il_episodes, "train", update_memory=True, imitation_learning=True)
+    if args.vectorised > 0:
+        params = env.env_params()
+        params.orca_safety_space = 0.0                    # the humans' own ORCA; the teacher's margin goes to VecExplorer
+        policy.build_action_space(robot.v_pref)
+        vec = VecExplorer(policy, args.vectorised, params, memory, policy.gamma, human_num=args.human_num,
+                          rule=env.train_val_sim, seed=args.seed * 1000 + rank,
+                          il_safety_space=il_policy.safety_space)
+        per_rank = (args.il_episodes + world - 1) // world
+        vec.run_k_episodes(per_rank, "train", update_memory=True, imitation_learning=True, first_case=rank * per_rank)
+        env.case_counter["train"] = per_rank * world
+    else:
+        env.case_counter["train"] = rank                  # rank-strided cases
+        stride_cases(env, world)
+        explorer.run_k_episodes(args.il_episodes, "train", update_memory=True, imitation_learning=True)
     il_epochs = args.il_epochs or tcfg.getint("imitation_learning", "il_epochs")
     loss = trainer.optimize_epoch(il_epochs) if len(memory) >= batch_size else float("nan")
     logging.info("Finish imitation learning. Experience set size: %d/%d, loss %.3e", len(memory), memory.capacity, loss)
@@ -116,8 +132,8 @@ def main(argv=None):
     eps_decay = tcfg.getfloat("train", "epsilon_decay")
     episode = 0
     if args.vectorised > 0:
-        episode = vectorised_rl(args, tcfg, policy, env, model, memory, trainer, explorer, train_episodes,
-                                (eps_start, eps_end, eps_decay), rank, world, device)
+        episode = vectorised_rl(args, tcfg, policy, env, model, vec, trainer, explorer, train_episodes,
+                                (eps_start, eps_end, eps_decay), rank, world)
     while episode < train_episodes:
         epsilon = eps_start + (eps_end - eps_start) / eps_decay * episode if episode < eps_decay else eps_end
         policy.set_epsilon(epsilon)
@@ -135,20 +151,13 @@ def main(argv=None):
     return dict(loss=loss, memory=len(memory), model=model, explorer=explorer, policy=policy, env=env, robot=robot)
 
 
-def vectorised_rl(args, tcfg, policy, env, model, memory, trainer, explorer, train_episodes, eps_sched, rank, world, device):
+def vectorised_rl(args, tcfg, policy, env, model, vec, trainer, explorer, train_episodes, eps_sched, rank, world):
     """RL phase of train.py:206-246 with waves of B episodes per rank: same epsilon schedule (evaluated at the episode
     counter of the wave), same sample : update ratio, same target-update / validation / checkpoint intervals (triggered
-    when a wave crosses a multiple).  Experience lives in a DeviceReplayMemory seeded with the imitation data."""
-    from aemcarl_b200.crowd_nav.utils.vec_explorer import DeviceReplayMemory, VecExplorer
+    when a wave crosses a multiple).  Experience stays in the DeviceReplayMemory the imitation phase filled."""
     B = args.vectorised
-    n = args.human_num
-    dmem = DeviceReplayMemory(memory.capacity, n, device)
-    if len(memory):
-        dmem.push_batch(torch.stack([m[0] for m in memory.memory]), torch.stack([m[1] for m in memory.memory]))
-    trainer.memory, trainer.data_loader = dmem, None
+    dmem = vec.memory
     policy.engine().set_precision(args.precision)
-    vec = VecExplorer(policy, B, env.env_params(), dmem, policy.gamma, human_num=n, rule=env.train_val_sim,
-                      seed=args.seed * 1000 + rank)
     vec.update_target_model(model)
     eps_start, eps_end, eps_decay = eps_sched
     base_case = env.case_counter["train"]

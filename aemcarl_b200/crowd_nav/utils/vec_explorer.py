@@ -97,9 +97,10 @@ class VecExplorer(object):
     `num_envs` episodes are in flight at once."""
 
     def __init__(self, policy, num_envs, env_params, memory=None, gamma=None, human_num=5, rule="circle_crossing",
-                 seed=0, scenario_kw=None):
+                 seed=0, scenario_kw=None, il_safety_space=0.0):
         self.policy = policy
         self.env_params = env_params          # aem_env_params of the configured CrowdSim (env.env_params())
+        self.il_safety_space = float(il_safety_space)     # [imitation_learning] safety_space of the ORCA teacher
         self.B = int(num_envs)
         self.n = int(human_num)
         self.rule = rule
@@ -133,8 +134,6 @@ class VecExplorer(object):
     def run_k_episodes(self, k, phase, update_memory=False, imitation_learning=False, episode=None, epsilon=None,
                        first_case=None, print_failure=False):
         from aemcarl_b200.vec_env import VecCrowdSim
-        if imitation_learning:
-            raise NotImplementedError("the ORCA teacher of the imitation phase runs through the serial Explorer")
         if update_memory and (self.memory is None or self.gamma is None):
             raise ValueError("Memory or gamma value is not set!")
         pol = self.policy
@@ -171,16 +170,20 @@ class VecExplorer(object):
         env_steps = 0
         pushed = 0
 
+        il_eng = self._teacher_engine() if imitation_learning else None
         while active.any():
             cur = eng.transform(env.robot, env.humans)                      # last_state of every env
-            best = env.lookahead()
-            if eps > 0.0:
-                explore = torch.rand((B,), device=dev, generator=self.gen) < eps
-                rnd = torch.randint(0, eng.A, (B,), device=dev, generator=self.gen, dtype=torch.int32)
-                # the goal short-circuit (action 0 inside the goal disc) precedes the epsilon draw (multi_human_rl.py:321)
-                at_goal = torch.linalg.norm(env.robot[:, 0:2] - env.robot[:, 5:7], dim=1) < env.robot[:, 4]
-                best = torch.where(explore & ~at_goal, rnd, best)
-            reward, done, info, dmin = env.apply(best, auto_reset=False)
+            if imitation_learning:
+                reward, done, info, dmin = self._teacher_step(env, eng, il_eng, v_pref)
+            else:
+                best = env.lookahead()
+                if eps > 0.0:
+                    explore = torch.rand((B,), device=dev, generator=self.gen) < eps
+                    rnd = torch.randint(0, eng.A, (B,), device=dev, generator=self.gen, dtype=torch.int32)
+                    # the goal short-circuit (action 0 inside the goal disc) precedes the epsilon draw (multi_human_rl.py:321)
+                    at_goal = torch.linalg.norm(env.robot[:, 0:2] - env.robot[:, 5:7], dim=1) < env.robot[:, 4]
+                    best = torch.where(explore & ~at_goal, rnd, best)
+                reward, done, info, dmin = env.apply(best, auto_reset=False)
             traj_s[rows, step_idx] = cur
             traj_r[rows, step_idx] = reward
             step_idx += 1
@@ -207,7 +210,7 @@ class VecExplorer(object):
             cum_reward[cases] = cr
             store = fin[np.isin(info_h[fin], (INFO_REACHGOAL, INFO_COLLISION))]
             if update_memory and len(store):
-                pushed += self._store(traj_s, traj_r, step_idx, store, gbar)
+                pushed += self._store(traj_s, traj_r, step_idx, store, gbar, imitation_learning)
             # next cases for the finished envs
             for b in fin:
                 if next_case < k:
@@ -250,8 +253,29 @@ class VecExplorer(object):
     def _case_size(self, phase):
         return {"train": np.iinfo(np.uint32).max - 2000, "val": 100, "test": 500}[phase]
 
-    def _store(self, traj_s, traj_r, step_idx, envs, gbar):
-        """RL targets of the finished episodes `envs` (explorer.py:132-139) -> replay memory, one batched target forward"""
+    def _teacher_engine(self):
+        """a second engine whose ORCA parameters are the teacher's (orca.py:82-132 with [imitation_learning] safety_space)"""
+        import copy
+        from aemcarl_b200.engine import get_engine
+        il = get_engine(self.device.index or 0, role="il_teacher")
+        p = copy.copy(self.env_params)
+        p.robot_visible = 0
+        p.orca_safety_space = self.il_safety_space
+        il.set_env_params(p)
+        return il
+
+    def _teacher_step(self, env, eng, il_eng, max_speed):
+        """robot.act(ob) with the ORCA teacher + env.step(action) for every env (explorer.py:51-53 in the imitation phase):
+        the humans move by their own ORCA solve (robot seen only if visible); the robot's action is agent 0 of ITS
+        simulator = the robot appended to the humans as one more ORCA agent, solved with the teacher's safety space."""
+        eng.orca(env.humans, env.robot, out=env.new_vel)
+        agents = torch.cat([env.humans, env.robot[:, None, :8]], dim=1).contiguous()
+        action = il_eng.orca(agents, env.robot)[:, self.n, :].contiguous()
+        return eng.env_step_xy(env.robot, env.humans, env.new_vel, env.global_time, action, max_speed)
+
+    def _store(self, traj_s, traj_r, step_idx, envs, gbar, imitation_learning=False):
+        """targets of the finished episodes `envs` -> replay memory.  RL (explorer.py:132-139): one batched target
+        forward; imitation (explorer.py:126-130): discounted Monte-Carlo return of the rest of the episode."""
         dev = self.device
         eb = torch.from_numpy(np.asarray(envs)).to(dev)
         lens = step_idx[eb]
@@ -262,7 +286,11 @@ class VecExplorer(object):
         states = traj_s[eb]                                    # [m, tmax, n, 13]
         rewards = traj_r[eb]
         values = rewards.clone()
-        if has_next.any():
+        if imitation_learning:
+            disc = torch.pow(torch.tensor(gbar, dtype=torch.float64, device=dev), t.to(torch.float64))     # gbar^s
+            tail = torch.flip(torch.cumsum(torch.flip(rewards * disc * valid, dims=[1]), dim=1), dims=[1])
+            values = tail / disc                                   # sum_{s >= i} gbar^(s - i) r_s
+        elif has_next.any():
             nxt = torch.roll(states, -1, dims=1)[has_next]     # state_{i+1} of every non-final step
             v = self._target_values(nxt).to(torch.float64)
             values[has_next] = rewards[has_next] + gbar * v

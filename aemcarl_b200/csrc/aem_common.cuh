@@ -160,10 +160,11 @@ cudaError_t launch_orca(int B, int n, const double *humans, const double *robot,
                         double *new_vel, cudaStream_t st);
 cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const double *humans,
                                  const double *new_vel, const double *global_time, const double *actions,
-                                 const double *lut, const aem_env_params &p, double amax, double *rewards,
+                                 int action_env_stride, const double *lut, const aem_env_params &p, double amax, double *rewards,
                                  int32_t *info, double *dmin, double *humans_next, cudaStream_t st);
 cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans, const double *new_vel,
-                             double *global_time, const double *actions, const int32_t *chosen,
+                             double *global_time, const double *actions, int action_env_stride,
+                             const int32_t *chosen,
                              const double *rewards, const int32_t *info, const double *dmin, double time_step,
                              double *out_reward, int32_t *out_done, int32_t *out_info, double *out_dmin,
                              cudaStream_t st);

@@ -570,7 +570,7 @@ int aem_env_lookahead(aem_handle h, int B, int n, const double *robot_d, const d
     if (!robot_d || !humans_d || !new_vel_d || !global_time_d || !rewards_d)
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
-    AEM_CUDA_CHECK(launch_env_lookahead(B, n, h->A, robot_d, humans_d, new_vel_d, global_time_d, h->actions_d,
+    AEM_CUDA_CHECK(launch_env_lookahead(B, n, h->A, robot_d, humans_d, new_vel_d, global_time_d, h->actions_d, 0,
                                         h->lut_d, h->params, action_amax(h), rewards_d, info_d, dmin_d,
                                         humans_next_d, as_stream(stream)));
     h->launches += (B > 0);
@@ -622,10 +622,33 @@ int aem_env_apply(aem_handle h, int B, int n, double *robot_d, double *humans_d,
     if (!robot_d || !humans_d || !new_vel_d || !global_time_d || !chosen_d)
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
-    AEM_CUDA_CHECK(launch_env_apply(B, n, h->A, robot_d, humans_d, new_vel_d, global_time_d, h->actions_d, chosen_d,
+    AEM_CUDA_CHECK(launch_env_apply(B, n, h->A, robot_d, humans_d, new_vel_d, global_time_d, h->actions_d, 0, chosen_d,
                                     rewards_d, info_d, dmin_d, h->params.time_step, out_reward_d, out_done_d,
                                     out_info_d, out_dmin_d, as_stream(stream)));
     h->launches += (B > 0);
+    return AEM_OK;
+}
+
+int aem_env_step_xy(aem_handle h, int B, int n, double *robot_d, double *humans_d, const double *new_vel_d,
+                    double *global_time_d, const double *actions_d, double max_speed, double *scratch_d,
+                    double *out_reward_d, int32_t *out_done_d, int32_t *out_info_d, double *out_dmin_d, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (!h->params_set) return aem_set_error(AEM_ERR_STATE, "aem_set_env_params has not been called");
+    if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (B == 0) return AEM_OK;
+    if (!robot_d || !humans_d || !new_vel_d || !global_time_d || !actions_d || !scratch_d || !out_reward_d)
+        return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    // scratch: rewards [B] f64 | dmin [B] f64 | info [B] i32 of the one action of every environment
+    double *rew = scratch_d, *dmn = scratch_d + B;
+    int32_t *inf = reinterpret_cast<int32_t *>(scratch_d + 2 * (size_t)B);
+    AEM_CUDA_CHECK(launch_env_lookahead(B, n, 1, robot_d, humans_d, new_vel_d, global_time_d, actions_d, 2, h->lut_d,
+                                        h->params, max_speed, rew, inf, dmn, nullptr, as_stream(stream)));
+    AEM_CUDA_CHECK(launch_env_apply(B, n, 1, robot_d, humans_d, new_vel_d, global_time_d, actions_d, 2, nullptr, rew, inf,
+                                    dmn, h->params.time_step, out_reward_d, out_done_d, out_info_d, out_dmin_d,
+                                    as_stream(stream)));
+    h->launches += 2;
     return AEM_OK;
 }
 

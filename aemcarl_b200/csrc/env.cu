@@ -102,8 +102,8 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 
 __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
     int B, int n, int A, const double *__restrict__ robot, const double *__restrict__ humans,
-    const double *__restrict__ new_vel, const double *__restrict__ global_time, const double *__restrict__ actions,
-    const double *__restrict__ lut, const aem_env_params p, double amax, int tile_cap,
+    const double *__restrict__ new_vel, const double *__restrict__ global_time, const double *__restrict__ actions_all,
+    int action_env_stride, const double *__restrict__ lut, const aem_env_params p, double amax, int tile_cap,
     double *__restrict__ rewards, int32_t *__restrict__ info, double *__restrict__ dmin_out,
     double *__restrict__ humans_next)
 {
@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
+    // shared action table (stride 0) or one private table per environment (arbitrary ActionXY per env, stride 2 A)
+    const double *__restrict__ actions = actions_all + (size_t)b * action_env_stride;
     for (int i = tid; i < n * 8; i += ENV_THREADS) sh[i] = humans[(size_t)b * n * 8 + i];
     if (tid < 9) sr9[tid] = robot[(size_t)b * 9 + tid];
     if (tid < AEM_MAX_ACTIONS) prob[tid] = 0.0;
@@ -222,7 +224,8 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
 
 __global__ void env_apply_kernel(int B, int n, int A, double *__restrict__ robot, double *__restrict__ humans,
                                  const double *__restrict__ new_vel, double *__restrict__ global_time,
-                                 const double *__restrict__ actions, const int32_t *__restrict__ chosen,
+                                 const double *__restrict__ actions_all, int action_env_stride,
+                                 const int32_t *__restrict__ chosen,
                                  const double *__restrict__ rewards, const int32_t *__restrict__ info,
                                  const double *__restrict__ dmin, double time_step, double *__restrict__ out_reward,
                                  int32_t *__restrict__ out_done, int32_t *__restrict__ out_info,
@@ -230,8 +233,9 @@ __global__ void env_apply_kernel(int B, int n, int A, double *__restrict__ robot
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    int a = chosen[b];
+    int a = chosen ? chosen[b] : 0;
     if (a < 0 || a >= A) a = 0;
+    const double *__restrict__ actions = actions_all + (size_t)b * action_env_stride;
     const double ax = actions[2 * a], ay = actions[2 * a + 1];
     if (rewards && out_reward) out_reward[b] = rewards[(size_t)b * A + a];
     if (info) {
@@ -258,7 +262,7 @@ static int g_tile_cap[64] = {0};     // per device: cudaFuncSetAttribute is a pe
 
 cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const double *humans,
                                     const double *new_vel, const double *global_time, const double *actions,
-                                    const double *lut, const aem_env_params &p, double amax, double *rewards,
+                                    int action_env_stride, const double *lut, const aem_env_params &p, double amax, double *rewards,
                                     int32_t *info, double *dmin, double *humans_next, cudaStream_t st)
 {
     if (B <= 0) return cudaSuccess;
@@ -274,13 +278,15 @@ cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const
         if (e != cudaSuccess) return e;
         g_tile_cap[dev & 63] = tile_cap;
     }
-    env_lookahead_kernel<<<B, ENV_THREADS, smem, st>>>(B, n, A, robot, humans, new_vel, global_time, actions, lut, p,
+    env_lookahead_kernel<<<B, ENV_THREADS, smem, st>>>(B, n, A, robot, humans, new_vel, global_time, actions,
+                                                       action_env_stride, lut, p,
                                                        amax, tile_cap, rewards, info, dmin, humans_next);
     return cudaGetLastError();
 }
 
 cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans, const double *new_vel,
-                             double *global_time, const double *actions, const int32_t *chosen,
+                             double *global_time, const double *actions, int action_env_stride,
+                             const int32_t *chosen,
                              const double *rewards, const int32_t *info, const double *dmin, double time_step,
                              double *out_reward, int32_t *out_done, int32_t *out_info, double *out_dmin,
                              cudaStream_t st)
@@ -288,7 +294,8 @@ cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans,
     if (B <= 0) return cudaSuccess;
     const int threads = 128;
     env_apply_kernel<<<(B + threads - 1) / threads, threads, 0, st>>>(B, n, A, robot, humans, new_vel, global_time,
-                                                                      actions, chosen, rewards, info, dmin, time_step,
+                                                                      actions, action_env_stride, chosen, rewards, info,
+                                                                      dmin, time_step,
                                                                       out_reward, out_done, out_info, out_dmin);
     return cudaGetLastError();
 }

@@ -161,6 +161,23 @@ class Engine:
         check(self.lib.aem_gru_act(self.h, S, T, _ptr(x), _ptr(out), _ptr(steps), self._stream()))
         return out, steps
 
+    def env_step_xy(self, robot, humans, new_vel, global_time, actions, max_speed):
+        """CrowdSim.step with one arbitrary ActionXY per env (actions [B,2] f64); updates the state in place and returns
+        (reward f64, done i32, info i32, dmin f64), each [B]"""
+        B, n, _ = humans.shape
+        for t in (robot, humans, new_vel, global_time, actions):
+            self._chk(t, F64)
+        dev = self.device
+        scratch = torch.empty((3 * B,), dtype=F64, device=dev)
+        reward = torch.empty((B,), dtype=F64, device=dev)
+        done = torch.empty((B,), dtype=I32, device=dev)
+        info = torch.empty((B,), dtype=I32, device=dev)
+        dmin = torch.empty((B,), dtype=F64, device=dev)
+        check(self.lib.aem_env_step_xy(self.h, B, n, _ptr(robot), _ptr(humans), _ptr(new_vel), _ptr(global_time),
+                                       _ptr(actions), float(max_speed), _ptr(scratch), _ptr(reward), _ptr(done),
+                                       _ptr(info), _ptr(dmin), self._stream()))
+        return reward, done, info, dmin
+
     def transform(self, robot, humans, out=None):
         """MultiHumanRL.transform of every env: robot [B,9] f64, humans [B,n,8] f64 -> rotated states [B,n,13] f32"""
         B, n, _ = humans.shape

@@ -16,6 +16,7 @@
  *   aem_env_reset_done  <- CrowdSim.reset for finished episodes of a batch (crowd_sim.py:486-552, explorer.py:44-47)
  *   aem_value_forward   <- model(state) on already rotated states (explorer.py:137, trainer.py:52,75)
  *   aem_gru_act         <- ATCBasic.forward components.py:107-137 (fused GRU-cell / adaptive-computation-time)
+ *   aem_env_step_xy     <- CrowdSim.step for one arbitrary ActionXY per environment (imitation phase, train.py:171-204)
  *   aem_transform       <- MultiHumanRL.transform multi_human_rl.py:423-438 (replay-memory sample of the current state)
  *   aem_decide_step_host<- Robot.act + CrowdSim.step through HOST buffers (explorer.py:51-53), the e2e call
  *
@@ -136,6 +137,14 @@ int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *
 
 /* x_d [S*T][13] f32, rows grouped in samples of T tokens -> out_d [S*T][50] f32, steps_d [S] u8 (may be NULL) */
 int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint8_t *steps_d, void *stream);
+
+/* CrowdSim.step(action) (crowd_sim.py:557-691) with ONE arbitrary ActionXY per environment -- what the imitation phase
+ * needs, where the robot executes the continuous ORCA velocity (train.py:171-204, explorer.py:51-53).
+ * actions_d [B][2] f64; max_speed >= every |action| (bounds the occupancy-map culling); scratch_d: 3 B doubles.
+ * Updates robot_d / humans_d / global_time_d in place like aem_env_apply; out_* [B]. */
+int aem_env_step_xy(aem_handle h, int B, int n, double *robot_d, double *humans_d, const double *new_vel_d,
+                    double *global_time_d, const double *actions_d, double max_speed, double *scratch_d,
+                    double *out_reward_d, int32_t *out_done_d, int32_t *out_info_d, double *out_dmin_d, void *stream);
 
 /* MultiHumanRL.transform (multi_human_rl.py:423-438): rotate() of the current joint state of every environment, the
  * sample Explorer stores in the replay memory.  robot_d [B][9] f64, humans_d [B][n][8] f64 -> states_d [B][n][13] f32 */

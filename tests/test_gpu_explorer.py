@@ -93,14 +93,49 @@ def test_epsilon_greedy_and_training_on_the_device_memory():
 
 
 def test_train_entry_point_with_the_vectorised_rl_phase(tmp_path):
-    """train.py --vectorised B: imitation data moves into the device memory, waves of B episodes add to it, the
-    optimizer runs on device-gathered mini-batches, the target network is refreshed across a wave boundary."""
+    """train.py --vectorised B: the imitation phase (ORCA teacher) and the RL waves both run B episodes in lock-step and
+    fill the device memory, the optimizer runs on device-gathered mini-batches, the target network is refreshed across a
+    wave boundary."""
     from aemcarl_b200.crowd_nav import train
     out = train.main(["--output_dir", str(tmp_path), "--il_episodes", "6", "--il_epochs", "2", "--train_episodes", "64",
                       "--vectorised", "32", "--updates_per_wave", "4"])
     ex = out["explorer"]
-    assert len(ex.device_memory) > out["memory"] > 50          # RL experience was added to the imitation data
+    assert out["memory"] == len(ex.device_memory) > 50         # imitation + RL experience, all in the device memory
     assert ex.vec_stats["success"] + ex.vec_stats["collision"] + ex.vec_stats["timeout"] == 32
     assert ex.vec.case_counter["train"] > 0
     assert (tmp_path / "rl_model.pth").exists()
     assert all(torch.isfinite(p).all() for p in out["model"].parameters())
+
+
+def test_vectorised_imitation_phase_reproduces_the_serial_teacher():
+    """Imitation learning (train.py:171-204): the robot follows the ORCA teacher (safety_space 0.15), every step is
+    stored with the discounted Monte-Carlo return.  Vectorised (robot appended to the humans as one more ORCA agent,
+    aem_env_step_xy for the continuous action) against the serial drop-in Explorer on the same 6 cases."""
+    from aemcarl_b200.crowd_nav.policy.policy_factory import policy_factory
+    env, robot, policy = setup()
+    dev = torch.device("cuda:0")
+    teacher = policy_factory["orca"]()
+    teacher.multiagent_training = policy.multiagent_training
+    teacher.safety_space = 0.15
+    robot.set_policy(teacher)
+    k = 6
+    mem = ReplayMemory(100000)
+    serial = Explorer(env, robot, dev, mem, policy.gamma, target_policy=policy)
+    env.case_counter["train"] = 0
+    s_stats = serial.run_k_episodes(k, "train", update_memory=True, imitation_learning=True)
+    s_states = [m[0].cpu().numpy() for m in mem.memory]
+    s_values = [m[1].item() for m in mem.memory]
+    params = env.env_params()
+    params.orca_safety_space = 0.0          # the humans' own ORCA (env.env_params() reads it from the humans' policy)
+
+    dmem = DeviceReplayMemory(100000, 5, dev)
+    vec = VecExplorer(policy, 4, params, dmem, policy.gamma, human_num=5, il_safety_space=0.15)
+    v_stats = vec.run_k_episodes(k, "train", update_memory=True, imitation_learning=True, first_case=0)
+    for key in ("success", "collision", "timeout", "too_close"):
+        assert v_stats[key] == s_stats[key], key
+    assert v_stats["avg_nav_time"] == pytest.approx(s_stats["avg_nav_time"], abs=1e-9)
+    assert len(dmem) == len(mem) > 100
+    a_s, a_v = _sorted_pairs(s_states, s_values)
+    b_s, b_v = _sorted_pairs(dmem.states[:len(dmem)].cpu().numpy(), dmem.values[:len(dmem)].cpu().numpy())
+    assert np.allclose(a_s, b_s, atol=2e-5), np.abs(a_s - b_s).max()
+    assert np.allclose(a_v, b_v, atol=2e-6), np.abs(a_v - b_v).max()
