@@ -79,6 +79,32 @@ class ATCBasic(nn.Module):
                 break
         return accum_hx / step_count, step_count
 
+    def forward_static(self, input, hx=None):
+        """The same function without host-side control flow, so that a training step can be captured in a CUDA graph:
+        all max_ponder steps are evaluated and the result of the step at which the reference's batch-global test
+        (components.py:132-134) stops is selected with tensor masks.  step_count comes back as a 0-dim tensor."""
+        x = input.reshape(-1, input.shape[2])
+        if self.act_fixed:
+            for _ in range(self.act_steps):
+                hx = self.rnn_cell(x, hx)
+            return hx, self.act_steps
+        accum_p = torch.zeros([x.shape[0], 1], device=x.device, dtype=x.dtype)
+        accum_hx = torch.zeros([x.shape[0], self.rnn_hidden_dim], device=x.device, dtype=x.dtype)
+        out = torch.zeros_like(accum_hx)
+        count = torch.zeros((), device=x.device, dtype=torch.int64)
+        stopped = torch.zeros((), device=x.device, dtype=torch.bool)
+        for k in range(1, self.max_ponder + 1):
+            hx = self.rnn_cell(x, hx)
+            halten_p = torch.sigmoid(self.ponder_linear(hx))
+            accum_p = accum_p + halten_p
+            accum_hx = accum_hx + halten_p * hx
+            stop_now = ~((accum_p < 1 - self.epsilon).any()) if k < self.max_ponder else torch.ones_like(stopped)
+            take = stop_now & ~stopped
+            out = torch.where(take, accum_hx / k, out)
+            count = torch.where(take, torch.full_like(count, k), count)
+            stopped = stopped | stop_now
+        return out, count
+
 
 class ValueNetworkTransformerAndGRU(nn.Module):
     def __init__(self, input_dim=13, self_state_dim=6, joint_state_dim=13, in_mlp_dims=(100, 50),
@@ -155,14 +181,15 @@ class ValueNetworkTransformerAndGRU(nn.Module):
         tok[:, 12] = tok[:, 3]
         return tok.unsqueeze(1)
 
-    def forward_torch(self, state):
+    def forward_torch(self, state, static=False):
         """differentiable restatement of qnetwork_factory.py:641-687 (dropout inactive: the module is used in
-        eval mode -- see hazard 1 in SURVEY.md; call .train() to get the reference's stochastic behaviour)"""
+        eval mode -- see hazard 1 in SURVEY.md; call .train() to get the reference's stochastic behaviour).
+        static=True: no host-side control flow (CUDA-graph capturable), same result."""
         size = state.shape
         self_state = state[:, 0, :self.self_state_dim].clone().detach()
         x = torch.cat([self._robot_token(state), state], dim=1)
         h0 = torch.zeros([size[0] * (size[1] + 1), self.in_mlp_dims[-1]], device=state.device, dtype=state.dtype)
-        out, self.step_cnt = self.in_mlp(x, h0)
+        out, self.step_cnt = self.in_mlp.forward_static(x, h0) if static else self.in_mlp(x, h0)
         enc_in = out.view(size[0], -1, 50).transpose(0, 1).contiguous()
         enc_out = self.transformer_encoder(enc_in).transpose(0, 1).contiguous()
         env_info = enc_out[:, 0, :]

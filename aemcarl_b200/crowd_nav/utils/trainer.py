@@ -44,8 +44,63 @@ def broadcast_parameters(model, src=0):
             dist.broadcast(p, src)
 
 
+class GraphedStep(object):
+    """One optimisation step as CUDA graphs: graph 1 = zero the gradients, forward (control-flow-free ACT,
+    value_network.forward_torch(static=True)), MSE, backward; then the flat gradient all-reduce of the data-parallel
+    run; graph 2 = the optimizer step (Adam with capturable=True).  ~150 tiny kernels per step are replayed with two
+    launches instead of being issued one by one from Python.  The warm-up steps capture needs are undone (parameters
+    and optimizer state are restored in place), so a graphed run equals an eager run step for step."""
+
+    def __init__(self, model, optimizer, criterion, inputs, values):
+        self.model, self.optimizer = model, optimizer
+        self.inputs = inputs.detach().clone()
+        self.values = values.detach().clone()
+        params = [p for p in model.parameters()]
+        saved_p = [p.detach().clone() for p in params]
+        saved_s = {id(t): t.detach().clone() for st in optimizer.state.values() for t in st.values()
+                   if torch.is_tensor(t)}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                optimizer.zero_grad(set_to_none=True)
+                out, _ = model.forward_torch(self.inputs, static=True)
+                criterion(out, self.values).backward()
+                optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.fwd_bwd = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.fwd_bwd):
+            out, _ = model.forward_torch(self.inputs, static=True)
+            self.loss = criterion(out, self.values)
+            self.loss.backward()
+        self.opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.opt):
+            optimizer.step()
+        with torch.no_grad():                      # undo the warm-up and the capture-time step
+            for p, q in zip(params, saved_p):
+                p.copy_(q)
+            for st in optimizer.state.values():
+                for t in st.values():
+                    if torch.is_tensor(t):
+                        t.copy_(saved_s[id(t)]) if id(t) in saved_s else t.zero_()
+
+    def matches(self, inputs, values):
+        return inputs.shape == self.inputs.shape and values.shape == self.values.shape and inputs.is_cuda
+
+    def __call__(self, inputs, values):
+        self.inputs.copy_(inputs)
+        self.values.copy_(values)
+        self.fwd_bwd.replay()
+        allreduce_gradients(self.model)
+        self.opt.replay()
+        return self.loss.detach().clone()
+
+
 class Trainer(object):
-    def __init__(self, model, memory, device, batch_size):
+    def __init__(self, model, memory, device, batch_size, cuda_graph=False):
+        self.cuda_graph = bool(cuda_graph)
+        self._graphed = None
         self.model = model
         self.device = device
         self.criterion = nn.MSELoss().to(device)
@@ -56,8 +111,10 @@ class Trainer(object):
 
     def set_learning_rate(self, learning_rate, optimizer_type="SGD"):
         logging.info("Current learning rate: %f,Optimizer Type %s", learning_rate, optimizer_type)
+        self._graphed = None
         if optimizer_type == "Adam":
-            self.optimizer = optim.Adam(self.model.parameters(), lr=learning_rate, betas=(0.9, 0.99), eps=1e-03)
+            self.optimizer = optim.Adam(self.model.parameters(), lr=learning_rate, betas=(0.9, 0.99), eps=1e-03,
+                                        capturable=self.cuda_graph)
         elif optimizer_type == "RMSprop":
             self.optimizer = optim.RMSprop(self.model.parameters(), lr=learning_rate, alpha=0.9)
         else:
@@ -66,13 +123,18 @@ class Trainer(object):
             self.optimizer = optim.SGD(self.model.parameters(), lr=learning_rate, momentum=0.9, weight_decay=0.00)
 
     def _step(self, inputs, values):
+        """one optimisation step; returns the loss as a 0-dim tensor (the callers synchronise once per call, not per step)"""
+        if self.cuda_graph and isinstance(self.optimizer, optim.Adam):
+            if self._graphed is None or not self._graphed.matches(inputs, values):
+                self._graphed = GraphedStep(self.model, self.optimizer, self.criterion, inputs, values)
+            return self._graphed(inputs, values)
         self.optimizer.zero_grad()
         outputs, _ = self.model(inputs)
         loss = self.criterion(outputs, values)
         loss.backward()
         allreduce_gradients(self.model)
         self.optimizer.step()
-        return loss.data.item()
+        return loss.detach()
 
     def _device_memory(self):
         """DeviceReplayMemory (utils/vec_explorer.py): mini-batches are gathered on the device, no DataLoader"""
@@ -93,8 +155,8 @@ class Trainer(object):
             for i, (inputs, values) in enumerate(batches):
                 if i >= steps_per_epoch:
                     break
-                epoch_loss += self._step(inputs, values)
-            average_epoch_loss = epoch_loss / len(self.memory)
+                epoch_loss = epoch_loss + self._step(inputs, values)
+            average_epoch_loss = float(epoch_loss) / len(self.memory)
             logging.debug("Average loss in epoch %d: %.2E", epoch, average_epoch_loss)
         return average_epoch_loss
 
@@ -107,7 +169,7 @@ class Trainer(object):
         losses = 0
         for _ in range(num_batches):
             inputs, values = self.memory.sample(self.batch_size) if fast else next(iter(self.data_loader))
-            losses += self._step(inputs, values)
-        average_loss = losses / num_batches
+            losses = losses + self._step(inputs, values)
+        average_loss = float(losses) / num_batches
         logging.debug("Average loss : %.2E", average_loss)
         return average_loss

@@ -98,7 +98,7 @@ def test_train_entry_point_with_the_vectorised_rl_phase(tmp_path):
     wave boundary."""
     from aemcarl_b200.crowd_nav import train
     out = train.main(["--output_dir", str(tmp_path), "--il_episodes", "6", "--il_epochs", "2", "--train_episodes", "64",
-                      "--vectorised", "32", "--updates_per_wave", "4"])
+                      "--vectorised", "32", "--updates_per_wave", "4", "--cuda_graph"])
     ex = out["explorer"]
     assert out["memory"] == len(ex.device_memory) > 50         # imitation + RL experience, all in the device memory
     assert ex.vec_stats["success"] + ex.vec_stats["collision"] + ex.vec_stats["timeout"] == 32
@@ -139,3 +139,28 @@ def test_vectorised_imitation_phase_reproduces_the_serial_teacher():
     b_s, b_v = _sorted_pairs(dmem.states[:len(dmem)].cpu().numpy(), dmem.values[:len(dmem)].cpu().numpy())
     assert np.allclose(a_s, b_s, atol=2e-5), np.abs(a_s - b_s).max()
     assert np.allclose(a_v, b_v, atol=2e-6), np.abs(a_v - b_v).max()
+
+
+def test_cuda_graph_training_step_equals_the_eager_step():
+    """the optimisation step replayed from CUDA graphs (control-flow-free ACT, Adam capturable) walks the
+    same trajectory as the eager step: same losses and parameters after 6 steps on the same mini-batches, and the
+    warm-up / capture leaves no trace."""
+    import copy
+    env, robot, policy = setup(seed=4, ponder_bias=-0.13)        # weights whose halting step varies with the batch
+    dev = torch.device("cuda:0")
+    model_a = policy.get_model()
+    model_b = copy.deepcopy(model_a).to(dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    batches = [(torch.randn((100, 5, 13), device=dev, generator=g), torch.randn((100, 1), device=dev, generator=g))
+               for _ in range(6)]
+    losses = {}
+    for name, model, graph in (("eager", model_a, False), ("graph", model_b, True)):
+        tr = Trainer(model, None, dev, 100, cuda_graph=graph)
+        tr.cuda_graph = True                      # both use Adam(capturable=True); only one replays graphs
+        tr.set_learning_rate(1e-3, "Adam")
+        tr.cuda_graph = graph
+        losses[name] = [float(tr._step(x, v)) for x, v in batches]
+    assert np.allclose(losses["eager"], losses["graph"], rtol=1e-5, atol=1e-7), (losses["eager"], losses["graph"])
+    for pa, pb in zip(model_a.parameters(), model_b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6)
+    assert losses["graph"][0] != losses["graph"][-1]

@@ -181,3 +181,29 @@ def test_device_replay_memory_ring_matches_reference_ring():
     assert seen.numel() == 6 and len(set(seen.reshape(-1).tolist())) == 6
     dev.clear()
     assert len(dev) == 0
+
+
+def test_control_flow_free_act_equals_the_reference_loop():
+    """ATCBasic.forward_static (CUDA-graph capturable) == ATCBasic.forward (components.py:107-137, batch-global halting)
+    for weights that halt after 1, 2-3 and 3 steps, values and gradients"""
+    import torch
+    from aemcarl_b200 import weights as wts
+    from aemcarl_b200.crowd_nav.default_configs import policy_config
+    from aemcarl_b200.crowd_nav.policy.policy_factory import policy_factory
+    policy = policy_factory["actenvcarl"]()
+    policy.configure(policy_config())
+    model = policy.get_model()
+    counts = set()
+    for seed, pb in ((1, None), (2, 4.0), (3, -1.0), (4, -0.13), (4, 0.9)):
+        model.load_flat_weights(wts.synthetic_weights(seed, pb))
+        x = torch.randn(9, 5, 13, generator=torch.Generator().manual_seed(seed))
+        grads = []
+        for static in (False, True):
+            model.zero_grad()
+            v, _ = model.forward_torch(x, static=static)
+            counts.add(int(model.step_cnt))
+            v.sum().backward()
+            grads.append((v.detach().clone(), [p.grad.clone() for p in model.parameters() if p.grad is not None]))
+        assert torch.equal(grads[0][0], grads[1][0])
+        assert all(torch.allclose(a, b, rtol=1e-6, atol=1e-8) for a, b in zip(grads[0][1], grads[1][1]))
+    assert len(counts) >= 2
