@@ -13,6 +13,14 @@ def average(input_list):
     return sum(input_list) / len(input_list) if input_list else 0
 
 
+def summary_line(phase, episode, success_rate, collision_rate, avg_nav_time, total_reward):
+    """The per-run summary of explorer.py:98-100, character for character: crowd_nav/utils/plot.py:38-55 parses the
+    TRAIN / VAL lines of output.log with regular expressions."""
+    extra_info = "" if episode is None else "in episode {} ".format(episode)
+    return "{:<5} {}has success rate: {:.2f}, collision rate: {:.2f}, nav time: {:.2f}, total reward: {:.4f}".format(
+        phase.upper(), extra_info, success_rate, collision_rate, avg_nav_time, total_reward)
+
+
 class Explorer(object):
     def __init__(self, env, robot, device, memory=None, gamma=None, target_policy=None):
         self.env = env
@@ -75,10 +83,8 @@ class Explorer(object):
         collision_rate = collision / k
         assert success + collision + timeout == k
         avg_nav_time = sum(success_times) / len(success_times) if success_times else self.env.time_limit
-        extra_info = "" if episode is None else "in episode {} ".format(episode)
-        logging.info("{:<5} {}has success rate: {:.2f}, collision rate: {:.2f}, nav time: {:.2f}, total reward: {:.4f}"
-                     .format(phase.upper(), extra_info, success_rate, collision_rate, avg_nav_time,
-                             average(cumulative_rewards)))
+        logging.info(summary_line(phase, episode, success_rate, collision_rate, avg_nav_time,
+                                  average(cumulative_rewards)))
         if phase in ["val", "test"]:
             total_time = sum(success_times + collision_times + timeout_times) * self.robot.time_step
             logging.info("Frequency of being in danger: %.2f and average min separate distance in danger: %.2f",

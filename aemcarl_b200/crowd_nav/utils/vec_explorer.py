@@ -21,7 +21,7 @@ import logging
 import numpy as np
 import torch
 
-from aemcarl_b200.crowd_nav.utils.explorer import average
+from aemcarl_b200.crowd_nav.utils.explorer import average, summary_line
 
 INFO_DANGER, INFO_REACHGOAL, INFO_COLLISION, INFO_TIMEOUT = 1, 2, 3, 4
 
@@ -235,9 +235,7 @@ class VecExplorer(object):
         time_limit = eng.params.time_limit
         s_times = nav_time[codes == INFO_REACHGOAL]
         avg_nav_time = float(s_times.mean()) if len(s_times) else time_limit
-        extra = "" if episode is None else "in episode {} ".format(episode)
-        logging.info("{:<5} {}has success rate: {:.2f}, collision rate: {:.2f}, nav time: {:.2f}, total reward: {:.4f}"
-                     .format(phase.upper(), extra, success / k, collision / k, avg_nav_time, average(list(cum_reward))))
+        logging.info(summary_line(phase, episode, success / k, collision / k, avg_nav_time, average(list(cum_reward))))
         if phase in ["val", "test"]:
             total_time = (nav_time[codes != INFO_TIMEOUT].sum() + time_limit * timeout) * dt
             logging.info("Frequency of being in danger: %.2f and average min separate distance in danger: %.2f",

@@ -207,3 +207,19 @@ def test_control_flow_free_act_equals_the_reference_loop():
         assert torch.equal(grads[0][0], grads[1][0])
         assert all(torch.allclose(a, b, rtol=1e-6, atol=1e-8) for a, b in zip(grads[0][1], grads[1][1]))
     assert len(counts) >= 2
+
+
+def test_summary_lines_are_parsed_by_the_reference_plot_tool():
+    """output.log compatibility: the TRAIN / VAL summary lines match what crowd_nav/utils/plot.py:38-55
+    extracts (episode, success rate, collision rate, nav time, total reward)"""
+    import re
+    from aemcarl_b200.crowd_nav.utils.explorer import summary_line
+    fields = (r" in episode (?P<episode>\d+) has success rate: (?P<sr>[0-1].\d+), collision rate: (?P<cr>[0-1].\d+), "
+              r"nav time: (?P<time>\d+.\d+), total reward: (?P<reward>[-+]?\d+.\d+)")
+    for phase, tag in (("train", "TRAIN"), ("val", "VAL  ")):
+        line = summary_line(phase, 1200, 0.83, 0.05, 11.25, -0.03125)
+        m = re.search(tag + fields, line)
+        assert m, line
+        assert (int(m["episode"]), float(m["sr"]), float(m["cr"]), float(m["time"])) == (1200, 0.83, 0.05, 11.25)
+        assert float(m["reward"]) == -0.0312 or float(m["reward"]) == -0.0313
+    assert summary_line("test", None, 1.0, 0.0, 10.5, 0.3).startswith("TEST  has success rate: 1.00, collision rate: 0.00")
