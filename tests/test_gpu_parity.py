@@ -123,6 +123,37 @@ def test_env_lookahead_random_vs_oracle(engine, oracle, actions, n):
     engine.set_env_params(make_env_params())
 
 
+@pytest.mark.parametrize("n", [1, 5, 18])
+def test_env_step_xy_vs_oracle(engine, oracle, n):
+    """aem_env_step_xy: CrowdSim.step (crowd_sim.py:557-691, update=True) with one ARBITRARY ActionXY per environment
+    (the imitation phase's continuous ORCA actions) against the oracle evaluated env by env with that env's action."""
+    rng = np.random.RandomState(700 + n)
+    B = 48
+    robot, humans, gt = random_states(rng, B, n)
+    gt[1] = 19.0
+    robot[2, 5:7] = robot[2, 0:2] + [0.05, 0.0]
+    acts = rng.uniform(-1.0, 1.0, (B, 2))
+    acts /= np.maximum(1.0, np.linalg.norm(acts, axis=1, keepdims=True))
+    acts[3] = 0.0
+    engine.set_env_params(make_env_params())
+    p = oracle.default_params()
+    nv = oracle.orca(humans, robot, p)
+    r_d, h_d, t_d = dev(robot.copy()), dev(humans.copy()), dev(gt.copy())
+    reward, done, info, dmin = [t.cpu().numpy() for t in engine.env_step_xy(r_d, h_d, dev(nv), t_d, dev(acts), 1.0)]
+    for b in range(B):
+        sl = slice(b, b + 1)
+        ref = oracle.env_lookahead(robot[sl], humans[sl], nv[sl], gt[sl], acts[sl], p)
+        assert abs(reward[b] - ref[0][0, 0]) <= 1e-12 and info[b] == ref[1][0, 0], b
+        assert done[b] == (1 if ref[1][0, 0] >= 2 else 0)
+        if np.isfinite(ref[2][0, 0]):
+            assert abs(dmin[b] - ref[2][0, 0]) <= 1e-15
+        r2, h2, t2 = robot[sl].copy(), humans[sl].copy(), gt[sl].copy()
+        oracle.env_apply(r2, h2, nv[sl], t2, acts[sl], np.zeros(1, dtype=np.int32), p)
+        assert np.array_equal(r_d[b].cpu().numpy(), r2[0]) and np.array_equal(h_d[b].cpu().numpy(), h2[0])
+        assert abs(t_d[b].item() - t2[0]) <= 1e-12
+    assert len(set(info.tolist())) >= 3
+
+
 def check_values(net, ref_net, steps, ref_steps, values, ref_values, best, ref_best, margin_of=None):
     """north-star tolerance.  `margin_of(b, a)` (optional) returns the oracle's ACT halting margin of sample (b, a):
     the halting test accum_p < 0.95 (components.py:132-134) is a hard threshold, so an implementation with different
