@@ -1,16 +1,23 @@
 // lookahead_h16.cu -- tensor-core lookahead kernel, FP16x3 operands, TWO tiles in flight per SM (sm_100a).
+// The shipped default (aem_set_precision mode 2).  History and measurements: profiles/r01_lookahead_h16_final_ncu.md.
 //
-// Same function and epilogue structure as lookahead_tc.cu, re-laid-out so that one 128-row tile needs only 256 TMEM
-// columns, <= 128 registers / thread and ~112 KB of shared memory; two CTAs then share an SM and the hardware overlaps
-// the MMA / commit latency of one tile with the epilogue of the other (lookahead_tc.cu serialises them: its ncu profile
-// shows 55 % of the warp time waiting on tcgen05.commit or CTA barriers).
-//   * operands: x = hi + lo with hi = fp16(x), lo = fp16(x - hi); D = A_hi W_hi + A_lo W_hi + A_hi W_lo with
-//     tcgen05.mma.kind::f16 (K = 16 per instruction, FP32 accumulation in TMEM).  For this network's value ranges the
-//     split carries ~22 mantissa bits (tools/tc_probe16.cu: ~1e-6 relative), same class as 3xTF32;
-//   * A operands are packed two fp16 per 32-bit TMEM column (even k in the low half) -> half the columns of TF32;
-//   * layers whose output feeds the next GEMM directly (z1, r1, linear1, action_mlp.0) are converted IN PLACE: each
-//     thread's accumulator columns become the (hi | lo) operand columns of the same thread;
-//   * weight images img[k/8][n][8] (fp16, hi and lo) stream through a 3 x 16 KB bulk-TMA ring.
+// Same function as lookahead.cu / lookahead_tc.cu, laid out so that one 128-row tile needs only 256 TMEM columns,
+// 128 registers / thread and 114 KB of shared memory; two CTAs then share an SM and the hardware overlaps the MMA /
+// commit latency of one tile with the epilogue of the other.
+//   * operands: x = hi + lo, hi and lo fp16; D = A_hi W_hi + A_lo W_hi + A_hi W_lo with tcgen05.mma.kind::f16 (K = 16
+//     per instruction, FP32 accumulation in TMEM): ~21-22 mantissa bits for this network's value ranges
+//     (tools/tc_probe16.cu: ~1e-6 relative), same class as 3xTF32;
+//   * A operands live in TMEM, two fp16 per 32-bit column (even k in the low half); layers whose output feeds the next
+//     GEMM directly (z1, r1, linear1, action_mlp.0) are converted IN PLACE, 16 accumulator columns -> 8 hi + 8 lo operand
+//     columns of the same thread, with the ReLU inside the conversions (hi rounds toward zero);
+//   * biases ride in the weight images: slot 31 of half 1 of every operand is kept at exactly 1.0 (capi.cu pack_h16);
+//   * weight images img[k/8][n][8] (fp16, hi and lo) stream through a 4 x 12 KB bulk-copy ring: warp 0 consumes (ring
+//     position in registers, chunk count published before each tcgen05.commit), lane 0 of warp 1 produces (releases the
+//     slots after the event, requests the next chunks from a flat table);
+//   * rows of a tile: token 0 of every sample first, so the last encoder layer and the action MLP (token 0 only) skip the
+//     epilogues of warps without such a row;
+//   * one copy of the gate (z / r), FFN-chunk and LayerNorm code (the two CTAs of an SM run half a tile apart: the
+//     instruction cache decides), attention with float4 key / value rows and a streaming softmax.
 // Layout of every layer (N / K permutation and padding) is defined in capi.cu pack_h16.
 #include <cuda_fp16.h>
 #include <stdio.h>
@@ -28,21 +35,21 @@ using namespace aemtc;
 
 constexpr int NT = 256;
 constexpr int NBUF = 4;                 // a two-layer issue group (in_proj heads, linear1 chunks) holds 4 chunks at once
-constexpr int WBUF_BYTES = 12288;       // 16 KB images (N*K = 8192 fp16) are streamed as two 8 KB k-halves
+constexpr int WBUF_BYTES = 12288;       // one N = 96, K = 64 image; 16 KB images (N*K = 8192 fp16) stream as two 8 KB k-halves
 constexpr int KV_PITCH = 116;           // [k head 0 (28) | k head 1 (28) | v head 0 (28) | v head 1 (28)] + 4: float4 access, conflict-free
 constexpr int NEV = 4;
 constexpr int PBLK_MAX = H16_PBLK_FLOATS;
 
 // ---- tensor-memory column map: 256 columns per CTA ----
 constexpr uint32_t A1 = 0;              // [h;x]   K = 64  : hi cols [0,32) lo cols [32,64)
-constexpr uint32_t D1 = 64;             // z1 / r1 accumulators N = 128 = [64 | 64]; converted in place to A2 (K = 128)
+constexpr uint32_t D1 = 64;             // z1 / r1 accumulators N = 128 = [64 | 64]; converted in place to A2 (K = 128, 8 x [hi8 | lo8])
 constexpr uint32_t D2 = 192;            // z2 / r2 / q accumulators N = 64
 constexpr uint32_t A3 = 64;             // [r*h;x] K = 64 (aliases the dead A2)
 constexpr uint32_t AE = 0;              // encoder stream operand K = 64
 constexpr uint32_t DIN = 64;            // in_proj accumulators, 2 heads x 96
 constexpr uint32_t AATT = 64;           // attention output operand K = 64 (D_IN is consumed by then)
 constexpr uint32_t DOUT = 128;          // out_proj accumulators N = 64
-constexpr uint32_t DF1A = 64, DF1B = 160;   // linear1 chunks N = 96 = [48 | 48]; converted in place (K = 96)
+constexpr uint32_t DF1A = 64, DF1B = 160;   // linear1 chunks N = 96 = [48 | 48]; converted in place (K = 96, 6 x [hi8 | lo8])
 constexpr uint32_t DF2 = 0;             // linear2 accumulators N = 64 (aliases the dead AE)
 constexpr uint32_t DA0 = 64;            // action_mlp.0 accumulators N = 128, converted in place
 constexpr uint32_t DA2 = 192;           // action_mlp.2 accumulators N = 64
