@@ -64,6 +64,9 @@ SYMBOLS = {
     "aem_env_step_xy": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, ctypes.c_double, _VP, _VP, _VP,
                                        _VP, _VP, _VP]),
     "aem_transform": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),
+    "aem_train_grad": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 8),
+    "aem_adam_step": (ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_double, ctypes.c_int, ctypes.c_double, _VP]),
     "aem_launch_count": (ctypes.c_longlong, [_VP]),
 }
 

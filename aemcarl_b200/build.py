@@ -22,6 +22,7 @@ SOURCES = {
     "lookahead_tc.cu": [],
     "lookahead_h16.cu": [],
     "lookahead_q16.cu": [],
+    "train.cu": [],
     "env.cu": ["-fmad=false"],   # FP64 env arithmetic is a sequence of individually rounded Python float ops
     "orca.cu": ["-fmad=false"],
     "capi.cu": [],

@@ -156,8 +156,13 @@ class ValueNetworkTransformerAndGRU(nn.Module):
         for k, v in wts.unflatten(flat).items():
             sd[k].copy_(torch.from_numpy(v.copy()))
 
+    def note_external_update(self):
+        """the parameters were updated through raw pointers (aem_adam_step): torch's version counters did not move"""
+        self._extern_version = getattr(self, "_extern_version", 0) + 1
+
     def _param_version(self):
-        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        return (getattr(self, "_extern_version", 0),) + tuple(p._version for p in self.parameters()) \
+            + tuple(p.data_ptr() for p in self.parameters())
 
     def sync_engine(self, engine):
         """(re)upload the weights to `engine` when any parameter changed since the last upload"""

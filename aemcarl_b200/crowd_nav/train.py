@@ -65,6 +65,8 @@ def main(argv=None):
                          "reference's one-episode-at-a-time loop")
     ap.add_argument("--cuda_graph", action="store_true",
                     help="replay the optimisation step (forward, MSE, backward, Adam) from CUDA graphs")
+    ap.add_argument("--fused_step", action="store_true",
+                    help="the optimisation step as hand-written kernels (csrc/train.cu: aem_train_grad + aem_adam_step)")
     ap.add_argument("--updates_per_wave", type=int, default=None,
                     help="optimizer steps after each wave of B episodes (default: train_batches x B, the reference's ratio)")
     ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3", "fp16x3q"],
@@ -93,7 +95,7 @@ def main(argv=None):
         memory = DeviceReplayMemory(tcfg.getint("train", "capacity"), args.human_num, device)
     else:
         memory = ReplayMemory(tcfg.getint("train", "capacity"))
-    trainer = Trainer(model, memory, device, batch_size, cuda_graph=args.cuda_graph)
+    trainer = Trainer(model, memory, device, batch_size, cuda_graph=args.cuda_graph, fused=args.fused_step)
     explorer = Explorer(env, robot, device, memory, policy.gamma, target_policy=policy)
 
     # ---- imitation learning (train.py:171-204)

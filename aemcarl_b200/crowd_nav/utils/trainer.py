@@ -97,9 +97,78 @@ class GraphedStep(object):
         return self.loss.detach().clone()
 
 
+class FusedStep(object):
+    """One optimisation step as hand-written kernels (csrc/train.cu): aem_train_grad (forward with the
+    reference's batch-global ACT halting + MSE + backward, three launches) -> the flat gradient all-reduce of the
+    data-parallel run -> aem_adam_step (one launch).  The live parameters of the module become views into ONE flat
+    float32[113752] vector in blob order, so the kernels, the NCCL all-reduce and the lookahead engine's weight upload all
+    work on the same memory without gather / scatter copies.  Adam moments are views into flat vectors too, and are
+    shared with the torch optimizer's state so optimizer.state_dict() stays meaningful."""
+
+    def __init__(self, model, optimizer, device):
+        from aemcarl_b200 import weights as wts
+        from aemcarl_b200.engine import get_engine
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("the fused training step is a CUDA kernel; there is no CPU fallback")
+        self.model, self.optimizer = model, optimizer
+        self.engine = get_engine(dev.index or 0, role="trainer")
+        self.engine.set_act_mode(model.act_fixed, model.act_steps)
+        named = dict(model.named_parameters())
+        self.flat = torch.empty(wts.NUM_WEIGHTS, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step = 0
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.values = None
+        self.steps = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._params = []
+        with torch.no_grad():
+            for key, (off, shape) in wts.weight_offsets().items():
+                p = named[key]
+                n = p.numel()
+                view = self.flat[off:off + n].view(shape)
+                view.copy_(p.data)
+                p.data = view                                   # the module now lives in the flat vector
+                st = optimizer.state.get(p)
+                if st:                                          # continue from eager / graphed steps
+                    self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    self.step = max(self.step, int(st["step"]))
+                self._params.append((p, off, n, shape))
+        self.export_state()
+
+    def export_state(self):
+        """make the torch optimizer's state describe the flat vectors (views, no copies)"""
+        for p, off, n, shape in self._params:
+            self.optimizer.state[p] = {"step": torch.tensor(float(self.step)),
+                                       "exp_avg": self.exp_avg[off:off + n].view(shape),
+                                       "exp_avg_sq": self.exp_avg_sq[off:off + n].view(shape)}
+
+    def __call__(self, inputs, values):
+        g = self.optimizer.param_groups[0]
+        inputs = inputs.detach().to(torch.float32).contiguous()
+        targets = values.detach().to(torch.float32).reshape(-1).contiguous()
+        if self.values is None or self.values.numel() != inputs.shape[0]:
+            self.values = torch.empty(inputs.shape[0], dtype=torch.float32, device=inputs.device)
+        self.engine.train_grad(self.flat, inputs, targets, self.grad, self.loss, self.values, self.steps)
+        world = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+        self.step += 1
+        self.engine.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"], g["eps"], self.step,
+                              1.0 / world)
+        self.model.note_external_update()
+        return self.loss[0].clone()
+
+
 class Trainer(object):
-    def __init__(self, model, memory, device, batch_size, cuda_graph=False):
+    def __init__(self, model, memory, device, batch_size, cuda_graph=False, fused=False):
         self.cuda_graph = bool(cuda_graph)
+        self.fused = bool(fused)
+        self._fused = None
         self._graphed = None
         self.model = model
         self.device = device
@@ -112,6 +181,7 @@ class Trainer(object):
     def set_learning_rate(self, learning_rate, optimizer_type="SGD"):
         logging.info("Current learning rate: %f,Optimizer Type %s", learning_rate, optimizer_type)
         self._graphed = None
+        self._fused = None
         if optimizer_type == "Adam":
             self.optimizer = optim.Adam(self.model.parameters(), lr=learning_rate, betas=(0.9, 0.99), eps=1e-03,
                                         capturable=self.cuda_graph)
@@ -124,6 +194,13 @@ class Trainer(object):
 
     def _step(self, inputs, values):
         """one optimisation step; returns the loss as a 0-dim tensor (the callers synchronise once per call, not per step)"""
+        if self.fused:
+            if not isinstance(self.optimizer, optim.Adam) or self.model.training or getattr(self.model, "act_fixed", False):
+                raise NotImplementedError("the fused training step covers Adam on the eval()-mode adaptive network "
+                                          "(dropout inactive, act_fixed = False)")
+            if self._fused is None:
+                self._fused = FusedStep(self.model, self.optimizer, inputs.device)
+            return self._fused(inputs, values)
         if self.cuda_graph and isinstance(self.optimizer, optim.Adam):
             if self._graphed is None or not self._graphed.matches(inputs, values):
                 self._graphed = GraphedStep(self.model, self.optimizer, self.criterion, inputs, values)

@@ -136,6 +136,11 @@ struct aem_handle_s {
     double *s_robot, *s_humans, *s_time, *s_newvel, *s_rewards, *s_dmin, *s_hnext, *s_values, *s_oreward;
     int32_t *s_info, *s_best, *s_odone, *s_oinfo;
     void *s_stream;
+    // scratch of the training step (train.cu): per-CTA gradient slices, squared errors, halting flags, activation stash
+    float *tr_part, *tr_sqerr, *tr_stash;
+    int *tr_flags;
+    int tr_grid, tr_B;
+    size_t tr_stash_floats;
 };
 
 #define AEM_CUDA_CHECK(expr)                                                      \
@@ -172,6 +177,11 @@ cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans,
 cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double *global_time, const int32_t *done,
                              const int32_t *info, const double *pool_robot, const double *pool_humans, int P,
                              int32_t *case_idx, int case_stride, unsigned long long *outcome_counts, cudaStream_t st);
+
+cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, const float *states, const float *targets,
+                              float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st);
+cudaError_t launch_adam(size_t count, float *p, const float *g, float *m, float *v, double lr, double b1, double b2, double eps,
+                        int step, double gscale, cudaStream_t st);
 
 struct LookaheadArgs {
     NetParams net;

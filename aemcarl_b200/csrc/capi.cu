@@ -394,6 +394,7 @@ int aem_destroy(aem_handle h)
     cudaFree(h->s_rewards); cudaFree(h->s_dmin); cudaFree(h->s_hnext); cudaFree(h->s_values);
     cudaFree(h->s_oreward); cudaFree(h->s_info); cudaFree(h->s_best); cudaFree(h->s_odone); cudaFree(h->s_oinfo);
     if (h->s_stream) cudaStreamDestroy(as_stream(h->s_stream));
+    cudaFree(h->tr_part); cudaFree(h->tr_sqerr); cudaFree(h->tr_stash); cudaFree(h->tr_flags);
     delete h;
     return AEM_OK;
 }
@@ -803,6 +804,33 @@ int aem_decide_step_host(aem_handle h, int B, int n, double gamma_bar, double *r
     if (values_h)
         AEM_CUDA_CHECK(cudaMemcpyAsync(values_h, h->s_values, sizeof(double) * B * A, cudaMemcpyDeviceToHost, st));
     AEM_CUDA_CHECK(cudaStreamSynchronize(st));
+    return AEM_OK;
+}
+
+int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const float *states_d, const float *targets_d,
+                   float *grad_d, float *loss_d, float *values_d, int32_t *steps_d, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (B < 1 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (!params_d || !states_d || !targets_d || !grad_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    if (h->net.act_fixed) return aem_set_error(AEM_ERR_INVALID, "aem_train_grad implements the adaptive (act_fixed = 0) network");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_train_grad(h, B, n, params_d, states_d, targets_d, grad_d, loss_d, values_d, steps_d, as_stream(stream)));
+    h->launches += 3;
+    return AEM_OK;
+}
+
+int aem_adam_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *exp_avg_d, float *exp_avg_sq_d,
+                  double lr, double beta1, double beta2, double eps, int step, double grad_scale, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (!params_d || !grad_d || !exp_avg_d || !exp_avg_sq_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    if (step < 1 || !(beta1 >= 0 && beta1 < 1) || !(beta2 >= 0 && beta2 < 1)) return aem_set_error(AEM_ERR_INVALID, "bad step / betas");
+    if (count == 0) return AEM_OK;
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_adam(count, params_d, grad_d, exp_avg_d, exp_avg_sq_d, lr, beta1, beta2, eps, step, grad_scale,
+                               as_stream(stream)));
+    h->launches += 1;
     return AEM_OK;
 }
 

@@ -186,6 +186,28 @@ class Engine:
         check(self.lib.aem_transform(self.h, B, n, _ptr(robot), _ptr(humans), _ptr(out), self._stream()))
         return out
 
+    # ---- value-network regression step (trainer.py:47-58) ------------------------------------------------
+    def train_grad(self, params, states, targets, grad, loss=None, values=None, steps=None):
+        """forward + MSE + backward of the flag-5 network on [B, n, 13] rotated states (batch-global ACT halting);
+        params / grad: flat float32[113752] in blob order; returns (grad, loss[1], values[B], steps[1])"""
+        B, n, _ = states.shape
+        self._chk(states, F32, (B, n, 13)); self._chk(targets.view(-1), F32, (B,))
+        self._chk(params, F32, (_lib.NUM_WEIGHTS,)); self._chk(grad, F32, (_lib.NUM_WEIGHTS,))
+        loss = torch.empty((1,), dtype=F32, device=self.device) if loss is None else loss
+        values = torch.empty((B,), dtype=F32, device=self.device) if values is None else values
+        steps = torch.empty((1,), dtype=I32, device=self.device) if steps is None else steps
+        check(self.lib.aem_train_grad(self.h, B, n, _ptr(params), _ptr(states), _ptr(targets), _ptr(grad), _ptr(loss),
+                                      _ptr(values), _ptr(steps), self._stream()))
+        return grad, loss, values, steps
+
+    def adam_step(self, params, grad, exp_avg, exp_avg_sq, lr, betas, eps, step, grad_scale=1.0):
+        """torch.optim.Adam.step() on flat float32 vectors (no weight decay / amsgrad); step is 1-based"""
+        for t in (params, grad, exp_avg, exp_avg_sq):
+            self._chk(t, F32, (params.numel(),))
+        check(self.lib.aem_adam_step(self.h, params.numel(), _ptr(params), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                     float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), float(grad_scale),
+                                     self._stream()))
+
     # ---- host-buffer call (the e2e path) -------------------------------------------------------
     def decide_step_host(self, robot, humans, global_time, gamma_bar, want_values=False):
         """robot [B,9], humans [B,n,8], global_time [B]: contiguous float64 numpy arrays, updated IN PLACE."""

@@ -18,6 +18,8 @@
  *   aem_gru_act         <- ATCBasic.forward components.py:107-137 (fused GRU-cell / adaptive-computation-time)
  *   aem_env_step_xy     <- CrowdSim.step for one arbitrary ActionXY per environment (imitation phase, train.py:171-204)
  *   aem_transform       <- MultiHumanRL.transform multi_human_rl.py:423-438 (replay-memory sample of the current state)
+ *   aem_train_grad      <- Trainer.optimize_batch / optimize_epoch forward + MSE + backward (crowd_nav/utils/trainer.py:47-58,70-82)
+ *   aem_adam_step       <- optimizer.step() of optim.Adam (trainer.py:30,56,80)
  *   aem_decide_step_host<- Robot.act + CrowdSim.step through HOST buffers (explorer.py:51-53), the e2e call
  *
  * Conventions: plain pointers and sizes only; `*_d` = device pointer, `*_h` = host pointer; all device entry
@@ -149,6 +151,22 @@ int aem_env_step_xy(aem_handle h, int B, int n, double *robot_d, double *humans_
 /* MultiHumanRL.transform (multi_human_rl.py:423-438): rotate() of the current joint state of every environment, the
  * sample Explorer stores in the replay memory.  robot_d [B][9] f64, humans_d [B][n][8] f64 -> states_d [B][n][13] f32 */
 int aem_transform(aem_handle h, int B, int n, const double *robot_d, const double *humans_d, float *states_d, void *stream);
+
+/* Value-network regression step (crowd_nav/utils/trainer.py:47-58,70-82: outputs = model(inputs); loss = MSELoss(outputs,
+ * values); loss.backward()): forward of ValueNetworkTransformerAndGRU (qnetwork_factory.py:641-687) on B rotated states with
+ * the reference's BATCH-GLOBAL halting (components.py:132-134), mean squared error against targets_d, and the gradient with
+ * respect to every live parameter.  Dropout is inactive (the eval()-mode network every other entry point evaluates).
+ * params_d [AEM_NUM_WEIGHTS] f32 (blob order; the caller's live parameters, not the handle's copy), states_d [B][n][13] f32,
+ * targets_d [B] f32 -> grad_d [AEM_NUM_WEIGHTS] f32 (overwritten; deterministic summation order), loss_d [1] f32,
+ * values_d [B] f32, steps_d [1] i32 = the batch's GRU step count (the last three may be NULL).  Three kernel launches. */
+int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const float *states_d, const float *targets_d,
+                   float *grad_d, float *loss_d, float *values_d, int32_t *steps_d, void *stream);
+
+/* torch.optim.Adam.step() (trainer.py:30 uses betas (0.9, 0.99), eps 1e-3; no weight decay, no amsgrad) on flat vectors of
+ * `count` floats: step = 1-based number of this update; the gradient is multiplied by grad_scale first (1 / world_size
+ * after a summing all-reduce). */
+int aem_adam_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *exp_avg_d, float *exp_avg_sq_d,
+                  double lr, double beta1, double beta2, double eps, int step, double grad_scale, void *stream);
 
 /* ---- host-buffer call: one full env-step (predict + step) for B environments ----
  * In/out (updated in place): robot_h [B][9], humans_h [B][n][8], global_time_h [B].

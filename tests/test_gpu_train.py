@@ -1,0 +1,149 @@
+"""GPU parity of the hand-written training step (csrc/train.cu): aem_train_grad against torch autograd of
+the module mirror (float64 on the same device), aem_adam_step / the FusedStep trainer against torch.optim.Adam."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from aemcarl_b200 import weights as wts
+from test_train_math import autograd_reference, random_batch
+
+pytestmark = pytest.mark.gpu
+
+# float32 kernel against a float64 reference: per-tensor gradient error relative to the tensor's largest entry
+GRAD_RTOL = 2e-4
+VALUE_ATOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from aemcarl_b200.engine import Engine
+    return Engine(0)
+
+
+def run_kernel(eng, flat, states, targets):
+    dev = eng.device
+    p = torch.from_numpy(np.asarray(flat, dtype=np.float32)).to(dev)
+    s = torch.from_numpy(np.asarray(states, dtype=np.float32)).to(dev).contiguous()
+    t = torch.from_numpy(np.asarray(targets, dtype=np.float32)).to(dev)
+    g = torch.full((wts.NUM_WEIGHTS,), float("nan"), device=dev)
+    g, loss, values, steps = eng.train_grad(p, s, t, g)
+    torch.cuda.synchronize()
+    return float(loss[0]), g.cpu().numpy().astype(np.float64), values.cpu().numpy().astype(np.float64), int(steps[0])
+
+
+def check_grad(grad, ref):
+    assert np.isfinite(grad).all()
+    for key, (off, shape) in wts.weight_offsets().items():
+        n = int(np.prod(shape))
+        a, b = grad[off:off + n], ref[off:off + n]
+        scale = max(np.abs(b).max(), 1e-4)
+        assert np.abs(a - b).max() <= GRAD_RTOL * scale, (key, np.abs(a - b).max(), scale)
+
+
+@pytest.mark.parametrize("ponder_bias,expect_K", [(4.0, 1), (None, 2), (-2.0, 3)])
+@pytest.mark.parametrize("B,n", [(100, 5), (7, 1), (33, 10), (9, 18), (300, 5), (5, 32)])
+def test_train_grad_matches_autograd(eng, ponder_bias, expect_K, B, n):
+    """the trainer's batch (100 x 5 humans), one human, global-stash sizes (n = 10, 18, 32) and a batch larger than the
+    grid (300: CTAs accumulate several samples into their slice), for K = 1, 2, 3 batch-global GRU steps"""
+    flat = wts.synthetic_weights(3, ponder_bias=ponder_bias)
+    states, targets = random_batch(B + n, B, n)
+    states = states.astype(np.float32).astype(np.float64)
+    targets = targets.astype(np.float32).astype(np.float64)
+    loss_r, grad_r, val_r, K_r = autograd_reference(flat, states, targets, device="cuda:0")
+    loss, grad, values, K = run_kernel(eng, flat, states, targets)
+    assert K == K_r and (expect_K != 3 or K == 3)
+    assert np.abs(values - val_r).max() < VALUE_ATOL
+    assert loss == pytest.approx(loss_r, rel=1e-4)
+    check_grad(grad, grad_r)
+
+
+def test_train_grad_is_deterministic(eng):
+    flat = wts.synthetic_weights(5)
+    states, targets = random_batch(2, 100, 5)
+    a = run_kernel(eng, flat, states, targets)
+    b = run_kernel(eng, flat, states, targets)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+def test_mixed_halting_batch_uses_the_batch_global_count(eng):
+    """components.py:132-134: one sample that needs a third step makes the whole batch take it"""
+    flat = wts.synthetic_weights(4, ponder_bias=-0.13)
+    states, targets = random_batch(11, 64, 5)
+    loss_r, grad_r, val_r, K_r = autograd_reference(flat, states, targets, device="cuda:0")
+    loss, grad, values, K = run_kernel(eng, flat, states, targets)
+    assert K == K_r
+    assert np.abs(values - val_r).max() < VALUE_ATOL
+    check_grad(grad, grad_r)
+
+
+def test_adam_step_equals_torch_adam(eng):
+    dev = eng.device
+    g = torch.Generator(device=dev).manual_seed(1)
+    p0 = torch.randn(wts.NUM_WEIGHTS, device=dev, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.99), eps=1e-3)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for step in range(1, 6):
+        grad = torch.randn(wts.NUM_WEIGHTS, device=dev, generator=g) * 0.1
+        ref.grad = grad.clone()
+        opt.step()
+        eng.adam_step(p, grad, m, v, 1e-3, (0.9, 0.99), 1e-3, step)
+        assert torch.allclose(p, ref.detach(), rtol=2e-7, atol=2e-7), float((p - ref.detach()).abs().max())   # 1 ulp
+    assert torch.allclose(m, opt.state[ref]["exp_avg"], rtol=1e-6, atol=1e-9)
+    assert torch.allclose(v, opt.state[ref]["exp_avg_sq"], rtol=1e-6, atol=1e-12)
+    # a summed gradient of two ranks, averaged by grad_scale
+    p2, m2, v2 = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    p3, m3, v3 = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    grad = torch.randn(wts.NUM_WEIGHTS, device=dev, generator=g)
+    eng.adam_step(p2, grad * 2, m2, v2, 1e-3, (0.9, 0.99), 1e-3, 1, grad_scale=0.5)
+    eng.adam_step(p3, grad, m3, v3, 1e-3, (0.9, 0.99), 1e-3, 1)
+    assert torch.equal(p2, p3)
+
+
+def test_fused_trainer_walks_with_the_eager_trainer():
+    """Trainer(fused=True) against the eager torch step on the same six mini-batches: same losses, same parameters; the
+    module's parameters are views into the flat vector, the lookahead engine sees the updated weights, and the torch
+    optimizer's state describes the fused moments."""
+    from aemcarl_b200.crowd_nav.utils.trainer import Trainer
+    from test_gpu_api import setup
+    env, robot, policy = setup(seed=4, ponder_bias=-0.13)
+    dev = torch.device("cuda:0")
+    model_a = policy.get_model()
+    model_b = copy.deepcopy(model_a).to(dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    batches = [(torch.randn((100, 5, 13), device=dev, generator=g), torch.randn((100, 1), device=dev, generator=g))
+               for _ in range(6)]
+    losses = {}
+    trainers = {}
+    for name, model, fused in (("eager", model_a, False), ("fused", model_b, True)):
+        tr = Trainer(model, None, dev, 100, fused=fused)
+        tr.set_learning_rate(1e-3, "Adam")
+        losses[name] = [float(tr._step(x, v)) for x, v in batches]
+        trainers[name] = tr
+    assert np.allclose(losses["eager"], losses["fused"], rtol=2e-4, atol=1e-6), (losses["eager"], losses["fused"])
+    for (k, pa), pb in zip(model_a.named_parameters(), model_b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-3, atol=2e-5), (k, float((pa - pb).abs().max()))
+    assert losses["fused"][0] != losses["fused"][-1]
+    fs = trainers["fused"]._fused
+    assert fs.step == 6
+    flat_now = torch.from_numpy(model_b.flat_weights()).to(dev)
+    assert torch.equal(flat_now, fs.flat)                       # parameters ARE the flat vector
+    fs.export_state()
+    st = trainers["fused"].optimizer.state[next(model_b.parameters())]
+    assert float(st["step"]) == 6 and st["exp_avg"].data_ptr() == fs.exp_avg.data_ptr()
+    # the value kernel of the policy path picks the new weights up (version bump through note_external_update)
+    x = batches[0][0][:1]
+    with torch.no_grad():
+        v_kernel = float(model_b(x)[0])
+        v_torch = float(model_b.forward_torch(x)[0])
+    assert v_kernel == pytest.approx(v_torch, abs=2e-5)
+    # one eager step of the same optimizer continues from the fused state
+    tr = trainers["fused"]
+    tr.fused = False
+    before = fs.flat.clone()
+    tr._step(*batches[0])
+    assert not torch.equal(before, torch.from_numpy(model_b.flat_weights()).to(dev))
