@@ -813,6 +813,7 @@ int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const floa
     if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
     if (B < 1 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
     if (!params_d || !states_d || !targets_d || !grad_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    if (((uintptr_t)params_d & 15) != 0) return aem_set_error(AEM_ERR_INVALID, "params_d must be 16-byte aligned (bulk copies)");
     if (h->net.act_fixed) return aem_set_error(AEM_ERR_INVALID, "aem_train_grad implements the adaptive (act_fixed = 0) network");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     AEM_CUDA_CHECK(launch_train_grad(h, B, n, params_d, states_d, targets_d, grad_d, loss_d, values_d, steps_d, as_stream(stream)));

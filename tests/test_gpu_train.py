@@ -93,8 +93,8 @@ def test_adam_step_equals_torch_adam(eng):
         opt.step()
         eng.adam_step(p, grad, m, v, 1e-3, (0.9, 0.99), 1e-3, step)
         assert torch.allclose(p, ref.detach(), rtol=2e-7, atol=2e-7), float((p - ref.detach()).abs().max())   # 1 ulp
-    assert torch.allclose(m, opt.state[ref]["exp_avg"], rtol=1e-6, atol=1e-9)
-    assert torch.allclose(v, opt.state[ref]["exp_avg_sq"], rtol=1e-6, atol=1e-12)
+    assert torch.allclose(m, opt.state[ref]["exp_avg"], rtol=1e-5, atol=1e-8)
+    assert torch.allclose(v, opt.state[ref]["exp_avg_sq"], rtol=1e-5, atol=1e-10)
     # a summed gradient of two ranks, averaged by grad_scale
     p2, m2, v2 = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
     p3, m3, v3 = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)

@@ -1,6 +1,6 @@
 """Aggregate an ncu source-page export (SASS level) per line of the KERNEL body: the outermost source line of every
 instruction (through the inlined-at chain of nvdisasm -gi) -> executed warp instructions, stall samples, top stalls.
-usage: python tools/ncu_lines.py <report.ncu-rep> <object.o> [top]"""
+usage: python tools/ncu_lines.py <report.ncu-rep> <object.o> [top] [byline|-] [kernel-name substring when the object holds several]"""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 rep, obj = sys.argv[1], os.path.abspath(sys.argv[2]); top = int(sys.argv[3]) if len(sys.argv) > 3 else 50
 with tempfile.TemporaryDirectory() as d:
@@ -8,7 +8,12 @@ with tempfile.TemporaryDirectory() as d:
     cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
     dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], cwd=d, check=True, capture_output=True, text=True).stdout
 addr2line = {}; last = None
+want = sys.argv[5] if len(sys.argv) > 5 else None; insec = want is None
 for l in dis.splitlines():
+    if l.startswith("//---------------------") and want is not None:
+        insec = want in l
+        continue
+    if not insec: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', l)
     if m:
         last = (os.path.basename(m.group(1)), int(m.group(2)))       # the last annotation before an instruction is the outermost
