@@ -41,6 +41,13 @@ class EnvParams(ctypes.Structure):
     ]
 
 
+class ScenarioParams(ctypes.Structure):
+    """aem_scenario_params (env.config [sim] / [humans] / [robot] values that enter the scenario draw)."""
+    _fields_ = [("circle_radius", ctypes.c_double), ("square_width", ctypes.c_double), ("discomfort_dist", ctypes.c_double),
+                ("robot_radius", ctypes.c_double), ("robot_v_pref", ctypes.c_double), ("human_radius", ctypes.c_double),
+                ("human_v_pref", ctypes.c_double), ("randomize_attributes", ctypes.c_int32), ("pad_", ctypes.c_int32)]
+
+
 # every symbol include/aemcarl_b200.h declares: name -> (restype, argtypes)
 _VP = ctypes.c_void_p
 SYMBOLS = {
@@ -64,6 +71,8 @@ SYMBOLS = {
     "aem_env_step_xy": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, ctypes.c_double, _VP, _VP, _VP,
                                        _VP, _VP, _VP]),
     "aem_transform": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),
+    "aem_generate_scenarios": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
+                                              ctypes.POINTER(ScenarioParams), _VP, _VP, _VP]),
     "aem_train_grad": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 8),
     "aem_adam_step": (ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_double, ctypes.c_int, ctypes.c_double, _VP]),

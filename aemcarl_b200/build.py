@@ -23,6 +23,7 @@ SOURCES = {
     "lookahead_h16.cu": [],
     "lookahead_q16.cu": [],
     "train.cu": [],
+    "scenario.cu": ["-fmad=false"],   # Python float arithmetic of the scenario draw, op by op
     "env.cu": ["-fmad=false"],   # FP64 env arithmetic is a sequence of individually rounded Python float ops
     "orca.cu": ["-fmad=false"],
     "capi.cu": [],

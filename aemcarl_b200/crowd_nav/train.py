@@ -152,7 +152,8 @@ def main(argv=None):
             torch.save(model.state_dict(), os.path.join(args.output_dir, "rl_model_%d.pth" % episode))
     if rank == 0:
         torch.save(model.state_dict(), os.path.join(args.output_dir, "rl_model.pth"))
-    return dict(loss=loss, memory=len(memory), model=model, explorer=explorer, policy=policy, env=env, robot=robot)
+    return dict(loss=loss, memory=len(memory), model=model, explorer=explorer, policy=policy, env=env, robot=robot,
+                trainer=trainer)
 
 
 def vectorised_rl(args, tcfg, policy, env, model, vec, trainer, explorer, train_episodes, eps_sched, rank, world):

@@ -97,7 +97,7 @@ class VecExplorer(object):
     `num_envs` episodes are in flight at once."""
 
     def __init__(self, policy, num_envs, env_params, memory=None, gamma=None, human_num=5, rule="circle_crossing",
-                 seed=0, scenario_kw=None, il_safety_space=0.0):
+                 seed=0, scenario_kw=None, il_safety_space=0.0, device_scenarios=None):
         self.policy = policy
         self.env_params = env_params          # aem_env_params of the configured CrowdSim (env.env_params())
         self.il_safety_space = float(il_safety_space)     # [imitation_learning] safety_space of the ORCA teacher
@@ -114,6 +114,9 @@ class VecExplorer(object):
         self.case_counter = {"train": 0, "val": 0, "test": 0}
         self.last_stats = None
         self._target_engine = None
+        # scenario pools: None = drawn on the device for the training phase (aem_generate_scenarios; 4096 cases cost ~1 s in
+        # the host generator), on the host (bit-exact with the reference) for val / test; True / False force one of them
+        self.device_scenarios = device_scenarios
 
     def update_target_model(self, target_model):
         import copy
@@ -142,8 +145,10 @@ class VecExplorer(object):
         eng.set_env_params(self.env_params)
         first = self.case_counter[phase] if first_case is None else int(first_case)
         B = min(self.B, int(k))
+        on_device = self.device_scenarios if self.device_scenarios is not None else phase == "train"
         env = VecCrowdSim(eng, B, human_num=self.n, rule=self.rule, phase=phase, first_case=first, pool_size=int(k),
-                          gamma=self.gamma, scenario_kw=self.scenario_kw)
+                          gamma=self.gamma, scenario_kw=self.scenario_kw,
+                          device_scenarios=on_device and self.rule in ("circle_crossing", "square_crossing"))
         if pol.action_space is None:
             pol.build_action_space(float(env.pool_robot_h[0, 7]))
             eng = pol.engine()
@@ -154,24 +159,33 @@ class VecExplorer(object):
         tmax = int(round(eng.params.time_limit / dt)) + 2
         eps = float(epsilon if epsilon is not None else (pol.epsilon or 0.0)) if phase == "train" else 0.0
 
-        traj_s = torch.zeros((B, tmax, self.n, 13), dtype=torch.float32, device=dev)
-        traj_r = torch.zeros((B, tmax), dtype=torch.float64, device=dev)
+        # Everything below stays on the device and is issued without a host synchronisation: trajectories are written
+        # straight into per-CASE rows (row k is a dummy for environments that ran out of cases), finished environments
+        # take the next case in environment order (prefix sum over the done flags = the order of the serial loop
+        # `for b in fin`), and the host looks at the device only every `check_every` steps to see whether any
+        # environment is still playing.
+        k = int(k)
+        traj_s = torch.zeros((k + 1, tmax, self.n, 13), dtype=torch.float32, device=dev)
+        traj_r = torch.zeros((k + 1, tmax), dtype=torch.float64, device=dev)
+        traj_info = torch.zeros((k + 1, tmax), dtype=torch.int32, device=dev)
+        traj_dmin = torch.zeros((k + 1, tmax), dtype=torch.float64, device=dev)
+        ep_len = torch.zeros((k + 1,), dtype=torch.int64, device=dev)
+        ep_code = torch.full((k + 1,), -1, dtype=torch.int32, device=dev)
+        ep_time = torch.zeros((k + 1,), dtype=torch.float64, device=dev)
         step_idx = torch.zeros((B,), dtype=torch.int64, device=dev)
-        rows = torch.arange(B, device=dev)
-        case_of_env = np.arange(B)                   # pool index each env is playing
-        active = np.ones(B, dtype=bool)
-        next_case = B
-        codes = np.full(k, -1, dtype=np.int64)
-        nav_time = np.zeros(k)
-        cum_reward = np.zeros(k)
-        too_close, min_dist = 0, []
+        case_of_env = torch.arange(B, device=dev, dtype=torch.int64)      # pool index each env is playing
+        active = torch.ones((B,), dtype=torch.bool, device=dev)
+        next_case = torch.full((), B, dtype=torch.int64, device=dev)
+        env_steps_d = torch.zeros((), dtype=torch.int64, device=dev)
+        dummy = torch.full((B,), k, dtype=torch.int64, device=dev)
+        zero_t = torch.zeros((), dtype=torch.float64, device=dev)
         disc = torch.pow(torch.tensor(gbar, dtype=torch.float64, device=dev),
                          torch.arange(tmax, device=dev, dtype=torch.float64))
-        env_steps = 0
-        pushed = 0
+        check_every = 4
+        it = 0
 
         il_eng = self._teacher_engine() if imitation_learning else None
-        while active.any():
+        while True:
             cur = eng.transform(env.robot, env.humans)                      # last_state of every env
             if imitation_learning:
                 reward, done, info, dmin = self._teacher_step(env, eng, il_eng, v_pref)
@@ -184,48 +198,47 @@ class VecExplorer(object):
                     at_goal = torch.linalg.norm(env.robot[:, 0:2] - env.robot[:, 5:7], dim=1) < env.robot[:, 4]
                     best = torch.where(explore & ~at_goal, rnd, best)
                 reward, done, info, dmin = env.apply(best, auto_reset=False)
-            traj_s[rows, step_idx] = cur
-            traj_r[rows, step_idx] = reward
+            row = torch.where(active, case_of_env, dummy)
+            traj_s[row, step_idx] = cur
+            traj_r[row, step_idx] = reward
+            traj_info[row, step_idx] = info
+            traj_dmin[row, step_idx] = dmin
+            env_steps_d += active.sum()
             step_idx += 1
             step_idx.clamp_(max=tmax - 1)               # envs without a case left keep stepping harmlessly
-            done_h = done.cpu().numpy() != 0
-            info_h = info.cpu().numpy()
-            act_idx = np.nonzero(active)[0]
-            env_steps += len(act_idx)
-            danger = active & (info_h == INFO_DANGER)
-            if danger.any():
-                too_close += int(danger.sum())
-                min_dist.extend(dmin.cpu().numpy()[danger].tolist())
-            fin = np.nonzero(active & done_h)[0]
-            if len(fin) == 0:
-                continue
-            fin_t = torch.from_numpy(fin).to(dev)
-            lens = step_idx[fin_t]
-            live_steps = torch.arange(tmax, device=dev).unsqueeze(0) < lens.unsqueeze(1)
-            cr = (traj_r[fin_t] * disc.unsqueeze(0) * live_steps).sum(dim=1).cpu().numpy()
-            gt_h = env.global_time[fin_t].cpu().numpy()
-            cases = case_of_env[fin]
-            codes[cases] = info_h[fin]
-            nav_time[cases] = gt_h
-            cum_reward[cases] = cr
-            store = fin[np.isin(info_h[fin], (INFO_REACHGOAL, INFO_COLLISION))]
-            if update_memory and len(store):
-                pushed += self._store(traj_s, traj_r, step_idx, store, gbar, imitation_learning)
-            # next cases for the finished envs
-            for b in fin:
-                if next_case < k:
-                    case_of_env[b] = next_case
-                    next_case += 1
-                else:
-                    active[b] = False
-            reload = np.array([b for b in fin if active[b]], dtype=np.int64)
-            if len(reload):
-                rb = torch.from_numpy(reload).to(dev)
-                cb = torch.from_numpy(case_of_env[reload]).to(dev)
-                env.robot[rb] = env.pool_robot[cb]
-                env.humans[rb] = env.pool_humans[cb]
-                env.global_time[rb] = 0.0
-            step_idx[fin_t] = 0
+            fin = active & (done != 0)
+            erow = torch.where(fin, case_of_env, dummy)
+            ep_len[erow] = step_idx
+            ep_code[erow] = info
+            ep_time[erow] = env.global_time
+            newcase = next_case + torch.cumsum(fin, dim=0) - 1              # next cases in environment order
+            next_case += fin.sum()
+            has = fin & (newcase < k)
+            case_of_env = torch.where(has, newcase, case_of_env)
+            active = active & ~(fin & ~has)
+            src = newcase.clamp(max=k - 1)
+            env.robot.copy_(torch.where(has[:, None], env.pool_robot[src], env.robot))
+            env.humans.copy_(torch.where(has[:, None, None], env.pool_humans[src], env.humans))
+            env.global_time.copy_(torch.where(has, zero_t, env.global_time))
+            step_idx = torch.where(fin, torch.zeros_like(step_idx), step_idx)
+            it += 1
+            if it % check_every == 0 and not bool(active.any()):            # the only host synchronisation of the loop
+                break
+
+        # ---- one pass over the finished wave: statistics and the replay-memory pairs ----
+        lens = ep_len[:k]
+        live = torch.arange(tmax, device=dev).unsqueeze(0) < lens.unsqueeze(1)
+        cum_reward = (traj_r[:k] * disc.unsqueeze(0) * live).sum(dim=1).cpu().numpy()
+        codes = ep_code[:k].cpu().numpy().astype(np.int64)
+        nav_time = ep_time[:k].cpu().numpy()
+        danger = live & (traj_info[:k] == INFO_DANGER)
+        too_close = int(danger.sum().item())
+        min_dist = traj_dmin[:k][danger].cpu().numpy().tolist()
+        env_steps = int(env_steps_d.item())
+        pushed = 0
+        store = np.nonzero(np.isin(codes, (INFO_REACHGOAL, INFO_COLLISION)))[0]
+        if update_memory and len(store):
+            pushed = self._store(traj_s, traj_r, ep_len, store, gbar, imitation_learning)
 
         self.case_counter[phase] = (first + k) % max(1, self._case_size(phase))
         success = int((codes == INFO_REACHGOAL).sum())

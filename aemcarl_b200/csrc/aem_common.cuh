@@ -178,6 +178,8 @@ cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double
                              const int32_t *info, const double *pool_robot, const double *pool_humans, int P,
                              int32_t *case_idx, int case_stride, unsigned long long *outcome_counts, cudaStream_t st);
 
+cudaError_t launch_scenarios(int rule, uint32_t first_seed, int count, int n, const aem_scenario_params &p, double *robot,
+                             double *humans, cudaStream_t st);
 cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, const float *states, const float *targets,
                               float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st);
 cudaError_t launch_adam(size_t count, float *p, const float *g, float *m, float *v, double lr, double b1, double b2, double eps,

@@ -807,6 +807,20 @@ int aem_decide_step_host(aem_handle h, int B, int n, double gamma_bar, double *r
     return AEM_OK;
 }
 
+int aem_generate_scenarios(aem_handle h, int rule, uint32_t first_seed, int count, int n, const aem_scenario_params *p,
+                           double *robot_d, double *humans_d, void *stream)
+{
+    if (!h || !p) return aem_set_error(AEM_ERR_INVALID, "null argument");
+    if (rule != 0 && rule != 1) return aem_set_error(AEM_ERR_INVALID, "rule must be 0 (circle_crossing) or 1 (square_crossing)");
+    if (count < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad count / n");
+    if (count == 0) return AEM_OK;
+    if (!robot_d || !humans_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_scenarios(rule, first_seed, count, n, *p, robot_d, humans_d, as_stream(stream)));
+    h->launches += 1;
+    return AEM_OK;
+}
+
 int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const float *states_d, const float *targets_d,
                    float *grad_d, float *loss_d, float *values_d, int32_t *steps_d, void *stream)
 {

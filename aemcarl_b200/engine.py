@@ -186,6 +186,24 @@ class Engine:
         check(self.lib.aem_transform(self.h, B, n, _ptr(robot), _ptr(humans), _ptr(out), self._stream()))
         return out
 
+    def generate_scenarios(self, phase, first_case, count, human_num, rule, circle_radius=4.0, square_width=10.0,
+                           discomfort_dist=0.2, robot_radius=0.3, robot_v_pref=1.0, human_radius=0.3, human_v_pref=1.0,
+                           randomize_attributes=False):
+        """CrowdSim.reset's scenario draw for cases first_case .. first_case + count - 1 of `phase` on the device; the same
+        arguments and layout as scenarios.generate_pool -> (robot [count, 9], humans [count, n, 8]) f64 device tensors"""
+        from . import scenarios
+        rules = {"circle_crossing": 0, "square_crossing": 1}
+        if rule not in rules:
+            raise NotImplementedError("device scenario generation covers circle_crossing and square_crossing")
+        p = _lib.ScenarioParams(circle_radius, square_width, discomfort_dist, robot_radius, robot_v_pref, human_radius,
+                                human_v_pref, int(bool(randomize_attributes)), 0)
+        robot = torch.empty((count, 9), dtype=F64, device=self.device)
+        humans = torch.empty((count, human_num, 8), dtype=F64, device=self.device)
+        seed = scenarios.case_seed(phase, int(first_case))
+        check(self.lib.aem_generate_scenarios(self.h, rules[rule], ctypes.c_uint32(seed & 0xffffffff), int(count), int(human_num),
+                                              ctypes.byref(p), _ptr(robot), _ptr(humans), self._stream()))
+        return robot, humans
+
     # ---- value-network regression step (trainer.py:47-58) ------------------------------------------------
     def train_grad(self, params, states, targets, grad, loss=None, values=None, steps=None):
         """forward + MSE + backward of the flag-5 network on [B, n, 13] rotated states (batch-global ACT halting);

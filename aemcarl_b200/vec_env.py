@@ -16,7 +16,7 @@ from .engine import Engine, F64, I32, make_env_params
 
 class VecCrowdSim:
     def __init__(self, engine, num_envs, human_num=5, rule="circle_crossing", phase="train", first_case=0,
-                 pool_size=None, gamma=0.9, case_stride=None, scenario_kw=None):
+                 pool_size=None, gamma=0.9, case_stride=None, scenario_kw=None, device_scenarios=False):
         assert isinstance(engine, Engine)
         self.engine = engine
         self.B, self.n = int(num_envs), int(human_num)
@@ -27,10 +27,17 @@ class VecCrowdSim:
         self.first_case = first_case
         self.case_stride = int(case_stride if case_stride is not None else num_envs)
         kw = dict(scenario_kw or {})
-        pr, ph = scenarios.generate_pool(phase, first_case, self.pool_size, self.n, rule, **kw)
-        self.pool_robot_h, self.pool_humans_h = pr, ph
-        self.pool_robot = torch.from_numpy(pr).to(self.device)
-        self.pool_humans = torch.from_numpy(ph).to(self.device)
+        if device_scenarios:
+            # aem_generate_scenarios: the same seeded MT19937 draws on the device (square rule bit-exact, circle rule
+            # within an ulp of cos / sin); the host generator stays the bit-exact path of the evaluation phases
+            self.pool_robot, self.pool_humans = engine.generate_scenarios(phase, first_case, self.pool_size, self.n, rule, **kw)
+            self.pool_robot_h = self.pool_robot[:1].cpu().numpy()
+            self.pool_humans_h = None
+        else:
+            pr, ph = scenarios.generate_pool(phase, first_case, self.pool_size, self.n, rule, **kw)
+            self.pool_robot_h, self.pool_humans_h = pr, ph
+            self.pool_robot = torch.from_numpy(pr).to(self.device)
+            self.pool_humans = torch.from_numpy(ph).to(self.device)
         B, n, A = self.B, self.n, engine.A
         dev = self.device
         self.robot = torch.empty((B, 9), dtype=F64, device=dev)

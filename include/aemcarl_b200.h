@@ -18,6 +18,7 @@
  *   aem_gru_act         <- ATCBasic.forward components.py:107-137 (fused GRU-cell / adaptive-computation-time)
  *   aem_env_step_xy     <- CrowdSim.step for one arbitrary ActionXY per environment (imitation phase, train.py:171-204)
  *   aem_transform       <- MultiHumanRL.transform multi_human_rl.py:423-438 (replay-memory sample of the current state)
+ *   aem_generate_scenarios <- CrowdSim.reset's seeded scenario draw, crowd_sim.py:486-552,390-442
  *   aem_train_grad      <- Trainer.optimize_batch / optimize_epoch forward + MSE + backward (crowd_nav/utils/trainer.py:47-58,70-82)
  *   aem_adam_step       <- optimizer.step() of optim.Adam (trainer.py:30,56,80)
  *   aem_decide_step_host<- Robot.act + CrowdSim.step through HOST buffers (explorer.py:51-53), the e2e call
@@ -78,6 +79,19 @@ typedef struct {
     double orca_safety_space;
 } aem_env_params;
 
+/* CrowdSim.configure / Agent attributes that enter the scenario draw (env.config [sim], [humans], [robot]) */
+typedef struct {
+    double circle_radius;
+    double square_width;
+    double discomfort_dist;
+    double robot_radius;
+    double robot_v_pref;
+    double human_radius;
+    double human_v_pref;
+    int32_t randomize_attributes;
+    int32_t pad_;
+} aem_scenario_params;
+
 typedef struct aem_handle_s *aem_handle;
 
 int aem_version(void);
@@ -132,6 +146,15 @@ int aem_env_reset_done(aem_handle h, int B, int n, double *robot_d, double *huma
                        const int32_t *done_d, const int32_t *info_d, const double *pool_robot_d,
                        const double *pool_humans_d, int P, int32_t *case_idx_d, int case_stride,
                        unsigned long long *outcome_counts_d, void *stream);
+
+/* CrowdSim.reset's scenario draw (crowd_sim.py:486-552 with generate_circle_crossing_human :390-411 /
+ * generate_square_crossing_human :413-442, agent.py:39-45) for `count` consecutive cases on the device: case c is seeded like
+ * np.random.seed(first_seed + c) (first_seed = the phase's counter offset + first case, crowd_sim.py:501-505) and replays the
+ * legacy MT19937 stream in the reference's call order, rejection sampling included.  rule: 0 = circle_crossing,
+ * 1 = square_crossing.  -> robot_d [count][9] f64, humans_d [count][n][8] f64.  Square rule: bit-exact; circle rule: cos / sin
+ * come from libdevice (<= 1 ulp from numpy's). */
+int aem_generate_scenarios(aem_handle h, int rule, uint32_t first_seed, int count, int n, const aem_scenario_params *p,
+                           double *robot_d, double *humans_d, void *stream);
 
 /* states_d [S][n][13] f32 (rotated joint states) -> values_d [S] f32, steps_d [S] u8 (may be NULL) */
 int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *values_d, uint8_t *steps_d,

@@ -216,3 +216,34 @@ def test_mixed_rule_episodes_run_with_a_varying_number_of_humans(golden_dir):
             steps += 1
         assert done and isinstance(info, (ReachGoal, Collision, Timeout))
     assert len(seen) >= 3
+
+
+@pytest.mark.parametrize("rule,n,randomize", [("square_crossing", 10, False), ("square_crossing", 5, True),
+                                               ("circle_crossing", 5, False), ("circle_crossing", 5, True),
+                                               ("circle_crossing", 10, False)])
+def test_device_scenario_generation_replays_the_seeded_stream(rule, n, randomize):
+    """aem_generate_scenarios against the host generator, which reproduces 208 cases recorded from the
+    reference bit for bit (tests/test_oracle_golden.py): MT19937 stream, draw order and rejection sampling identical --
+    square rule bit-exact; circle rule within 2 ulp of the 4 m radius (libdevice cos / sin against numpy's)."""
+    from aemcarl_b200 import scenarios
+    from aemcarl_b200.engine import get_engine
+    eng = get_engine(0)
+    for phase, first in (("train", 123), ("val", 0), ("test", 37)):
+        r_h, h_h = scenarios.generate_pool(phase, first, 256, n, rule, randomize_attributes=randomize)
+        r_d, h_d = eng.generate_scenarios(phase, first, 256, n, rule, randomize_attributes=randomize)
+        r_d, h_d = r_d.cpu().numpy(), h_d.cpu().numpy()
+        assert np.array_equal(r_d, r_h)
+        if rule == "square_crossing":
+            assert np.array_equal(h_d, h_h)
+        else:
+            assert np.abs(h_d - h_h).max() <= 2 * np.spacing(4.0)
+            assert np.array_equal(h_d[:, :, [2, 3, 4, 7]], h_h[:, :, [2, 3, 4, 7]])
+
+
+def test_device_scenario_generation_gives_up_on_an_infeasible_draw():
+    """18 humans with randomised radii do not fit on the 4 m circle: the reference's rejection loop never returns; the kernel
+    gives the case up (NaN) instead of hanging the GPU"""
+    from aemcarl_b200.engine import get_engine
+    r, h = get_engine(0).generate_scenarios("train", 0, 8, 30, "circle_crossing", randomize_attributes=True)
+    torch.cuda.synchronize()
+    assert torch.isnan(h).any()

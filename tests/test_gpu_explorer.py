@@ -107,6 +107,24 @@ def test_train_entry_point_with_the_vectorised_rl_phase(tmp_path):
     assert all(torch.isfinite(p).all() for p in out["model"].parameters())
 
 
+def test_train_entry_point_with_the_fused_optimisation_step(tmp_path):
+    """train.py --fused_step: imitation epochs and RL updates run through aem_train_grad + aem_adam_step (csrc/train.cu);
+    the policy's lookahead engine keeps seeing the updated weights, the checkpoint holds the trained parameters."""
+    from aemcarl_b200.crowd_nav import train
+    out = train.main(["--output_dir", str(tmp_path), "--il_episodes", "6", "--il_epochs", "2", "--train_episodes", "64",
+                      "--vectorised", "32", "--updates_per_wave", "4", "--fused_step"])
+    model = out["model"]
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+    assert out["trainer"]._fused is not None and out["trainer"]._fused.step > 0
+    sd = torch.load(tmp_path / "rl_model.pth", map_location="cpu")
+    for k, v in model.state_dict().items():
+        assert torch.equal(sd[k], v.cpu()), k
+    ref = type(model)()
+    ref.load_state_dict(sd)                                    # a reference-shaped module loads the checkpoint
+    assert out["explorer"].vec_stats["success"] + out["explorer"].vec_stats["collision"] \
+        + out["explorer"].vec_stats["timeout"] == 32
+
+
 def test_vectorised_imitation_phase_reproduces_the_serial_teacher():
     """Imitation learning (train.py:171-204): the robot follows the ORCA teacher (safety_space 0.15), every step is
     stored with the discounted Monte-Carlo return.  Vectorised (robot appended to the humans as one more ORCA agent,
