@@ -74,6 +74,8 @@ SYMBOLS = {
     "aem_generate_scenarios": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(ScenarioParams), _VP, _VP, _VP]),
     "aem_train_grad": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 8),
+    "aem_sample_batch": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP, ctypes.c_uint64, ctypes.c_uint64,
+                                        _VP, _VP, _VP, _VP]),
     "aem_adam_step": (ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_double, ctypes.c_int, ctypes.c_double, _VP]),
     "aem_launch_count": (ctypes.c_longlong, [_VP]),

@@ -835,6 +835,19 @@ int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const floa
     return AEM_OK;
 }
 
+int aem_sample_batch(aem_handle h, int N, int k, int n, const float *states_d, const float *values_d, uint64_t seed,
+                     uint64_t counter, float *out_states_d, float *out_values_d, int64_t *out_index_d, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (N < 1 || k < 1 || k > N || k > 8192 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad N / k / n");
+    if (!states_d || !values_d || !out_states_d || !out_values_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_sample_batch(N, k, n * 13, states_d, values_d, seed, counter, out_states_d, out_values_d, out_index_d,
+                                       as_stream(stream)));
+    h->launches += 1;
+    return AEM_OK;
+}
+
 int aem_adam_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *exp_avg_d, float *exp_avg_sq_d,
                   double lr, double beta1, double beta2, double eps, int step, double grad_scale, void *stream)
 {

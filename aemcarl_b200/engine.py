@@ -218,6 +218,17 @@ class Engine:
                                       _ptr(values), _ptr(steps), self._stream()))
         return grad, loss, values, steps
 
+    def sample_batch(self, states, values, size, k, seed, counter, want_index=False):
+        """k of the first `size` (state, value) pairs of a replay ring, uniformly without replacement -> ([k, n, 13], [k, 1])"""
+        cap, n, _ = states.shape
+        self._chk(states, F32, (cap, n, 13)); self._chk(values, F32, (cap, 1))
+        out_s = torch.empty((k, n, 13), dtype=F32, device=self.device)
+        out_v = torch.empty((k, 1), dtype=F32, device=self.device)
+        idx = torch.empty((k,), dtype=torch.int64, device=self.device) if want_index else None
+        check(self.lib.aem_sample_batch(self.h, int(size), int(k), n, _ptr(states), _ptr(values), ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                                        ctypes.c_uint64(counter), _ptr(out_s), _ptr(out_v), _ptr(idx), self._stream()))
+        return (out_s, out_v, idx) if want_index else (out_s, out_v)
+
     def adam_step(self, params, grad, exp_avg, exp_avg_sq, lr, betas, eps, step, grad_scale=1.0):
         """torch.optim.Adam.step() on flat float32 vectors (no weight decay / amsgrad); step is 1-based"""
         for t in (params, grad, exp_avg, exp_avg_sq):

@@ -20,6 +20,7 @@
  *   aem_transform       <- MultiHumanRL.transform multi_human_rl.py:423-438 (replay-memory sample of the current state)
  *   aem_generate_scenarios <- CrowdSim.reset's seeded scenario draw, crowd_sim.py:486-552,390-442
  *   aem_train_grad      <- Trainer.optimize_batch / optimize_epoch forward + MSE + backward (crowd_nav/utils/trainer.py:47-58,70-82)
+ *   aem_sample_batch    <- next(iter(DataLoader(memory, batch_size, shuffle=True))), trainer.py:70-72 + memory.py
  *   aem_adam_step       <- optimizer.step() of optim.Adam (trainer.py:30,56,80)
  *   aem_decide_step_host<- Robot.act + CrowdSim.step through HOST buffers (explorer.py:51-53), the e2e call
  *
@@ -184,6 +185,13 @@ int aem_transform(aem_handle h, int B, int n, const double *robot_d, const doubl
  * values_d [B] f32, steps_d [1] i32 = the batch's GRU step count (the last three may be NULL).  Three kernel launches. */
 int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const float *states_d, const float *targets_d,
                    float *grad_d, float *loss_d, float *values_d, int32_t *steps_d, void *stream);
+
+/* One mini-batch of the replay memory (memory.py:4-28 read through DataLoader(memory, batch_size, shuffle=True), trainer.py:70-72):
+ * k of the N stored pairs, uniformly at random WITHOUT replacement (Floyd's algorithm on a counter-based generator: the same
+ * (seed, counter) gives the same batch).  states_d [N][n][13] f32, values_d [N] f32 -> out_states_d [k][n][13], out_values_d [k],
+ * out_index_d [k] i64 (may be NULL). */
+int aem_sample_batch(aem_handle h, int N, int k, int n, const float *states_d, const float *values_d, uint64_t seed,
+                     uint64_t counter, float *out_states_d, float *out_values_d, int64_t *out_index_d, void *stream);
 
 /* torch.optim.Adam.step() (trainer.py:30 uses betas (0.9, 0.99), eps 1e-3; no weight decay, no amsgrad) on flat vectors of
  * `count` floats: step = 1-based number of this update; the gradient is multiplied by grad_scale first (1 / world_size

@@ -147,3 +147,27 @@ def test_fused_trainer_walks_with_the_eager_trainer():
     before = fs.flat.clone()
     tr._step(*batches[0])
     assert not torch.equal(before, torch.from_numpy(model_b.flat_weights()).to(dev))
+
+
+def test_sample_batch_draws_a_uniform_subset_without_replacement(eng):
+    """aem_sample_batch against its contract: k distinct indices below `size`, the gathered rows, reproducible per (seed, counter),
+    different across counters, and uniform over the ring (chi-square over 200 bins of 2,000 batches)."""
+    dev = eng.device
+    cap, size, k, n = 5000, 4000, 100, 5
+    states = torch.arange(cap, device=dev, dtype=torch.float32).view(cap, 1, 1).expand(cap, n, 13).contiguous()
+    values = -torch.arange(cap, device=dev, dtype=torch.float32).view(cap, 1)
+    s, v, idx = eng.sample_batch(states, values, size, k, 7, 1, want_index=True)
+    assert idx.min() >= 0 and idx.max() < size and len(torch.unique(idx)) == k
+    assert torch.equal(s, states[idx]) and torch.equal(v, values[idx])
+    s2, v2, idx2 = eng.sample_batch(states, values, size, k, 7, 1, want_index=True)
+    assert torch.equal(idx, idx2)
+    assert not torch.equal(idx, eng.sample_batch(states, values, size, k, 7, 2, want_index=True)[2])
+    counts = torch.zeros(size, device=dev)
+    for c in range(2000):
+        counts[eng.sample_batch(states, values, size, k, 11, c, want_index=True)[2]] += 1
+    bins = counts.view(200, -1).sum(1).cpu().numpy()
+    expect = 2000 * k / 200
+    chi2 = float(((bins - expect) ** 2 / expect).sum())
+    assert chi2 < 300, chi2                                  # 199 degrees of freedom: mean 199, sd 20
+    full = eng.sample_batch(states, values, 64, 64, 3, 9, want_index=True)[2]     # k == size: a permutation of everything
+    assert sorted(full.tolist()) == list(range(64))
