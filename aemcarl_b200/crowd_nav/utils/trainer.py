@@ -100,7 +100,7 @@ class GraphedStep(object):
 class FusedStep(object):
     """One optimisation step as hand-written kernels (csrc/train.cu): aem_train_grad (forward with the
     reference's batch-global ACT halting + MSE + backward, three launches) -> the flat gradient all-reduce of the
-    data-parallel run -> aem_adam_step (one launch).  The live parameters of the module become views into ONE flat
+    data-parallel run -> aem_adam_step / aem_sgd_step / aem_rmsprop_step (one launch; the three optimizers of trainer.py:24-34).  The live parameters of the module become views into ONE flat
     float32[113752] vector in blob order, so the kernels, the NCCL all-reduce and the lookahead engine's weight upload all
     work on the same memory without gather / scatter copies.  Adam moments are views into flat vectors too, and are
     shared with the torch optimizer's state so optimizer.state_dict() stays meaningful."""
@@ -112,6 +112,7 @@ class FusedStep(object):
         if dev.type != "cuda":
             raise RuntimeError("the fused training step is a CUDA kernel; there is no CPU fallback")
         self.model, self.optimizer = model, optimizer
+        self.kind = {optim.Adam: "adam", optim.SGD: "sgd", optim.RMSprop: "rmsprop"}[type(optimizer)]
         self.engine = get_engine(dev.index or 0, role="trainer")
         self.engine.set_act_mode(model.act_fixed, model.act_steps)
         named = dict(model.named_parameters())
@@ -133,18 +134,29 @@ class FusedStep(object):
                 p.data = view                                   # the module now lives in the flat vector
                 st = optimizer.state.get(p)
                 if st:                                          # continue from eager / graphed steps
-                    self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
-                    self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
-                    self.step = max(self.step, int(st["step"]))
+                    if self.kind == "adam":
+                        self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                        self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                        self.step = max(self.step, int(st["step"]))
+                    elif self.kind == "sgd" and st.get("momentum_buffer") is not None:
+                        self.exp_avg[off:off + n].copy_(st["momentum_buffer"].reshape(-1))
+                        self.step = max(self.step, 1)
+                    elif self.kind == "rmsprop":
+                        self.exp_avg_sq[off:off + n].copy_(st["square_avg"].reshape(-1))
+                        self.step = max(self.step, int(st["step"]))
                 self._params.append((p, off, n, shape))
         self.export_state()
 
     def export_state(self):
         """make the torch optimizer's state describe the flat vectors (views, no copies)"""
         for p, off, n, shape in self._params:
-            self.optimizer.state[p] = {"step": torch.tensor(float(self.step)),
-                                       "exp_avg": self.exp_avg[off:off + n].view(shape),
-                                       "exp_avg_sq": self.exp_avg_sq[off:off + n].view(shape)}
+            m, v = self.exp_avg[off:off + n].view(shape), self.exp_avg_sq[off:off + n].view(shape)
+            if self.kind == "adam":
+                self.optimizer.state[p] = {"step": torch.tensor(float(self.step)), "exp_avg": m, "exp_avg_sq": v}
+            elif self.kind == "sgd":
+                self.optimizer.state[p] = {"momentum_buffer": m if self.step > 0 else None}
+            else:
+                self.optimizer.state[p] = {"step": torch.tensor(float(self.step)), "square_avg": v}
 
     def __call__(self, inputs, values):
         g = self.optimizer.param_groups[0]
@@ -158,8 +170,13 @@ class FusedStep(object):
             world = dist.get_world_size()
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
         self.step += 1
-        self.engine.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"], g["eps"], self.step,
-                              1.0 / world)
+        if self.kind == "adam":
+            self.engine.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"], g["eps"], self.step,
+                                  1.0 / world)
+        elif self.kind == "sgd":
+            self.engine.sgd_step(self.flat, self.grad, self.exp_avg, g["lr"], g["momentum"], self.step, 1.0 / world)
+        else:
+            self.engine.rmsprop_step(self.flat, self.grad, self.exp_avg_sq, g["lr"], g["alpha"], g["eps"], 1.0 / world)
         self.model.note_external_update()
         return self.loss[0].clone()
 
@@ -195,8 +212,8 @@ class Trainer(object):
     def _step(self, inputs, values):
         """one optimisation step; returns the loss as a 0-dim tensor (the callers synchronise once per call, not per step)"""
         if self.fused:
-            if not isinstance(self.optimizer, optim.Adam) or self.model.training or getattr(self.model, "act_fixed", False):
-                raise NotImplementedError("the fused training step covers Adam on the eval()-mode adaptive network "
+            if self.model.training or getattr(self.model, "act_fixed", False):
+                raise NotImplementedError("the fused training step covers the eval()-mode adaptive network "
                                           "(dropout inactive, act_fixed = False)")
             if self._fused is None:
                 self._fused = FusedStep(self.model, self.optimizer, inputs.device)

@@ -182,6 +182,10 @@ cudaError_t launch_scenarios(int rule, uint32_t first_seed, int count, int n, co
                              double *humans, cudaStream_t st);
 cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, const float *states, const float *targets,
                               float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st);
+cudaError_t launch_sgd(size_t count, float *p, const float *g, float *buf, double lr, double momentum, int step, double gscale,
+                       cudaStream_t st);
+cudaError_t launch_rmsprop(size_t count, float *p, const float *g, float *sq, double lr, double alpha, double eps, double gscale,
+                           cudaStream_t st);
 cudaError_t launch_sample_batch(int N, int k, int row_floats, const float *states, const float *values, uint64_t seed,
                                 uint64_t counter, float *out_states, float *out_values, int64_t *out_index, cudaStream_t st);
 cudaError_t launch_adam(size_t count, float *p, const float *g, float *m, float *v, double lr, double b1, double b2, double eps,

@@ -862,6 +862,31 @@ int aem_adam_step(aem_handle h, size_t count, float *params_d, const float *grad
     return AEM_OK;
 }
 
+int aem_sgd_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *momentum_buf_d, double lr,
+                 double momentum, int step, double grad_scale, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (!params_d || !grad_d || !momentum_buf_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    if (step < 1) return aem_set_error(AEM_ERR_INVALID, "step is 1-based");
+    if (count == 0) return AEM_OK;
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_sgd(count, params_d, grad_d, momentum_buf_d, lr, momentum, step, grad_scale, as_stream(stream)));
+    h->launches += 1;
+    return AEM_OK;
+}
+
+int aem_rmsprop_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *square_avg_d, double lr,
+                     double alpha, double eps, double grad_scale, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (!params_d || !grad_d || !square_avg_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    if (count == 0) return AEM_OK;
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_rmsprop(count, params_d, grad_d, square_avg_d, lr, alpha, eps, grad_scale, as_stream(stream)));
+    h->launches += 1;
+    return AEM_OK;
+}
+
 long long aem_launch_count(aem_handle h) { return h ? h->launches : 0; }
 
 }  // extern "C"

@@ -749,6 +749,44 @@ __global__ void __launch_bounds__(256) adam_kernel(size_t count, float *__restri
     p[e] = p[e] - step_size * (mm / denom);
 }
 
+// torch.optim.SGD(momentum, dampening 0, no Nesterov, no weight decay): buf = g on the first step, else momentum buf + g
+__global__ void __launch_bounds__(256) sgd_kernel(size_t count, float *__restrict__ p, const float *__restrict__ g,
+                                                   float *__restrict__ buf, float lr, float momentum, int first, float gscale)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const float gr = g[e] * gscale;
+    const float b = first ? gr : buf[e] * momentum + gr;
+    buf[e] = b;
+    p[e] = p[e] - lr * b;
+}
+
+// torch.optim.RMSprop(alpha, eps; not centered, no momentum): sq = alpha sq + (1 - alpha) g^2; p -= lr g / (sqrt(sq) + eps)
+__global__ void __launch_bounds__(256) rmsprop_kernel(size_t count, float *__restrict__ p, const float *__restrict__ g,
+                                                       float *__restrict__ sq, float lr, float alpha, float eps, float gscale)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const float gr = g[e] * gscale;
+    const float s = sq[e] * alpha + (1.0f - alpha) * gr * gr;
+    sq[e] = s;
+    p[e] = p[e] - lr * (gr / (sqrtf(s) + eps));
+}
+
+cudaError_t launch_sgd(size_t count, float *p, const float *g, float *buf, double lr, double momentum, int step, double gscale,
+                       cudaStream_t st)
+{
+    sgd_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(count, p, g, buf, (float)lr, (float)momentum, step == 1, (float)gscale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rmsprop(size_t count, float *p, const float *g, float *sq, double lr, double alpha, double eps, double gscale,
+                           cudaStream_t st)
+{
+    rmsprop_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(count, p, g, sq, (float)lr, (float)alpha, (float)eps, (float)gscale);
+    return cudaGetLastError();
+}
+
 // One uniformly random mini-batch WITHOUT replacement from the replay ring (what next(iter(DataLoader(memory, batch_size,
 // shuffle=True))) yields, trainer.py:70-72, memory.py): Floyd's subset algorithm by warp 0 (membership test by ballot), then
 // every thread gathers.  Replaces randperm(N) + two index kernels (0.11 ms at N = 100,000) with one ~5 us launch.

@@ -237,6 +237,16 @@ class Engine:
                                      float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), float(grad_scale),
                                      self._stream()))
 
+    def sgd_step(self, params, grad, momentum_buf, lr, momentum, step, grad_scale=1.0):
+        """torch.optim.SGD(momentum).step() on flat float32 vectors; step is 1-based (the first call initialises the buffer)"""
+        check(self.lib.aem_sgd_step(self.h, params.numel(), _ptr(params), _ptr(grad), _ptr(momentum_buf), float(lr), float(momentum),
+                                    int(step), float(grad_scale), self._stream()))
+
+    def rmsprop_step(self, params, grad, square_avg, lr, alpha, eps, grad_scale=1.0):
+        """torch.optim.RMSprop(alpha, eps).step() on flat float32 vectors"""
+        check(self.lib.aem_rmsprop_step(self.h, params.numel(), _ptr(params), _ptr(grad), _ptr(square_avg), float(lr), float(alpha),
+                                        float(eps), float(grad_scale), self._stream()))
+
     # ---- host-buffer call (the e2e path) -------------------------------------------------------
     def decide_step_host(self, robot, humans, global_time, gamma_bar, want_values=False):
         """robot [B,9], humans [B,n,8], global_time [B]: contiguous float64 numpy arrays, updated IN PLACE."""

@@ -21,7 +21,7 @@
  *   aem_generate_scenarios <- CrowdSim.reset's seeded scenario draw, crowd_sim.py:486-552,390-442
  *   aem_train_grad      <- Trainer.optimize_batch / optimize_epoch forward + MSE + backward (crowd_nav/utils/trainer.py:47-58,70-82)
  *   aem_sample_batch    <- next(iter(DataLoader(memory, batch_size, shuffle=True))), trainer.py:70-72 + memory.py
- *   aem_adam_step       <- optimizer.step() of optim.Adam (trainer.py:30,56,80)
+ *   aem_adam_step / aem_sgd_step / aem_rmsprop_step <- optimizer.step() of the three optimizers of trainer.py:24-34
  *   aem_decide_step_host<- Robot.act + CrowdSim.step through HOST buffers (explorer.py:51-53), the e2e call
  *
  * Conventions: plain pointers and sizes only; `*_d` = device pointer, `*_h` = host pointer; all device entry
@@ -198,6 +198,13 @@ int aem_sample_batch(aem_handle h, int N, int k, int n, const float *states_d, c
  * after a summing all-reduce). */
 int aem_adam_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *exp_avg_d, float *exp_avg_sq_d,
                   double lr, double beta1, double beta2, double eps, int step, double grad_scale, void *stream);
+
+/* The other two optimizers Trainer.set_learning_rate offers (trainer.py:24-34): optim.SGD(momentum = 0.9) -- momentum_buf_d is
+ * initialised by the step == 1 call -- and optim.RMSprop(alpha = 0.9, eps = 1e-8; not centered, no momentum). */
+int aem_sgd_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *momentum_buf_d, double lr,
+                 double momentum, int step, double grad_scale, void *stream);
+int aem_rmsprop_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *square_avg_d, double lr,
+                     double alpha, double eps, double grad_scale, void *stream);
 
 /* ---- host-buffer call: one full env-step (predict + step) for B environments ----
  * In/out (updated in place): robot_h [B][9], humans_h [B][n][8], global_time_h [B].

@@ -171,3 +171,26 @@ def test_sample_batch_draws_a_uniform_subset_without_replacement(eng):
     assert chi2 < 300, chi2                                  # 199 degrees of freedom: mean 199, sd 20
     full = eng.sample_batch(states, values, 64, 64, 3, 9, want_index=True)[2]     # k == size: a permutation of everything
     assert sorted(full.tolist()) == list(range(64))
+
+
+@pytest.mark.parametrize("optimizer", ["SGD", "RMSprop"])
+def test_fused_sgd_and_rmsprop_walk_with_torch(optimizer):
+    """the other two optimizers of Trainer.set_learning_rate (trainer.py:24-34) through the fused step"""
+    from aemcarl_b200.crowd_nav.utils.trainer import Trainer
+    from test_gpu_api import setup
+    env, robot, policy = setup(seed=4, ponder_bias=-0.13)
+    dev = torch.device("cuda:0")
+    model_a = policy.get_model()
+    model_b = copy.deepcopy(model_a).to(dev)
+    g = torch.Generator(device=dev).manual_seed(6)
+    batches = [(torch.randn((100, 5, 13), device=dev, generator=g), torch.randn((100, 1), device=dev, generator=g))
+               for _ in range(5)]
+    losses = {}
+    for name, model, fused in (("eager", model_a, False), ("fused", model_b, True)):
+        tr = Trainer(model, None, dev, 100, fused=fused)
+        tr.set_learning_rate(1e-3, optimizer)
+        losses[name] = [float(tr._step(x, v)) for x, v in batches]
+    assert np.allclose(losses["eager"], losses["fused"], rtol=2e-4, atol=1e-6), (losses["eager"], losses["fused"])
+    for (k, pa), pb in zip(model_a.named_parameters(), model_b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-3, atol=2e-5), (k, float((pa - pb).abs().max()))
+    assert losses["fused"][0] != losses["fused"][-1]
