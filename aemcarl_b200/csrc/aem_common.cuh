@@ -137,10 +137,10 @@ struct aem_handle_s {
     int32_t *s_info, *s_best, *s_odone, *s_oinfo;
     void *s_stream;
     // scratch of the training step (train.cu): per-CTA gradient slices, squared errors, halting flags, activation stash
-    float *tr_part, *tr_sqerr, *tr_stash;
+    float *tr_part, *tr_sqerr, *tr_stash, *tr_gru;
     int *tr_flags;
     int tr_grid, tr_B;
-    size_t tr_stash_floats;
+    size_t tr_stash_floats, tr_gru_floats;
 };
 
 #define AEM_CUDA_CHECK(expr)                                                      \

@@ -395,6 +395,8 @@ struct TrainArgs {
     float *values;      // [B] or null
     int *flags;         // [2]
     float *stash_g;     // [grid][stash] when the stash does not fit in shared memory, else null
+    float *gru_g;       // [B][layout.enc]: the probe's GRU-ACT intermediates (x, h_0..3, three step blocks) handed to the
+                        // forward / backward kernel, or null (the probe keeps one step block, the main kernel recomputes)
     int B, n;
 };
 
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_probe_kernel(TrainArgs a)
     extern __shared__ __align__(16) float sm[];
     const int T = a.n + 1;
     TrLayout L = tr_layout(T);
-    L.gru_step = 0;                                 // the probe keeps nothing: every step reuses one stash block
+    if (!a.gru_g) L.gru_step = 0;                   // no hand-off: every step reuses one stash block
     __shared__ __align__(8) uint64_t bars[2];
     WPipe pipe;
     pipe.init(sm, sm + TR_WS_FLOATS, bars);
@@ -428,6 +430,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_probe_kernel(TrainArgs a)
                 if (un1) atomicOr(a.flags + 0, 1);
                 if (un2) atomicOr(a.flags + 1, 1);
             }
+        }
+        if (a.gru_g) {                              // x | h_0..h_3 | step blocks 1..3, as tr_layout lays them out
+            float *dst = a.gru_g + (size_t)b * L.enc;
+            for (int e = threadIdx.x; e < L.enc; e += blockDim.x) dst[e] = st[e];
         }
         psync();
     }
@@ -459,7 +465,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
         for (int e = tid; e < NUM_WEIGHTS; e += nt) G[e] = 0.0f;
         return;
     }
-    pipe.issue(w + OFF_Z1W, 100, 63);
+    if (a.gru_g) pipe.issue(w + OFF_ENC + ENC_INW, 150, 50);
+    else pipe.issue(w + OFF_Z1W, 100, 63);
     int iter = 0;
     for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++iter) {
         const bool acc = iter > 0, more = b + (int)gridDim.x < a.B;
@@ -467,8 +474,21 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
         const float *Ws;
         // =========================================== forward ===========================================
         float *A = buf[0], *hxb = buf[1];
-        load_tokens(state, a.n, st + L.x, hxb, st + L.h, A);
-        gru_forward(w, st, L, T, K, A, hxb, pipe, nullptr, w + OFF_ENC + ENC_INW, 150, 50);
+        if (a.gru_g) {                              // the probe already ran the GRU steps of this sample: take its stash
+            const float *src = a.gru_g + (size_t)b * L.enc;
+            for (int e = tid; e < L.enc; e += nt) st[e] = src[e];
+            psync();
+            for (int e = tid; e < T * 50; e += nt) {                // A = sum_{k <= K} p_k h_k, accumulated like gru_forward
+                float s = 0.0f;
+                for (int k = 1; k <= K; ++k)
+                    s = fmaf(gru_stash(st + L.gru + (k - 1) * L.gru_step, T).p[e / 50], st[L.h + k * T * 50 + e], s);
+                A[e] = s;
+            }
+            psync();
+        } else {
+            load_tokens(state, a.n, st + L.x, hxb, st + L.h, A);
+            gru_forward(w, st, L, T, K, A, hxb, pipe, nullptr, w + OFF_ENC + ENC_INW, 150, 50);
+        }
         for (int l = 0; l < 3; ++l) {
             const float *E = w + OFF_ENC + l * ENC_SIZE;
             EncStash c = enc_stash(st + L.enc + l * L.enc_layer, T);
@@ -704,6 +724,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
             lin_bwd_x<50, 100, 100>(Ws, dr, 50, T, [=](int r, int i, float v) { d1[r * 100 + i] = g.ar1[r * 100 + i] > 0.0f ? v : 0.0f; });
             Ws = pipe.take();
             if (k > 1) pipe.issue(w + OFF_QW, 50, 63);
+            else if (more && a.gru_g) pipe.issue(w + OFF_ENC + ENC_INW, 150, 50);
             else if (more) pipe.issue(w + OFF_Z1W, 100, 63);
             lin_bwd_w<100, 63>(G + OFF_R1W, G + OFF_R1B, d1, 100, hxb, 64, T, gacc);
             lin_bwd_x<100, 63, 50>(Ws, d1, 100, T, [=](int r, int i, float v) { dh[r * 50 + i] += v; });
@@ -845,10 +866,10 @@ size_t train_smem_bytes(int T, bool stash_in_smem)
     return f * sizeof(float);
 }
 
-size_t probe_smem_bytes(int T)
+size_t probe_smem_bytes(int T, bool handoff)
 {
-    const TrLayout L = tr_layout(T);
-    return (2 * TR_WS_FLOATS + (size_t)T * 50 + T * 64 + ((3 * T + 3) & ~3) + L.gru + L.gru_step) * sizeof(float);   // x, h, one step
+    const TrLayout L = tr_layout(T);     // x, h and one step block -- or all three when the stash is handed to the main kernel
+    return (2 * TR_WS_FLOATS + (size_t)T * 50 + T * 64 + ((3 * T + 3) & ~3) + (handoff ? L.enc : L.gru + L.gru_step)) * sizeof(float);
 }
 
 cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, const float *states, const float *targets,
@@ -859,11 +880,12 @@ cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, c
     const size_t smem_limit = 227 * 1024;
     const bool in_smem = train_smem_bytes(T, true) <= smem_limit;
     const int grid = B < h->num_sms ? B : h->num_sms;
+    const bool handoff = probe_smem_bytes(T, true) <= smem_limit;
     cudaError_t e;
-    if (grid > h->tr_grid || B > h->tr_B || (!in_smem && (size_t)grid * L.total > h->tr_stash_floats)) {   // (re)allocate scratch
+    if (grid > h->tr_grid || B > h->tr_B || (handoff && (size_t)B * L.enc > h->tr_gru_floats) || (!in_smem && (size_t)grid * L.total > h->tr_stash_floats)) {   // (re)allocate scratch
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-        cudaFree(h->tr_part); cudaFree(h->tr_sqerr); cudaFree(h->tr_flags); cudaFree(h->tr_stash);
-        h->tr_part = h->tr_sqerr = h->tr_stash = nullptr; h->tr_flags = nullptr;
+        cudaFree(h->tr_part); cudaFree(h->tr_sqerr); cudaFree(h->tr_flags); cudaFree(h->tr_stash); cudaFree(h->tr_gru);
+        h->tr_part = h->tr_sqerr = h->tr_stash = h->tr_gru = nullptr; h->tr_flags = nullptr;
         h->tr_grid = grid > h->tr_grid ? grid : h->tr_grid;
         h->tr_B = B > h->tr_B ? B : h->tr_B;
         if ((e = cudaMalloc(&h->tr_part, (size_t)h->tr_grid * NUM_WEIGHTS * sizeof(float))) != cudaSuccess) return e;
@@ -871,14 +893,17 @@ cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, c
         if ((e = cudaMalloc(&h->tr_flags, 2 * sizeof(int))) != cudaSuccess) return e;
         h->tr_stash_floats = in_smem ? 0 : (size_t)h->tr_grid * tr_layout(AEM_MAX_HUMANS + 1).total;
         if (h->tr_stash_floats && (e = cudaMalloc(&h->tr_stash, h->tr_stash_floats * sizeof(float))) != cudaSuccess) return e;
+        h->tr_gru_floats = handoff ? (size_t)h->tr_B * L.enc : 0;
+        if (h->tr_gru_floats && (e = cudaMalloc(&h->tr_gru, h->tr_gru_floats * sizeof(float))) != cudaSuccess) return e;
     }
     TrainArgs a;
     a.params = params; a.states = states; a.targets = targets;
     a.part = h->tr_part; a.sqerr = h->tr_sqerr; a.values = values; a.flags = h->tr_flags;
     a.stash_g = in_smem ? nullptr : h->tr_stash;
+    a.gru_g = handoff ? h->tr_gru : nullptr;
     a.B = B; a.n = n;
     if ((e = cudaMemsetAsync(h->tr_flags, 0, 2 * sizeof(int), st)) != cudaSuccess) return e;
-    const size_t psm = probe_smem_bytes(T), fsm = train_smem_bytes(T, in_smem);
+    const size_t psm = probe_smem_bytes(T, handoff), fsm = train_smem_bytes(T, in_smem);
     if (psm > smem_limit) return cudaErrorInvalidValue;
     if ((e = cudaFuncSetAttribute(train_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)) != cudaSuccess) return e;
     auto kern = in_smem ? train_fwdbwd_kernel<true> : train_fwdbwd_kernel<false>;
