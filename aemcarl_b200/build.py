@@ -22,7 +22,7 @@ SOURCES = {
     "lookahead_tc.cu": [],
     "lookahead_h16.cu": [],
     "lookahead_q16.cu": [],
-    "train.cu": [],
+    "train.cu": ["-DAEM_TRAIN_TIMELINE"] if os.environ.get("AEM_TRAIN_TIMELINE") else [],
     "scenario.cu": ["-fmad=false"],   # Python float arithmetic of the scenario draw, op by op
     "env.cu": ["-fmad=false"],   # FP64 env arithmetic is a sequence of individually rounded Python float ops
     "orca.cu": ["-fmad=false"],

@@ -3,19 +3,22 @@
 //   states with the reference's BATCH-GLOBAL adaptive-computation-time halting (components.py:132-134), MSE against the
 //   targets (trainer.py:53,76), the complete backward pass, and torch.optim.Adam's update (trainer.py:30).
 //
-// Shape of the problem: 100 samples x (n + 1) tokens x 113,752 parameters -- every weight is used for only T = n + 1 rows
-// per sample, so the step is bound by weight traffic out of L2 and by latency, not by FLOPs.  Design:
+// Shape of the problem: 100 samples x (n + 1) tokens x 113,752 parameters -- every weight meets only T = n + 1 rows per
+// sample, so the step is bound by latency (a chain of ~90 dependent small products per sample), not by FLOPs or HBM.
 //   * train_probe_kernel   one CTA per sample runs the three GRU steps and ORs "some row still below 1 - epsilon after
-//                          step k" into two global flags: the batch-global step count K every sample must use.
-//   * train_fwdbwd_kernel  one CTA per sample (grid-stride if the batch exceeds the grid): forward with every
-//                          intermediate kept in shared memory (80 KB at T = 6; global scratch when it does not fit),
-//                          then the hand-derived backward (tests/manual_backward.py is the same derivation in numpy,
-//                          checked against autograd).  Weights are staged layer by layer into shared memory with an odd
-//                          row pitch, so both products (y = W x and dx = W^T dy) read them without bank conflicts.
-//                          Weight gradients go to the CTA's OWN slice part[cta][113,752] -- no atomics.
+//                          step k" into two global flags: the batch-global step count K every sample must use.  Its GRU
+//                          intermediates are handed to the next kernel through an L2-resident scratch (no recompute).
+//   * train_fwdbwd_kernel  one CTA (512 threads) per sample (grid-stride if the batch exceeds the grid): forward with every
+//                          intermediate kept in shared memory (80 KB at T = 6; a global scratch slice when it does not
+//                          fit), then the hand-derived backward (tests/manual_backward.py is the same derivation in numpy,
+//                          checked against autograd).  Weights arrive one layer ahead by one cp.async.bulk per layer into a
+//                          two-slot ring.  y = W x and dx = W^T dy run on mma.sync.m16n8k8 (3xTF32, FP32-grade); the weight
+//                          gradient dW = dy^T x is an FP32 outer product with coalesced stores into the CTA's OWN slice
+//                          part[cta][113,752] -- no atomics.
 //   * train_reduce_kernel  grad[e] = sum over CTAs in a fixed order (deterministic), loss = mean squared error.
-//   * adam_kernel          one thread per parameter.
-// The gradient all-reduce of a data-parallel run sits between train_reduce_kernel and adam_kernel (trainer.py).
+//   * adam_kernel / sgd_kernel / rmsprop_kernel   one thread per parameter (the three optimizers of trainer.py:24-34).
+//   * sample_batch_kernel  a uniform mini-batch without replacement from the replay ring + gather, one launch.
+// The gradient all-reduce of a data-parallel run sits between train_reduce_kernel and the optimizer kernel (trainer.py).
 #include "aem_common.cuh"
 #include "tc_common.cuh"
 
@@ -72,7 +75,18 @@ __device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf
 // issue(): thread 0 arms the buffer's mbarrier with the byte count and starts cp.async.bulk on the 16-byte aligned
 // superset of the tensor (blob offsets are only 4-byte aligned); take(): every thread waits on that mbarrier.  The buffer
 // being refilled was last read two phases ago, i.e. before the previous psync().
+#ifdef AEM_TRAIN_TIMELINE
+// debug build only (python -m aemcarl_b200.build with AEM_TRAIN_TIMELINE=1): clock64 of CTA 0 at every barrier phase
+__device__ long long g_tr_tl[2048];
+__device__ int g_tr_tl_n;
+__device__ __forceinline__ void psync()
+{
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && g_tr_tl_n < 2048) g_tr_tl[g_tr_tl_n++] = clock64();
+}
+#else
 __device__ __forceinline__ void psync() { __syncthreads(); }
+#endif
 struct WPipe {
     float *b0, *b1;
     uint64_t *bars;          // [2] in shared memory
@@ -107,107 +121,142 @@ struct WPipe {
         if (cur) { aemtc::mbar_wait(bars + 1, par1); par1 ^= 1; p = b1 + head1; }
         else { aemtc::mbar_wait(bars, par0); par0 ^= 1; p = b0 + head0; }
         cur ^= 1;
+#ifdef AEM_TRAIN_TIMELINE
+        if (blockIdx.x == 0 && threadIdx.x == 0 && g_tr_tl_n < 2048) g_tr_tl[g_tr_tl_n++] = -clock64();     // weights arrived
+#endif
         return p;
     }
 };
 
-// The three products below keep a chunk of TR_RC token rows in registers, so a weight (or activation) is loaded once per
-// chunk instead of once per row; the reduction dimension is split over TR_KG adjacent lanes (shuffle reduction) so that
-// all 512 threads have work although a layer has only 50-150 outputs.  Activations are read as float2 (every pitch and
-// offset of the stash is even).
-constexpr int TR_RC = 6;        // rows per register chunk (T = 6 at the trainer's shape: one chunk)
-constexpr int TR_KG = 4;        // lanes sharing one output
-
-__device__ __forceinline__ float kg_sum(float v)
+// Two of the three products of a layer (y = W x, dx = W^T dy) run on the warp-level tensor-core instruction
+// mma.sync.m16n8k8 (TF32 inputs, FP32 accumulate) with the 3xTF32 split (hi = upper 19 bits, lo = x - hi; hi*hi + lo*hi + hi*lo),
+// i.e. FP32-grade results.  The 16-wide M dimension always carries WEIGHT-SHAPED indices (outputs or columns), the 8-wide N
+// dimension the token rows (T = 6 at the trainer's shape) or the other weight index, so 75 % of every instruction is useful
+// work and a 150 x 50 layer is 70 tiles.  (tcgen05 needs M = 128 rows and a commit / wait round trip per dependent step; for a
+// chain of ~90 dependent products over 6 rows the synchronous warp-level instruction is the right tool.)  Fragment layout
+// (PTX ISA, m16n8k8 .tf32): g = lane / 4, t = lane % 4;  A: a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4);
+// B: b0 (k = t, n = g) b1 (k = t + 4, n = g);  C: c0 (g, 2t) c1 (g, 2t + 1) c2 (g + 8, 2t) c3 (g + 8, 2t + 1).
+__device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo)
 {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v;
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+struct FragA { uint32_t hi[4], lo[4]; };
+struct FragB { uint32_t hi[2], lo[2]; };
+__device__ __forceinline__ FragA make_a(float a0, float a1, float a2, float a3)
+{
+    FragA f;
+    tf32_split(a0, f.hi[0], f.lo[0]); tf32_split(a1, f.hi[1], f.lo[1]);
+    tf32_split(a2, f.hi[2], f.lo[2]); tf32_split(a3, f.hi[3], f.lo[3]);
+    return f;
+}
+__device__ __forceinline__ FragB make_b(float b0, float b1)
+{
+    FragB f;
+    tf32_split(b0, f.hi[0], f.lo[0]); tf32_split(b1, f.hi[1], f.lo[1]);
+    return f;
+}
+__device__ __forceinline__ void mma3(float (&c)[4], const FragA &a, const FragB &b)
+{
+    mma_tf32(c, a.lo, b.hi);
+    mma_tf32(c, a.hi, b.lo);
+    mma_tf32(c, a.hi, b.hi);
 }
 
-// epi(r, o, b[o] + sum_i X[r][i] W[o][i]);  I even or odd, ldx even
+// epi(r, o, b[o] + sum_i X[r][i] W[o][i]):  Y^T [O x T] = W [O x I] X^T [I x T];  M = outputs, K = columns, N = rows
 template <int O, int I, class Epi>
 __device__ __forceinline__ void lin_fwd(const float *Ws, const float *__restrict__ bg, const float *X, int ldx, int T, Epi epi)
 {
-    constexpr int P = I;
-    static_assert(O * P + 8 <= TR_WS_FLOATS, "staging buffer");
-    const int kg = threadIdx.x & (TR_KG - 1), slot = threadIdx.x / TR_KG, nslot = blockDim.x / TR_KG;
-    for (int ob = 0; ob < O; ob += nslot) {                 // warp-uniform trip count (shuffles inside)
-        const int o = ob + slot;
-        if (ob + (int)(threadIdx.x >> 5) * (32 / TR_KG) >= O) break;      // the whole warp is past the last output
-        const bool live = o < O;
-        const float *w = Ws + (live ? o : 0) * P;
-        const float bias = live ? __ldg(bg + o) : 0.0f;
-        for (int r0 = 0; r0 < T; r0 += TR_RC) {
-            const int rows = T - r0 < TR_RC ? T - r0 : TR_RC;
-            float acc[TR_RC];
-#pragma unroll
-            for (int u = 0; u < TR_RC; ++u) acc[u] = 0.0f;
-            const float *x = X + r0 * ldx;
-            for (int i = 2 * kg; i + 1 < I; i += 2 * TR_KG) {
-                const float w0 = w[i], w1 = w[i + 1];
-#pragma unroll
-                for (int u = 0; u < TR_RC; ++u)
-                    if (u < rows) {
-                        const float2 xv = *reinterpret_cast<const float2 *>(x + u * ldx + i);
-                        acc[u] = fmaf(xv.y, w1, fmaf(xv.x, w0, acc[u]));
-                    }
+    static_assert(O * I + 8 <= TR_WS_FLOATS, "staging buffer");
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    constexpr int MT = (O + 15) / 16;
+    for (int mt = warp; mt < MT; mt += nw) {
+        const int oa = mt * 16 + g, ob = oa + 8;
+        const bool va = oa < O, vb = ob < O;
+        const float *wa = Ws + (va ? oa : 0) * I, *wb = Ws + (vb ? ob : 0) * I;
+        const float bias_a = va ? __ldg(bg + oa) : 0.0f, bias_b = vb ? __ldg(bg + ob) : 0.0f;
+        for (int r0 = 0; r0 < T; r0 += 8) {
+            const int row = r0 + g;
+            const bool rv = row < T;
+            const float *x = X + (rv ? row : 0) * ldx;
+            float c0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, c1[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // two chains: even / odd K steps
+#pragma unroll 2
+            for (int i0 = 0; i0 < I; i0 += 16) {
+                {
+                    const int ia = i0 + t, ib = ia + 4;
+                    const bool ka = ia < I, kb = ib < I;
+                    const FragA a = make_a(va && ka ? wa[ia] : 0.0f, vb && ka ? wb[ia] : 0.0f, va && kb ? wa[ib] : 0.0f,
+                                           vb && kb ? wb[ib] : 0.0f);
+                    mma3(c0, a, make_b(rv && ka ? x[ia] : 0.0f, rv && kb ? x[ib] : 0.0f));
+                }
+                if (i0 + 8 < I) {
+                    const int ia = i0 + 8 + t, ib = ia + 4;
+                    const bool ka = ia < I, kb = ib < I;
+                    const FragA a = make_a(va && ka ? wa[ia] : 0.0f, vb && ka ? wb[ia] : 0.0f, va && kb ? wa[ib] : 0.0f,
+                                           vb && kb ? wb[ib] : 0.0f);
+                    mma3(c1, a, make_b(rv && ka ? x[ia] : 0.0f, rv && kb ? x[ib] : 0.0f));
+                }
             }
-            if ((I & 1) && kg == ((I - 1) / 2) % TR_KG) {   // odd I: the last column
-                const float w0 = w[I - 1];
-#pragma unroll
-                for (int u = 0; u < TR_RC; ++u)
-                    if (u < rows) acc[u] = fmaf(x[u * ldx + I - 1], w0, acc[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < TR_RC; ++u) acc[u] = kg_sum(acc[u]);
-            static_assert(TR_RC <= 2 * TR_KG, "epilogue distribution");
-            const float v0 = kg == 0 ? acc[0] : kg == 1 ? acc[1] : kg == 2 ? acc[2] : acc[3];
-            const float v1 = kg == 0 ? acc[4] : acc[5];
-            if (live && kg < rows) epi(r0 + kg, o, v0 + bias);
-            if (live && kg + TR_KG < rows) epi(r0 + kg + TR_KG, o, v1 + bias);
+            const int ra = r0 + 2 * t, rb = ra + 1;
+            if (va && ra < T) epi(ra, oa, c0[0] + c1[0] + bias_a);
+            if (va && rb < T) epi(rb, oa, c0[1] + c1[1] + bias_a);
+            if (vb && ra < T) epi(ra, ob, c0[2] + c1[2] + bias_b);
+            if (vb && rb < T) epi(rb, ob, c0[3] + c1[3] + bias_b);
         }
     }
     psync();
 }
 
-// epi(r, i, sum_o dY[r][o] W[o][i]) for i < ICNT;  O even, lddy even
+// epi(r, i, sum_o dY[r][o] W[o][i]) for i < ICNT:  dX^T [I x T] = W^T [I x O] dY^T [O x T];  M = columns, K = outputs, N = rows
 template <int O, int I, int ICNT, class Epi>
 __device__ __forceinline__ void lin_bwd_x(const float *Ws, const float *dY, int lddy, int T, Epi epi)
 {
-    constexpr int P = I;
-    static_assert(O * P + 8 <= TR_WS_FLOATS && O % 2 == 0, "staging buffer / even O");
-    const int kg = threadIdx.x & (TR_KG - 1), slot = threadIdx.x / TR_KG, nslot = blockDim.x / TR_KG;
-    for (int ib = 0; ib < ICNT; ib += nslot) {
-        const int i = ib + slot;
-        if (ib + (int)(threadIdx.x >> 5) * (32 / TR_KG) >= ICNT) break;   // the whole warp is past the last column
-        const bool live = i < ICNT;
-        const float *w = Ws + (live ? i : 0);
-        for (int r0 = 0; r0 < T; r0 += TR_RC) {
-            const int rows = T - r0 < TR_RC ? T - r0 : TR_RC;
-            float acc[TR_RC];
-#pragma unroll
-            for (int u = 0; u < TR_RC; ++u) acc[u] = 0.0f;
-            const float *dy = dY + r0 * lddy;
-            for (int o = 2 * kg; o < O; o += 2 * TR_KG) {
-                const float w0 = w[o * P], w1 = w[(o + 1) * P];
-#pragma unroll
-                for (int u = 0; u < TR_RC; ++u)
-                    if (u < rows) {
-                        const float2 d = *reinterpret_cast<const float2 *>(dy + u * lddy + o);
-                        acc[u] = fmaf(d.y, w1, fmaf(d.x, w0, acc[u]));
-                    }
+    static_assert(O * I + 8 <= TR_WS_FLOATS, "staging buffer");
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    constexpr int MT = (ICNT + 15) / 16;
+    for (int mt = warp; mt < MT; mt += nw) {
+        const int ia = mt * 16 + g, ib = ia + 8;
+        const bool va = ia < ICNT, vb = ib < ICNT;
+        const float *wa = Ws + (va ? ia : 0), *wb = Ws + (vb ? ib : 0);
+        for (int r0 = 0; r0 < T; r0 += 8) {
+            const int row = r0 + g;
+            const bool rv = row < T;
+            const float *dy = dY + (rv ? row : 0) * lddy;
+            float c0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, c1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 2
+            for (int o0 = 0; o0 < O; o0 += 16) {
+                {
+                    const int oa = o0 + t, ob = oa + 4;
+                    const bool ka = oa < O, kb = ob < O;
+                    const FragA a = make_a(va && ka ? wa[oa * I] : 0.0f, vb && ka ? wb[oa * I] : 0.0f, va && kb ? wa[ob * I] : 0.0f,
+                                           vb && kb ? wb[ob * I] : 0.0f);
+                    mma3(c0, a, make_b(rv && ka ? dy[oa] : 0.0f, rv && kb ? dy[ob] : 0.0f));
+                }
+                if (o0 + 8 < O) {
+                    const int oa = o0 + 8 + t, ob = oa + 4;
+                    const bool ka = oa < O, kb = ob < O;
+                    const FragA a = make_a(va && ka ? wa[oa * I] : 0.0f, vb && ka ? wb[oa * I] : 0.0f, va && kb ? wa[ob * I] : 0.0f,
+                                           vb && kb ? wb[ob * I] : 0.0f);
+                    mma3(c1, a, make_b(rv && ka ? dy[oa] : 0.0f, rv && kb ? dy[ob] : 0.0f));
+                }
             }
-#pragma unroll
-            for (int u = 0; u < TR_RC; ++u) acc[u] = kg_sum(acc[u]);
-            const float v0 = kg == 0 ? acc[0] : kg == 1 ? acc[1] : kg == 2 ? acc[2] : acc[3];
-            const float v1 = kg == 0 ? acc[4] : acc[5];
-            if (live && kg < rows) epi(r0 + kg, i, v0);
-            if (live && kg + TR_KG < rows) epi(r0 + kg + TR_KG, i, v1);
+            const int ra = r0 + 2 * t, rb = ra + 1;
+            if (va && ra < T) epi(ra, ia, c0[0] + c1[0]);
+            if (va && rb < T) epi(rb, ia, c0[1] + c1[1]);
+            if (vb && ra < T) epi(ra, ib, c0[2] + c1[2]);
+            if (vb && rb < T) epi(rb, ib, c0[3] + c1[3]);
         }
     }
     psync();
 }
+
+constexpr int TR_RC = 6;        // rows per register chunk of the weight-gradient product (T = 6 at the trainer's shape)
 
 // gW[o][i] (+)= sum_r dY[r][o] X[r][i];  gb[o] (+)= sum_r dY[r][o]   (the CTA's own gradient slice: plain stores).
 // One thread per column i and group of rows o: X[.][i] stays in registers while the thread walks its o's.
@@ -857,6 +906,20 @@ cudaError_t launch_sample_batch(int N, int k, int row_floats, const float *state
                                                          out_index);
     return cudaGetLastError();
 }
+
+#ifdef AEM_TRAIN_TIMELINE
+extern "C" int aem_debug_train_timeline(long long *out_h, int max_n)
+{
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_tr_tl_n, sizeof(int));
+    if (n > max_n) n = max_n;
+    cudaMemcpyFromSymbol(out_h, g_tr_tl, sizeof(long long) * n);
+    int zero = 0;
+    cudaMemcpyToSymbol(g_tr_tl_n, &zero, sizeof(int));
+    return n;
+}
+#endif
 
 // ---- launchers ------------------------------------------------------------------------------------------------------
 size_t train_smem_bytes(int T, bool stash_in_smem)

@@ -173,9 +173,34 @@ def test_sample_batch_draws_a_uniform_subset_without_replacement(eng):
     assert sorted(full.tolist()) == list(range(64))
 
 
-@pytest.mark.parametrize("optimizer", ["SGD", "RMSprop"])
-def test_fused_sgd_and_rmsprop_walk_with_torch(optimizer):
-    """the other two optimizers of Trainer.set_learning_rate (trainer.py:24-34) through the fused step"""
+def test_sgd_and_rmsprop_steps_equal_torch(eng):
+    """aem_sgd_step / aem_rmsprop_step against torch.optim on the same gradient sequence (the other two optimizers of
+    Trainer.set_learning_rate, trainer.py:24-34)"""
+    dev = eng.device
+    g = torch.Generator(device=dev).manual_seed(2)
+    p0 = torch.randn(wts.NUM_WEIGHTS, device=dev, generator=g)
+    for kind in ("sgd", "rmsprop"):
+        ref = torch.nn.Parameter(p0.clone())
+        opt = torch.optim.SGD([ref], lr=1e-3, momentum=0.9) if kind == "sgd" else torch.optim.RMSprop([ref], lr=1e-3, alpha=0.9)
+        p, buf = p0.clone(), torch.zeros_like(p0)
+        for step in range(1, 6):
+            grad = torch.randn(wts.NUM_WEIGHTS, device=dev, generator=g) * 0.1
+            ref.grad = grad.clone()
+            opt.step()
+            if kind == "sgd":
+                eng.sgd_step(p, grad, buf, 1e-3, 0.9, step)
+            else:
+                eng.rmsprop_step(p, grad, buf, 1e-3, 0.9, 1e-8)
+            assert torch.allclose(p, ref.detach(), rtol=1e-6, atol=1e-6), (kind, step, float((p - ref.detach()).abs().max()))
+        state = opt.state[ref]["momentum_buffer" if kind == "sgd" else "square_avg"]
+        assert torch.allclose(buf, state, rtol=1e-5, atol=1e-7), kind
+
+
+def test_fused_sgd_walks_with_torch():
+    """Trainer(fused=True) with optim.SGD(momentum 0.9) against the eager step on the same five mini-batches.  (RMSprop divides by
+    sqrt(g^2) on its first step: rounding-level gradient differences become sign flips of +-lr, so only its update rule is
+    compared, above.)"""
+    optimizer = "SGD"
     from aemcarl_b200.crowd_nav.utils.trainer import Trainer
     from test_gpu_api import setup
     env, robot, policy = setup(seed=4, ponder_bias=-0.13)
@@ -194,3 +219,7 @@ def test_fused_sgd_and_rmsprop_walk_with_torch(optimizer):
     for (k, pa), pb in zip(model_a.named_parameters(), model_b.parameters()):
         assert torch.allclose(pa, pb, rtol=1e-3, atol=2e-5), (k, float((pa - pb).abs().max()))
     assert losses["fused"][0] != losses["fused"][-1]
+    # RMSprop runs through the same trainer path
+    tr = Trainer(copy.deepcopy(model_a).to(dev), None, dev, 100, fused=True)
+    tr.set_learning_rate(1e-3, "RMSprop")
+    assert all(np.isfinite(float(tr._step(x, v))) for x, v in batches)
