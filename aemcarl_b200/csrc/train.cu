@@ -264,22 +264,60 @@ constexpr int TR_RC = 6;        // rows per register chunk of the weight-gradien
 template <int O, int I>
 __device__ __forceinline__ void lin_bwd_w(float *gW, float *gb, const float *dY, int lddy, const float *X, int ldx, int T, bool acc)
 {
-    const int i = threadIdx.x % I, og = threadIdx.x / I, ng = blockDim.x / I;
+    // a thread owns TWO adjacent columns (i0, i0 + 1) and every ng-th output: each broadcast dY load feeds two FMAs (the phase
+    // is bound by shared-memory loads), four outputs are in flight (the per-output chain LDS -> FMAs -> STG is serial)
+    constexpr int IH = (I + 1) / 2;
+    const int ip = threadIdx.x % IH, og = threadIdx.x / IH, ng = blockDim.x / IH;
+    const int i0 = 2 * ip, i1 = i0 + 1;
+    const bool v1 = i1 < I;
     if (og < ng) {
         for (int r0 = 0; r0 < T; r0 += TR_RC) {
             const int rows = T - r0 < TR_RC ? T - r0 : TR_RC;
             const bool add = acc || r0 > 0;
-            float x[TR_RC];
+            float x0[TR_RC], x1[TR_RC];
 #pragma unroll
-            for (int u = 0; u < TR_RC; ++u) x[u] = u < rows ? X[(r0 + u) * ldx + i] : 0.0f;
+            for (int u = 0; u < TR_RC; ++u) {
+                x0[u] = u < rows ? X[(r0 + u) * ldx + i0] : 0.0f;
+                x1[u] = u < rows && v1 ? X[(r0 + u) * ldx + i1] : 0.0f;
+            }
             const float *dy = dY + r0 * lddy;
-            for (int o = og; o < O; o += ng) {
-                const float old = add ? gW[o * I + i] : 0.0f;
-                float s = 0.0f;
+            int o = og;
+            for (; o + 3 * ng < O; o += 4 * ng) {
+                float old0[4], old1[4], s0[4], s1[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    old0[j] = add ? gW[(o + j * ng) * I + i0] : 0.0f;
+                    old1[j] = add && v1 ? gW[(o + j * ng) * I + i1] : 0.0f;
+                    s0[j] = s1[j] = 0.0f;
+                }
 #pragma unroll
                 for (int u = 0; u < TR_RC; ++u)
-                    if (u < rows) s = fmaf(dy[u * lddy + o], x[u], s);
-                gW[o * I + i] = old + s;
+                    if (u < rows) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float d = dy[u * lddy + o + j * ng];
+                            s0[j] = fmaf(d, x0[u], s0[j]);
+                            s1[j] = fmaf(d, x1[u], s1[j]);
+                        }
+                    }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    gW[(o + j * ng) * I + i0] = old0[j] + s0[j];
+                    if (v1) gW[(o + j * ng) * I + i1] = old1[j] + s1[j];
+                }
+            }
+            for (; o < O; o += ng) {
+                const float old0 = add ? gW[o * I + i0] : 0.0f, old1 = add && v1 ? gW[o * I + i1] : 0.0f;
+                float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                for (int u = 0; u < TR_RC; ++u)
+                    if (u < rows) {
+                        const float d = dy[u * lddy + o];
+                        s0 = fmaf(d, x0[u], s0);
+                        s1 = fmaf(d, x1[u], s1);
+                    }
+                gW[o * I + i0] = old0 + s0;
+                if (v1) gW[o * I + i1] = old1 + s1;
             }
         }
     }
