@@ -223,3 +223,27 @@ def test_summary_lines_are_parsed_by_the_reference_plot_tool():
         assert (int(m["episode"]), float(m["sr"]), float(m["cr"]), float(m["time"])) == (1200, 0.83, 0.05, 11.25)
         assert float(m["reward"]) == -0.0312 or float(m["reward"]) == -0.0313
     assert summary_line("test", None, 1.0, 0.0, 10.5, 0.3).startswith("TEST  has success rate: 1.00, collision rate: 0.00")
+
+
+def test_fused_training_step_fails_loudly_without_cuda():
+    """Trainer(fused=True) is the CUDA kernel path (csrc/train.cu); on a CPU model it must raise, not fall back to autograd"""
+    import torch
+    from aemcarl_b200.crowd_nav.common.value_network import ValueNetworkTransformerAndGRU
+    from aemcarl_b200.crowd_nav.utils.trainer import Trainer
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    model = ValueNetworkTransformerAndGRU().eval()
+    tr = Trainer(model, None, torch.device("cpu"), 4, fused=True)
+    tr.set_learning_rate(1e-3, "Adam")
+    with pytest.raises(Exception) as e:
+        tr._step(torch.zeros((4, 5, 13)), torch.zeros((4, 1)))
+    assert "CUDA" in str(e.value) or "cuda" in str(e.value)
+    model.train()                                   # dropout-active training is outside the fused kernel's contract
+    with pytest.raises(NotImplementedError):
+        tr._step(torch.zeros((4, 5, 13)), torch.zeros((4, 1)))
+
+
+def test_device_scenario_params_struct_matches_header():
+    import ctypes
+    from aemcarl_b200._lib import ScenarioParams
+    assert ctypes.sizeof(ScenarioParams) == 7 * 8 + 8
