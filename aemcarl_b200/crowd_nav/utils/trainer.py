@@ -2,7 +2,11 @@
 RMSprop exactly as configured in the reference.  The one addition is the data-parallel hook: when
 torch.distributed is initialised, the flat gradient (113,752 live floats, one bucket) is all-reduced (NCCL over
 NVLink on GPUs, gloo in the CPU tests) and averaged between loss.backward() and optimizer.step() -- the only
-collective of the whole system."""
+collective of the whole system.  Three implementations of one optimisation step, same arithmetic contract:
+eager torch (the reference's code path), GraphedStep (the torch step replayed from CUDA graphs) and FusedStep (the hand-written
+kernels of csrc/train.cu on one flat parameter vector: aem_train_grad + all-reduce + aem_adam_step / aem_sgd_step /
+aem_rmsprop_step), selected by Trainer(cuda_graph=..., fused=...).  With a DeviceReplayMemory the mini-batches come from
+aem_sample_batch."""
 import logging
 
 import torch

@@ -12,9 +12,12 @@ Semantics kept from the reference:
   * RL target (explorer.py:132-139): value_i = r_i + gamma^(dt * v_pref) * V_target(state_{i+1}), last step value = r;
   * IL target (explorer.py:126-130): value_i = sum_{s >= i} gamma^((s - i) * dt * v_pref) * r_s;
   * the statistics and the log line of run_k_episodes (explorer.py:82-108).
-Differences (documented, unavoidable in a vectorised run): episodes finish out of case order, so the ORDER of the pairs
-in the ring differs (the multiset per episode is identical -- tests/test_gpu_explorer.py); epsilon-greedy draws come from
-a seeded torch.Generator on the device instead of the global numpy stream.
+Differences (documented, unavoidable in a vectorised run): the pairs of a wave are pushed in case order after the wave
+(the reference pushes episode by episode as they finish), so the ORDER of the pairs in the ring differs (the multiset per
+episode is identical -- tests/test_gpu_explorer.py); epsilon-greedy draws come from a seeded torch.Generator on the device
+instead of the global numpy stream; training scenario pools are drawn on the device (aem_generate_scenarios: the same seeded
+MT19937 stream, circle-rule coordinates within an ulp of numpy's cos / sin), val / test pools on the host (bit-exact).
+The loop itself never synchronises with the host except for one "anyone still playing?" flag every fourth step.
 """
 import logging
 
