@@ -156,13 +156,14 @@ class VecExplorer(object):
         eng.set_env_params(self.env_params)
         first = self.case_counter[phase] if first_case is None else int(first_case)
         B = min(self.B, int(k))
+        if pol.action_space is None:                 # before the env: its per-action buffers are sized by the action space
+            pol.build_action_space(float((self.scenario_kw or {}).get("robot_v_pref", 1.0)))
+            eng = pol.engine()
+            eng.set_env_params(self.env_params)
         on_device = self.device_scenarios if self.device_scenarios is not None else phase == "train"
         env = VecCrowdSim(eng, B, human_num=self.n, rule=self.rule, phase=phase, first_case=first, pool_size=int(k),
                           gamma=self.gamma, scenario_kw=self.scenario_kw,
                           device_scenarios=on_device and self.rule in ("circle_crossing", "square_crossing"))
-        if pol.action_space is None:
-            pol.build_action_space(float(env.pool_robot_h[0, 7]))
-            eng = pol.engine()
         dev = self.device
         dt = eng.params.time_step
         v_pref = float(env.pool_robot_h[0, 7])

@@ -182,3 +182,29 @@ def test_cuda_graph_training_step_equals_the_eager_step():
     for pa, pb in zip(model_a.parameters(), model_b.parameters()):
         assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6)
     assert losses["graph"][0] != losses["graph"][-1]
+
+
+def test_vectorised_explorer_phases_wave_sizes_and_rules():
+    """VecExplorer on a policy whose action space has not been built yet: val / test waves (host-drawn, bit-exact scenarios),
+    training waves smaller and larger than the batch, and the square rule with 10 humans (device-drawn scenarios); every
+    case ends in exactly one outcome and only training waves feed the memory."""
+    env, robot, policy = setup()
+    dev = torch.device("cuda:0")
+    policy.set_phase("train")
+    policy.set_epsilon(0.1)
+    mem = DeviceReplayMemory(100000, 5, dev)
+    vec = VecExplorer(policy, 64, env.env_params(), mem, policy.gamma, human_num=5)
+    vec.update_target_model(policy.get_model())
+    before = 0
+    for k, phase in ((100, "val"), (37, "test"), (5, "train"), (200, "train")):
+        st = vec.run_k_episodes(k, phase, update_memory=(phase == "train"), epsilon=0.1)
+        assert st["success"] + st["collision"] + st["timeout"] == k
+        assert st["env_steps"] >= k
+        assert (len(mem) > before) == (phase == "train")
+        assert len(mem) - before == st["pushed"]
+        before = len(mem)
+    mem10 = DeviceReplayMemory(10000, 10, dev)
+    vec10 = VecExplorer(policy, 32, env.env_params(), mem10, policy.gamma, human_num=10, rule="square_crossing")
+    vec10.update_target_model(policy.get_model())
+    st = vec10.run_k_episodes(48, "train", update_memory=True, epsilon=0.0)
+    assert st["success"] + st["collision"] + st["timeout"] == 48 and len(mem10) == st["pushed"] > 0
