@@ -24,5 +24,10 @@ for name, ckpt in (("imitation", "il_model.pth"), ("final", "rl_model.pth")):
     r = test.main(["--model_weights", os.path.join(out, ckpt), "--vectorised", "--cases", "500", "--precision", "fp16x3"])
     rows[name] = {"success": r["success"] / 500, "collision": r["collision"] / 500, "timeout": r["timeout"] / 500,
                   "seconds": time.time() - t0}
+# the trained weights through every arithmetic variant of the lookahead kernel: per-case outcomes of the 500 test cases
+codes = {}
+for prec in ("fp32", "tf32x3", "fp16x3"):
+    codes[prec] = test.main(["--model_weights", os.path.join(out, "rl_model.pth"), "--vectorised", "--cases", "500", "--precision", prec])["codes"]
+rows["outcomes_identical_across_precisions"] = {p: int((codes[p] != codes["fp32"]).sum()) for p in codes}
 print(json.dumps({"train_seconds": t_train, "il_episodes": a.il_episodes, "rl_episodes": a.train_episodes,
                   "optimizer_steps_rl": (a.train_episodes // a.vectorised) * a.updates_per_wave, "memory": res["memory"], "test": rows}))
