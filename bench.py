@@ -123,7 +123,7 @@ def run_reference(args, rank, world):
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
     actions = po.build_action_space()
-    W = wts.synthetic_weights(0)
+    W = wts.synthetic_weights(0) if not getattr(args, "weights", None) else np.load(args.weights).astype(np.float32)
     n = args.humans
     ns = args.ref_envs
     params = po.default_params()
@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3", "fp16x3q"],
                     help="value-network GEMM arithmetic: tcgen05 FP16x3 with two tiles per SM (default), tcgen05 3xTF32, "
                          "or the FP32 FFMA kernel")
+    ap.add_argument("--weights", default=None,
+                    help="flat float32 .npy (113,752 live parameters, blob order) instead of the random-init weights of the "
+                         "BASELINE workload, e.g. the trained policy tools/train_demo.py --save writes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -201,7 +204,7 @@ def main():
     actions = build_action_space(1.0)
     eng.set_action_space(actions)
     eng.set_env_params(make_env_params())
-    W = wts.synthetic_weights(0)
+    W = wts.synthetic_weights(0) if not getattr(args, "weights", None) else np.load(args.weights).astype(np.float32)
     eng.load_weights(W)
     eng.set_precision(args.precision)
     pool = args.pool or min(B, 8192)
@@ -339,8 +342,10 @@ def main():
                          "fp32": "f32"}[args.precision],
                "data": "synthetic",
                "config": {"workload": "batched lookahead inference: %d envs x %d humans x 81 actions per GPU, "
-                                      "random-init weights (synthetic_weights seed 0), %s train-stream "
-                                      "scenarios, predict + step" % (B, n, args.rule),
+                                      "%s, %s train-stream "
+                                      "scenarios, predict + step" % (B, n, "random-init weights (synthetic_weights seed 0)"
+                                                                     if not args.weights else "weights from " + args.weights,
+                                                                     args.rule),
                           "envs_per_gpu": B, "humans": n, "actions": 81, "l2": "flushed between timed iterations "
                           "(256 MB memset outside the event pairs)", "parallelism": "env-sharded x%d" % world},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

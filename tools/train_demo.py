@@ -11,6 +11,7 @@ ap.add_argument("--il_epochs", type=int, default=20)
 ap.add_argument("--train_episodes", type=int, default=16384)
 ap.add_argument("--vectorised", type=int, default=2048)
 ap.add_argument("--updates_per_wave", type=int, default=2000)
+ap.add_argument("--save", default=None, help="write the trained flat weights (.npy) here, e.g. for bench.py --weights")
 a = ap.parse_args()
 out = tempfile.mkdtemp()
 t0 = time.time()
@@ -18,6 +19,9 @@ res = train.main(["--output_dir", out, "--il_episodes", str(a.il_episodes), "--i
                   str(a.train_episodes), "--vectorised", str(a.vectorised), "--updates_per_wave", str(a.updates_per_wave), "--fused_step"])
 torch.cuda.synchronize()
 t_train = time.time() - t0
+if a.save:
+    import numpy as np
+    np.save(a.save, res["model"].flat_weights())
 rows = {}
 for name, ckpt in (("imitation", "il_model.pth"), ("final", "rl_model.pth")):
     t0 = time.time()
