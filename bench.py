@@ -52,12 +52,13 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.rows = []
+        self.first_timed_row = 0
         self.proc = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -68,6 +69,8 @@ class ClockSampler(threading.Thread):
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
+        if len(self.rows) > self.first_timed_row:      # rows of the timed region only
+            self.rows = self.rows[self.first_timed_row:]
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -237,11 +240,21 @@ def main():
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    if sampler:                                    # nvidia-smi needs ~0.1 s to start streaming: keep the GPU under the same
+        sampler.start()                            # load (untimed extra warm-up steps) until its first row arrives
+    for _ in range(60):
+        step()
+        torch.cuda.synchronize()
+        ready = torch.tensor([1 if (sampler is None or len(sampler.rows) > 0) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(ready, 0)
+        if int(ready.item()):
+            break
+    if sampler:
+        sampler.first_timed_row = len(sampler.rows)
     l0 = eng.launch_count()
     barrier()
     torch.cuda.synchronize()
-    if sampler:
-        sampler.start()
     for i in range(args.steps):
         flush.zero_()                              # L2 flush between timed iterations (outside the event pairs)
         step(evs[i])
