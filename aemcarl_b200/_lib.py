@@ -78,6 +78,9 @@ SYMBOLS = {
                                         _VP, _VP, _VP, _VP]),
     "aem_adam_step": (ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_double, ctypes.c_int, ctypes.c_double, _VP]),
+    "aem_train_step_adam": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP, ctypes.c_uint64, _VP, _VP, _VP, _VP,
+                                           _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _VP, _VP,
+                                           _VP, _VP, _VP, _VP]),
     "aem_sgd_step": (ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                     ctypes.c_double, _VP]),
     "aem_rmsprop_step": (ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double,

@@ -162,6 +162,54 @@ class FusedStep(object):
             else:
                 self.optimizer.state[p] = {"step": torch.tensor(float(self.step)), "square_avg": v}
 
+    def run_batches(self, memory, batch_size, num_batches, use_graph=False):
+        """num_batches iterations of optimize_batch (trainer.py:66-86) on a DeviceReplayMemory with Adam on ONE rank: every
+        per-step quantity (draw counter, step count, bias corrections, loss sum) lives on the device, so an iteration is
+        one C call (aem_train_step_adam: sample + forward / backward + update) -- or, with use_graph, one replay of the CUDA
+        graph that call was captured into (re-captured when the ring size or the learning rate changes)."""
+        g = self.optimizer.param_groups[0]
+        dev = self.flat.device
+        k = min(int(batch_size), len(memory))
+        n = memory.states.shape[1]
+        if getattr(self, "_dev_state", None) is None:
+            self._dev_state = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._adam_scal = torch.zeros(2, dtype=torch.float32, device=dev)
+            self._loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        if getattr(self, "_batch_states", None) is None or self._batch_states.shape != (k, n, 13):
+            self._batch_states = torch.empty((k, n, 13), dtype=torch.float32, device=dev)
+            self._batch_values = torch.empty((k,), dtype=torch.float32, device=dev)
+            self._graph_key = None
+        self._dev_state[1] = self.step                      # continue from steps taken through __call__ / torch
+        self._dev_state[0] = memory._samples_drawn + 1      # DeviceReplayMemory.sample() numbers its draws from 1
+        self._loss_sum.zero_()
+
+        def one():
+            self.engine.train_step_adam(memory.states, memory.values, len(memory), k, memory.sample_seed, self._dev_state,
+                                        self._adam_scal, self.flat, self.grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"],
+                                        g["eps"], self._batch_states, self._batch_values, self.loss, self._loss_sum, self.steps)
+
+        done = 0
+        if use_graph and num_batches > 2:
+            key = (len(memory), k, n, g["lr"], tuple(g["betas"]), g["eps"], memory.states.data_ptr(), memory.sample_seed)
+            if self._graph_key != key:
+                one()                                       # allocates the library's scratch outside the capture
+                done += 1
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    one()
+                done += 1                                   # the capture pass does not execute; replay it once to keep the count
+                self._graph.replay()
+                self._graph_key = key
+            for _ in range(num_batches - done):
+                self._graph.replay()
+        else:
+            for _ in range(num_batches):
+                one()
+        self.step += num_batches
+        memory._samples_drawn += num_batches
+        self.model.note_external_update()
+        return self._loss_sum[0] / num_batches
+
     def __call__(self, inputs, values):
         g = self.optimizer.param_groups[0]
         inputs = inputs.detach().to(torch.float32).contiguous()
@@ -262,6 +310,14 @@ class Trainer(object):
         if self.optimizer is None:
             raise ValueError("Learning rate is not set!")
         fast = self._device_memory()
+        if fast and self.fused and isinstance(self.optimizer, optim.Adam) and self.memory.device.type == "cuda" \
+                and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) \
+                and not self.model.training and not getattr(self.model, "act_fixed", False):
+            if self._fused is None:
+                self._fused = FusedStep(self.model, self.optimizer, self.memory.device)
+            average_loss = float(self._fused.run_batches(self.memory, self.batch_size, num_batches, use_graph=self.cuda_graph))
+            logging.debug("Average loss : %.2E", average_loss)
+            return average_loss
         if not fast and self.data_loader is None:
             self.data_loader = DataLoader(self.memory, self.batch_size, shuffle=True)
         losses = 0

@@ -181,7 +181,11 @@ cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double
 cudaError_t launch_scenarios(int rule, uint32_t first_seed, int count, int n, const aem_scenario_params &p, double *robot,
                              double *humans, cudaStream_t st);
 cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, const float *states, const float *targets,
-                              float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st);
+                              float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st, float *loss_sum = nullptr);
+cudaError_t launch_train_step_adam(aem_handle h, int N, int k, int n, const float *ring_states, const float *ring_values, uint64_t seed,
+                                   unsigned long long *dev_state, float *adam_scal, float *params, float *grad, float *m, float *v,
+                                   double lr, double b1, double b2, double eps, float *batch_states, float *batch_values, float *loss,
+                                   float *loss_sum, int32_t *steps, cudaStream_t st);
 cudaError_t launch_sgd(size_t count, float *p, const float *g, float *buf, double lr, double momentum, int step, double gscale,
                        cudaStream_t st);
 cudaError_t launch_rmsprop(size_t count, float *p, const float *g, float *sq, double lr, double alpha, double eps, double gscale,

@@ -862,6 +862,27 @@ int aem_adam_step(aem_handle h, size_t count, float *params_d, const float *grad
     return AEM_OK;
 }
 
+int aem_train_step_adam(aem_handle h, int N, int k, int n, const float *ring_states_d, const float *ring_values_d, uint64_t seed,
+                        unsigned long long *dev_state_d, float *adam_scal_d, float *params_d, float *grad_d, float *exp_avg_d,
+                        float *exp_avg_sq_d, double lr, double beta1, double beta2, double eps, float *batch_states_d,
+                        float *batch_values_d, float *loss_d, float *loss_sum_d, int32_t *steps_d, void *stream)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (N < 1 || k < 1 || k > N || k > 8192 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad N / k / n");
+    if (!ring_states_d || !ring_values_d || !dev_state_d || !adam_scal_d || !params_d || !grad_d || !exp_avg_d || !exp_avg_sq_d ||
+        !batch_states_d || !batch_values_d)
+        return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    if (((uintptr_t)params_d & 15) != 0) return aem_set_error(AEM_ERR_INVALID, "params_d must be 16-byte aligned (bulk copies)");
+    if (h->net.act_fixed) return aem_set_error(AEM_ERR_INVALID, "aem_train_step_adam implements the adaptive (act_fixed = 0) network");
+    if (!(beta1 >= 0 && beta1 < 1) || !(beta2 >= 0 && beta2 < 1)) return aem_set_error(AEM_ERR_INVALID, "bad betas");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_train_step_adam(h, N, k, n, ring_states_d, ring_values_d, seed, dev_state_d, adam_scal_d, params_d, grad_d,
+                                          exp_avg_d, exp_avg_sq_d, lr, beta1, beta2, eps, batch_states_d, batch_values_d, loss_d,
+                                          loss_sum_d, steps_d, as_stream(stream)));
+    h->launches += 5;
+    return AEM_OK;
+}
+
 int aem_sgd_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *momentum_buf_d, double lr,
                  double momentum, int step, double grad_scale, void *stream)
 {

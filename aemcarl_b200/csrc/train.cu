@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
 // grad[e] = sum_c part[c][e] in CTA order; block 0 also writes the loss and the step count
 __global__ void __launch_bounds__(256) train_reduce_kernel(const float *__restrict__ part, int G, float *__restrict__ grad,
                                                             const float *__restrict__ sqerr, int B, const int *flags,
-                                                            float *loss, int32_t *steps)
+                                                            float *loss, int32_t *steps, float *loss_sum)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < NUM_WEIGHTS) {
@@ -836,6 +836,7 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(const float *__restri
         for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
         if (threadIdx.x == 0) {
             if (loss) *loss = s / (float)B;
+            if (loss_sum) *loss_sum += s / (float)B;
             if (steps) *steps = flags[0] == 0 ? 1 : (flags[1] == 0 ? 2 : 3);
         }
     }
@@ -844,10 +845,14 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(const float *__restri
 // torch.optim.Adam (no weight decay, no amsgrad), single-tensor formulation of torch/optim/adam.py
 __global__ void __launch_bounds__(256) adam_kernel(size_t count, float *__restrict__ p, const float *__restrict__ g,
                                                     float *__restrict__ m, float *__restrict__ v, float step_size, float b1,
-                                                    float b2, float eps, float bc2_sqrt, float gscale)
+                                                    float b2, float eps, float bc2_sqrt, float gscale, const float *__restrict__ scal)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count) return;
+    if (scal) {                                      // step size and bias correction from the device-resident step count
+        step_size = scal[0];
+        bc2_sqrt = scal[1];
+    }
     const float gr = g[e] * gscale;
     const float mm = m[e] + (gr - m[e]) * (1.0f - b1);          // exp_avg.lerp_(grad, 1 - beta1)
     const float vv = v[e] * b2 + (1.0f - b2) * gr * gr;         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
@@ -909,9 +914,22 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t &x)
 __global__ void __launch_bounds__(256) sample_batch_kernel(int N, int k, int row_floats, const float *__restrict__ states,
                                                             const float *__restrict__ values, uint64_t seed, uint64_t counter,
                                                             float *__restrict__ out_states, float *__restrict__ out_values,
-                                                            int64_t *__restrict__ out_index)
+                                                            int64_t *__restrict__ out_index, unsigned long long *dev_state,
+                                                            float *adam_scal, double lr, double b1, double b2)
 {
+    // dev_state (optional, the graph-replayable step): [0] = draw counter, [1] = optimizer step count, both advanced here;
+    // adam_scal[0] = lr / (1 - b1^t), adam_scal[1] = sqrt(1 - b2^t) for the adam_kernel that follows in the stream
     extern __shared__ int picked[];                 // [k]
+    if (dev_state) counter = dev_state[0];
+    __syncthreads();
+    if (dev_state && threadIdx.x == 32) {
+        dev_state[0] = counter + 1;
+        const unsigned long long t = ++dev_state[1];
+        if (adam_scal) {
+            adam_scal[0] = (float)(lr / (1.0 - pow(b1, (double)t)));
+            adam_scal[1] = (float)sqrt(1.0 - pow(b2, (double)t));
+        }
+    }
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         uint64_t st = seed ^ (counter * 0xd1342543de82ef95ull + 0x2545f4914f6cdd1dull);
@@ -941,7 +959,7 @@ cudaError_t launch_sample_batch(int N, int k, int row_floats, const float *state
                                 uint64_t counter, float *out_states, float *out_values, int64_t *out_index, cudaStream_t st)
 {
     sample_batch_kernel<<<1, 256, k * sizeof(int), st>>>(N, k, row_floats, states, values, seed, counter, out_states, out_values,
-                                                         out_index);
+                                                         out_index, nullptr, nullptr, 0.0, 0.0, 0.0);
     return cudaGetLastError();
 }
 
@@ -974,7 +992,7 @@ size_t probe_smem_bytes(int T, bool handoff)
 }
 
 cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, const float *states, const float *targets,
-                              float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st)
+                              float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st, float *loss_sum)
 {
     const int T = n + 1;
     const TrLayout L = tr_layout(T);
@@ -1011,7 +1029,7 @@ cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, c
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return e;
     train_probe_kernel<<<grid, TR_THREADS, psm, st>>>(a);
     kern<<<grid, TR_THREADS, fsm, st>>>(a);
-    train_reduce_kernel<<<(NUM_WEIGHTS + 255) / 256, 256, 0, st>>>(h->tr_part, grid, grad, h->tr_sqerr, B, h->tr_flags, loss, steps);
+    train_reduce_kernel<<<(NUM_WEIGHTS + 255) / 256, 256, 0, st>>>(h->tr_part, grid, grad, h->tr_sqerr, B, h->tr_flags, loss, steps, loss_sum);
     return cudaGetLastError();
 }
 
@@ -1021,7 +1039,26 @@ cudaError_t launch_adam(size_t count, float *p, const float *g, float *m, float 
     const double bc1 = 1.0 - pow(b1, (double)step);             // torch computes these in Python floats
     const double bc2_sqrt = sqrt(1.0 - pow(b2, (double)step));
     adam_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(count, p, g, m, v, (float)(lr / bc1), (float)b1, (float)b2,
-                                                                 (float)eps, (float)bc2_sqrt, (float)gscale);
+                                                                 (float)eps, (float)bc2_sqrt, (float)gscale, nullptr);
+    return cudaGetLastError();
+}
+
+// One optimisation step whose every per-step quantity lives on the device (draw counter, optimizer step count, bias corrections,
+// loss accumulator): sample -> probe -> forward / backward -> reduce -> Adam, five launches and one memset with constant
+// arguments, so the sequence can be captured once in a CUDA graph and replayed (Trainer.optimize_batch).
+cudaError_t launch_train_step_adam(aem_handle h, int N, int k, int n, const float *ring_states, const float *ring_values, uint64_t seed,
+                                   unsigned long long *dev_state, float *adam_scal, float *params, float *grad, float *m, float *v,
+                                   double lr, double b1, double b2, double eps, float *batch_states, float *batch_values, float *loss,
+                                   float *loss_sum, int32_t *steps, cudaStream_t st)
+{
+    sample_batch_kernel<<<1, 256, k * sizeof(int), st>>>(N, k, n * 13, ring_states, ring_values, seed, 0ull, batch_states, batch_values,
+                                                         nullptr, dev_state, adam_scal, lr, b1, b2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if ((e = launch_train_grad(h, k, n, params, batch_states, batch_values, grad, loss, nullptr, steps, st, loss_sum)) != cudaSuccess)
+        return e;
+    adam_kernel<<<(NUM_WEIGHTS + 255) / 256, 256, 0, st>>>((size_t)NUM_WEIGHTS, params, grad, m, v, 0.0f, (float)b1, (float)b2, (float)eps,
+                                                          1.0f, 1.0f, adam_scal);
     return cudaGetLastError();
 }
 

@@ -237,6 +237,16 @@ class Engine:
                                      float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), float(grad_scale),
                                      self._stream()))
 
+    def train_step_adam(self, ring_states, ring_values, size, k, seed, dev_state, adam_scal, params, grad, exp_avg, exp_avg_sq,
+                        lr, betas, eps, batch_states, batch_values, loss, loss_sum, steps):
+        """one iteration of Trainer.optimize_batch with Adam, all per-step state on the device (graph-capturable)"""
+        cap, n, _ = ring_states.shape
+        check(self.lib.aem_train_step_adam(self.h, int(size), int(k), n, _ptr(ring_states), _ptr(ring_values),
+                                           ctypes.c_uint64(seed & (2 ** 64 - 1)), _ptr(dev_state), _ptr(adam_scal), _ptr(params),
+                                           _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), float(lr), float(betas[0]), float(betas[1]),
+                                           float(eps), _ptr(batch_states), _ptr(batch_values), _ptr(loss), _ptr(loss_sum), _ptr(steps),
+                                           self._stream()))
+
     def sgd_step(self, params, grad, momentum_buf, lr, momentum, step, grad_scale=1.0):
         """torch.optim.SGD(momentum).step() on flat float32 vectors; step is 1-based (the first call initialises the buffer)"""
         check(self.lib.aem_sgd_step(self.h, params.numel(), _ptr(params), _ptr(grad), _ptr(momentum_buf), float(lr), float(momentum),

@@ -20,6 +20,7 @@
  *   aem_transform       <- MultiHumanRL.transform multi_human_rl.py:423-438 (replay-memory sample of the current state)
  *   aem_generate_scenarios <- CrowdSim.reset's seeded scenario draw, crowd_sim.py:486-552,390-442
  *   aem_train_grad      <- Trainer.optimize_batch / optimize_epoch forward + MSE + backward (crowd_nav/utils/trainer.py:47-58,70-82)
+ *   aem_train_step_adam <- one iteration of Trainer.optimize_batch with Adam (sample + forward/backward + update), trainer.py:66-86
  *   aem_sample_batch    <- next(iter(DataLoader(memory, batch_size, shuffle=True))), trainer.py:70-72 + memory.py
  *   aem_adam_step / aem_sgd_step / aem_rmsprop_step <- optimizer.step() of the three optimizers of trainer.py:24-34
  *   aem_decide_step_host<- Robot.act + CrowdSim.step through HOST buffers (explorer.py:51-53), the e2e call
@@ -198,6 +199,16 @@ int aem_sample_batch(aem_handle h, int N, int k, int n, const float *states_d, c
  * after a summing all-reduce). */
 int aem_adam_step(aem_handle h, size_t count, float *params_d, const float *grad_d, float *exp_avg_d, float *exp_avg_sq_d,
                   double lr, double beta1, double beta2, double eps, int step, double grad_scale, void *stream);
+
+/* One iteration of Trainer.optimize_batch (trainer.py:66-86) with Adam, every per-step quantity resident on the device: draw a
+ * mini-batch of k pairs from the replay ring (first N entries), aem_train_grad on it, Adam update.  dev_state_d: u64[2] =
+ * {draws so far, optimizer steps so far}, both advanced by the call; adam_scal_d: f32[2] scratch (step size, bias correction);
+ * loss_sum_d (may be NULL) accumulates the losses.  All arguments are constant from step to step, so the five launches can be
+ * captured once in a CUDA graph and replayed.  batch_states_d [k][n][13] / batch_values_d [k]: the drawn batch (scratch). */
+int aem_train_step_adam(aem_handle h, int N, int k, int n, const float *ring_states_d, const float *ring_values_d, uint64_t seed,
+                        unsigned long long *dev_state_d, float *adam_scal_d, float *params_d, float *grad_d, float *exp_avg_d,
+                        float *exp_avg_sq_d, double lr, double beta1, double beta2, double eps, float *batch_states_d,
+                        float *batch_values_d, float *loss_d, float *loss_sum_d, int32_t *steps_d, void *stream);
 
 /* The other two optimizers Trainer.set_learning_rate offers (trainer.py:24-34): optim.SGD(momentum = 0.9) -- momentum_buf_d is
  * initialised by the step == 1 call -- and optim.RMSprop(alpha = 0.9, eps = 1e-8; not centered, no momentum). */

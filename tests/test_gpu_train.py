@@ -223,3 +223,40 @@ def test_fused_sgd_walks_with_torch():
     tr = Trainer(copy.deepcopy(model_a).to(dev), None, dev, 100, fused=True)
     tr.set_learning_rate(1e-3, "RMSprop")
     assert all(np.isfinite(float(tr._step(x, v))) for x, v in batches)
+
+
+def test_optimize_batch_single_call_and_graph_replay():
+    """Trainer.optimize_batch on a DeviceReplayMemory with the fused Adam step: (a) one C call per iteration with the step state
+    on the device (aem_train_step_adam) walks like sample() + step; (b) replaying the CUDA graph of that call gives bit-identical
+    parameters; (c) a changed ring size re-captures."""
+    from aemcarl_b200.crowd_nav.utils.trainer import Trainer
+    from aemcarl_b200.crowd_nav.utils.vec_explorer import DeviceReplayMemory
+    from test_gpu_api import setup
+    env, robot, policy = setup(seed=4, ponder_bias=-0.13)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(9)
+    states = torch.randn((5000, 5, 13), device=dev, generator=g)
+    values = torch.randn((5000, 1), device=dev, generator=g)
+    flats = {}
+    for name, graph, single in (("stepwise", False, False), ("single_call", False, True), ("graph", True, True)):
+        mem = DeviceReplayMemory(8000, 5, dev)
+        mem.push_batch(states[:4000], values[:4000])
+        model = copy.deepcopy(policy.get_model()).to(dev)
+        tr = Trainer(model, mem, dev, 100, fused=True, cuda_graph=graph)
+        tr.set_learning_rate(1e-3, "Adam")
+        if single:
+            l1 = tr.optimize_batch(12)
+            mem.push_batch(states[4000:], values[4000:])            # the ring grows: the graph is re-captured
+            l2 = tr.optimize_batch(8)
+        else:
+            losses = [float(tr._step(*mem.sample(100))) for _ in range(12)]
+            l1 = float(np.mean(losses))
+            mem.push_batch(states[4000:], values[4000:])
+            l2 = float(np.mean([float(tr._step(*mem.sample(100))) for _ in range(8)]))
+        assert np.isfinite(l1) and np.isfinite(l2)
+        assert tr._fused.step == 20 and mem._samples_drawn == 20
+        flats[name] = (tr._fused.flat.clone(), l1, l2)
+    assert torch.equal(flats["single_call"][0], flats["graph"][0])
+    assert flats["single_call"][1:] == flats["graph"][1:]
+    assert torch.allclose(flats["stepwise"][0], flats["single_call"][0], rtol=1e-5, atol=1e-6)
+    assert flats["stepwise"][1] == pytest.approx(flats["single_call"][1], rel=1e-5)

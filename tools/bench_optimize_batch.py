@@ -1,4 +1,5 @@
-"""Trainer.optimize_batch on the on-device replay memory (100,000 pairs, batch 100): mini-batch sampling + the optimisation step.
+"""Trainer.optimize_batch on the on-device replay memory (100,000 pairs, batch 100): mini-batch sampling + the optimisation step:
+the CUDA-graph replay of the torch step, the hand-written kernels (one C call per iteration), and the CUDA-graph replay of that call.
 usage: python tools/bench_optimize_batch.py [--steps 2000]"""
 import argparse, copy, json, sys, time
 import torch
@@ -12,7 +13,7 @@ dev = torch.device("cuda:0")
 mem = DeviceReplayMemory(100000, 5, dev)
 mem.push_batch(torch.randn((100000, 5, 13), device=dev), torch.randn((100000, 1), device=dev))
 res = {}
-for name, graph, fused in (("cuda_graph", True, False), ("fused_kernels", False, True)):
+for name, graph, fused in (("cuda_graph", True, False), ("fused_kernels", False, True), ("fused_kernels_graph", True, True)):
     model = copy.deepcopy(policy.get_model()).to(dev)
     tr = Trainer(model, mem, dev, 100, cuda_graph=graph, fused=fused)
     tr.set_learning_rate(1e-3, "Adam")
