@@ -4,7 +4,7 @@ sys.path.insert(0, ".")
 from aemcarl_b200.crowd_nav import train, test
 out = tempfile.mkdtemp()
 res = train.main(["--output_dir", out, "--il_episodes", "32", "--il_epochs", "2", "--train_episodes", "128", "--vectorised", "64",
-                  "--updates_per_wave", "20", "--fused_step"])
+                  "--updates_per_wave", "20", "--fused_step", "--cuda_graph"])
 ckpt = os.path.join(out, "rl_model.pth")
 a = test.main(["--model_weights", ckpt, "--cases", "3"])
 b = test.main(["--model_weights", ckpt, "--vectorised", "--cases", "100", "--precision", "fp16x3"])
