@@ -128,6 +128,9 @@ class VecExplorer(object):
         # scenario pools: None = drawn on the device for the training phase (aem_generate_scenarios; 4096 cases cost ~1 s in
         # the host generator), on the host (bit-exact with the reference) for val / test; True / False force one of them
         self.device_scenarios = device_scenarios
+        # when the cases of a wave have run out, the kernels keep running on the environments still playing only, re-packed to
+        # the front whenever fewer than this fraction of the current batch is left (None: never re-pack)
+        self.compact_below = 0.75
 
     def update_target_model(self, target_model):
         import copy
@@ -204,8 +207,8 @@ class VecExplorer(object):
             else:
                 best = env.lookahead()
                 if eps > 0.0:
-                    explore = torch.rand((B,), device=dev, generator=self.gen) < eps
-                    rnd = torch.randint(0, eng.A, (B,), device=dev, generator=self.gen, dtype=torch.int32)
+                    explore = torch.rand((env.B,), device=dev, generator=self.gen) < eps
+                    rnd = torch.randint(0, eng.A, (env.B,), device=dev, generator=self.gen, dtype=torch.int32)
                     # the goal short-circuit (action 0 inside the goal disc) precedes the epsilon draw (multi_human_rl.py:321)
                     at_goal = torch.linalg.norm(env.robot[:, 0:2] - env.robot[:, 5:7], dim=1) < env.robot[:, 4]
                     best = torch.where(explore & ~at_goal, rnd, best)
@@ -234,8 +237,20 @@ class VecExplorer(object):
             env.global_time.copy_(torch.where(has, zero_t, env.global_time))
             step_idx = torch.where(fin, torch.zeros_like(step_idx), step_idx)
             it += 1
-            if it % check_every == 0 and not bool(active.any()):            # the only host synchronisation of the loop
-                break
+            if it % check_every == 0:                       # the only host synchronisation of the loop
+                n_act = int(active.sum().item())
+                if n_act == 0:
+                    break
+                if self.compact_below and n_act <= self.compact_below * env.B and env.B > 64:
+                    # The cases have run out and part of the batch has finished for good (an environment only goes inactive
+                    # when no case is left, so nothing is assigned any more): move the environments still playing to the front
+                    # and let the kernels run on them alone.
+                    keep = torch.nonzero(active).reshape(-1)
+                    for t in (env.robot, env.humans, env.global_time):
+                        t[:n_act] = t[keep]
+                    step_idx, case_of_env, dummy = step_idx[keep], case_of_env[keep], dummy[:n_act]
+                    active = torch.ones((n_act,), dtype=torch.bool, device=dev)
+                    env = env.narrow(n_act)
 
         # ---- one pass over the finished wave: statistics and the replay-memory pairs ----
         lens = ep_len[:k]

@@ -104,5 +104,17 @@ class VecCrowdSim:
         self.lookahead()
         return self.apply(auto_reset=auto_reset)
 
+    def narrow(self, n):
+        """a view of the first n environments (all per-environment buffers sliced, the scenario pool shared): the kernels of a
+        batch whose tail has finished run on the environments that are still playing only"""
+        import copy
+        v = copy.copy(self)
+        v.B = int(n)
+        for name in ("robot", "humans", "global_time", "case_idx", "new_vel", "rewards", "info", "dmin", "humans_next", "values",
+                     "net_values", "act_steps", "best"):
+            setattr(v, name, getattr(self, name)[:n])
+        v.last = None
+        return v
+
     def state_numpy(self):
         return (self.robot.cpu().numpy(), self.humans.cpu().numpy(), self.global_time.cpu().numpy())

@@ -208,3 +208,28 @@ def test_vectorised_explorer_phases_wave_sizes_and_rules():
     vec10.update_target_model(policy.get_model())
     st = vec10.run_k_episodes(48, "train", update_memory=True, epsilon=0.0)
     assert st["success"] + st["collision"] + st["timeout"] == 48 and len(mem10) == st["pushed"] > 0
+
+
+def test_repacking_the_running_environments_changes_nothing():
+    """When a wave's cases have run out, VecExplorer re-packs the environments that are still playing to the front of the
+    batch and runs the kernels on them alone.  With epsilon = 0 the wave must be the same with and without it: outcomes,
+    navigation times, returns and the pushed (state, value) pairs."""
+    env, robot, policy = setup()
+    dev = torch.device("cuda:0")
+    policy.set_phase("train")
+    policy.set_epsilon(0.0)
+    out = {}
+    for name, frac in (("packed", 0.75), ("plain", None)):
+        mem = DeviceReplayMemory(100000, 5, dev)
+        vec = VecExplorer(policy, 256, env.env_params(), mem, policy.gamma, human_num=5)
+        vec.compact_below = frac
+        vec.update_target_model(policy.get_model())
+        st = vec.run_k_episodes(256, "train", update_memory=True, epsilon=0.0, first_case=500)
+        out[name] = (st, mem.states[:len(mem)].cpu().numpy(), mem.values[:len(mem)].cpu().numpy())
+    a, b = out["packed"], out["plain"]
+    assert np.array_equal(a[0]["codes"], b[0]["codes"])
+    for key in ("success", "collision", "timeout", "too_close", "env_steps", "pushed", "avg_nav_time"):
+        assert a[0][key] == b[0][key], key
+    assert np.array_equal(np.asarray(a[0]["cumulative_rewards"]), np.asarray(b[0]["cumulative_rewards"]))
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[0]["timeout"] > 0 and a[0]["success"] + a[0]["collision"] > 0      # the wave really had a long tail
