@@ -196,6 +196,7 @@ class VecExplorer(object):
         zero_t = torch.zeros((), dtype=torch.float64, device=dev)
         disc = torch.pow(torch.tensor(gbar, dtype=torch.float64, device=dev),
                          torch.arange(tmax, device=dev, dtype=torch.float64))
+        slot = torch.arange(B, device=dev)                  # original environment index of every running environment
         check_every = 4
         it = 0
 
@@ -207,8 +208,9 @@ class VecExplorer(object):
             else:
                 best = env.lookahead()
                 if eps > 0.0:
-                    explore = torch.rand((env.B,), device=dev, generator=self.gen) < eps
-                    rnd = torch.randint(0, eng.A, (env.B,), device=dev, generator=self.gen, dtype=torch.int32)
+                    # drawn for the ORIGINAL batch and indexed by slot, so re-packing does not change any decision
+                    explore = torch.rand((B,), device=dev, generator=self.gen)[slot] < eps
+                    rnd = torch.randint(0, eng.A, (B,), device=dev, generator=self.gen, dtype=torch.int32)[slot]
                     # the goal short-circuit (action 0 inside the goal disc) precedes the epsilon draw (multi_human_rl.py:321)
                     at_goal = torch.linalg.norm(env.robot[:, 0:2] - env.robot[:, 5:7], dim=1) < env.robot[:, 4]
                     best = torch.where(explore & ~at_goal, rnd, best)
@@ -248,7 +250,7 @@ class VecExplorer(object):
                     keep = torch.nonzero(active).reshape(-1)
                     for t in (env.robot, env.humans, env.global_time):
                         t[:n_act] = t[keep]
-                    step_idx, case_of_env, dummy = step_idx[keep], case_of_env[keep], dummy[:n_act]
+                    step_idx, case_of_env, dummy, slot = step_idx[keep], case_of_env[keep], dummy[:n_act], slot[keep]
                     active = torch.ones((n_act,), dtype=torch.bool, device=dev)
                     env = env.narrow(n_act)
 

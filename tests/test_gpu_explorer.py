@@ -212,19 +212,19 @@ def test_vectorised_explorer_phases_wave_sizes_and_rules():
 
 def test_repacking_the_running_environments_changes_nothing():
     """When a wave's cases have run out, VecExplorer re-packs the environments that are still playing to the front of the
-    batch and runs the kernels on them alone.  With epsilon = 0 the wave must be the same with and without it: outcomes,
-    navigation times, returns and the pushed (state, value) pairs."""
+    batch and runs the kernels on them alone.  The wave must be the same with and without it -- also with epsilon-greedy
+    exploration (the draws are made per original slot): outcomes, navigation times, returns and the pushed (state, value) pairs."""
     env, robot, policy = setup()
     dev = torch.device("cuda:0")
     policy.set_phase("train")
-    policy.set_epsilon(0.0)
+    policy.set_epsilon(0.2)
     out = {}
     for name, frac in (("packed", 0.75), ("plain", None)):
         mem = DeviceReplayMemory(100000, 5, dev)
-        vec = VecExplorer(policy, 256, env.env_params(), mem, policy.gamma, human_num=5)
+        vec = VecExplorer(policy, 256, env.env_params(), mem, policy.gamma, human_num=5, seed=3)
         vec.compact_below = frac
         vec.update_target_model(policy.get_model())
-        st = vec.run_k_episodes(256, "train", update_memory=True, epsilon=0.0, first_case=500)
+        st = vec.run_k_episodes(256, "train", update_memory=True, epsilon=0.2, first_case=500)
         out[name] = (st, mem.states[:len(mem)].cpu().numpy(), mem.values[:len(mem)].cpu().numpy())
     a, b = out["packed"], out["plain"]
     assert np.array_equal(a[0]["codes"], b[0]["codes"])
