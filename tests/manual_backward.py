@@ -72,8 +72,12 @@ def batch_steps(flat, states, K_max=3, eps=0.05):
     return K
 
 
-def sample_forward_backward(flat, state, target, K, batch):
-    """one sample: value, and d(mean squared error over `batch` samples)/d(parameters) as a flat float64 vector"""
+def sample_forward_backward(flat, state, target, K, batch, masks=None):
+    """one sample: value, and d(mean squared error over `batch` samples)/d(parameters) as a flat float64 vector.
+    masks (optional): per encoder layer a dict of the four inverted-dropout masks of nn.TransformerEncoderLayer, already scaled
+    by 1 / (1 - p): "attn" [2, T, T] on the softmax output, "ao" [T, 50] on the attention branch before the residual, "f1"
+    [T, 150] after the FFN's ReLU, "f2" [T, 50] on the FFN branch before the residual (the derivation a dropout-active fused
+    training step would follow)."""
     W = {k: v.astype(np.float64) for k, v in wts.unflatten(flat).items()}
     G = {k: np.zeros_like(v) for k, v in W.items()}
     state = state.astype(np.float64)
@@ -103,13 +107,17 @@ def sample_forward_backward(flat, state, target, K, batch):
             s = s - s.max(axis=1, keepdims=True)
             e = np.exp(s)
             P[hd] = e / e.sum(axis=1, keepdims=True)
-            ctx[:, sl] = P[hd] @ v[:, sl]
-        ao = ctx @ W[p + "self_attn.out_proj.weight"].T + W[p + "self_attn.out_proj.bias"]
+        mk = masks[l] if masks is not None else dict(attn=1.0, ao=1.0, f1=1.0, f2=1.0)
+        Pd = P * mk["attn"]                                  # dropout on the attention weights
+        for hd in range(2):
+            sl = slice(25 * hd, 25 * hd + 25)
+            ctx[:, sl] = Pd[hd] @ v[:, sl]
+        ao = (ctx @ W[p + "self_attn.out_proj.weight"].T + W[p + "self_attn.out_proj.bias"]) * mk["ao"]
         y1, xh1, rs1 = _ln_fwd(X + ao, W[p + "norm1.weight"], W[p + "norm1.bias"])
-        f1 = np.maximum(y1 @ W[p + "linear1.weight"].T + W[p + "linear1.bias"], 0)
-        f2 = f1 @ W[p + "linear2.weight"].T + W[p + "linear2.bias"]
+        f1 = np.maximum(y1 @ W[p + "linear1.weight"].T + W[p + "linear1.bias"], 0) * mk["f1"]
+        f2 = (f1 @ W[p + "linear2.weight"].T + W[p + "linear2.bias"]) * mk["f2"]
         y2, xh2, rs2 = _ln_fwd(y1 + f2, W[p + "norm2.weight"], W[p + "norm2.bias"])
-        layers.append(dict(X=X, q=q, k=k, v=v, P=P, ctx=ctx, y1=y1, xh1=xh1, rs1=rs1, f1=f1, xh2=xh2, rs2=rs2))
+        layers.append(dict(X=X, q=q, k=k, v=v, P=P, Pd=Pd, ctx=ctx, y1=y1, xh1=xh1, rs1=rs1, f1=f1, xh2=xh2, rs2=rs2, mk=mk))
         X = y2
     ain = np.concatenate([state[0, :6], X[0]])
     a1 = np.maximum(W["action_mlp.0.weight"] @ ain + W["action_mlp.0.bias"], 0)
@@ -133,24 +141,28 @@ def sample_forward_backward(flat, state, target, K, batch):
         ds2, dg, db = _ln_bwd(dX, c["xh2"], c["rs2"], W[p + "norm2.weight"])
         G[p + "norm2.weight"] += dg
         G[p + "norm2.bias"] += db
-        G[p + "linear2.weight"] += ds2.T @ c["f1"]
-        G[p + "linear2.bias"] += ds2.sum(0)
-        df1 = (ds2 @ W[p + "linear2.weight"]) * (c["f1"] > 0)
+        mk = c["mk"]
+        df2 = ds2 * mk["f2"]
+        G[p + "linear2.weight"] += df2.T @ c["f1"]
+        G[p + "linear2.bias"] += df2.sum(0)
+        df1 = (df2 @ W[p + "linear2.weight"]) * mk["f1"] * (c["f1"] != 0)      # f1 already carries mask and ReLU
         G[p + "linear1.weight"] += df1.T @ c["y1"]
         G[p + "linear1.bias"] += df1.sum(0)
         dy1 = ds2 + df1 @ W[p + "linear1.weight"]
         ds1, dg, db = _ln_bwd(dy1, c["xh1"], c["rs1"], W[p + "norm1.weight"])
         G[p + "norm1.weight"] += dg
         G[p + "norm1.bias"] += db
-        G[p + "self_attn.out_proj.weight"] += ds1.T @ c["ctx"]
-        G[p + "self_attn.out_proj.bias"] += ds1.sum(0)
-        dctx = ds1 @ W[p + "self_attn.out_proj.weight"]
+        dao = ds1 * mk["ao"]
+        G[p + "self_attn.out_proj.weight"] += dao.T @ c["ctx"]
+        G[p + "self_attn.out_proj.bias"] += dao.sum(0)
+        dctx = dao @ W[p + "self_attn.out_proj.weight"]
         dqkv = np.zeros((T, 150))
         for hd in range(2):
             sl = slice(25 * hd, 25 * hd + 25)
             Ph = c["P"][hd]
-            dP = dctx[:, sl] @ c["v"][:, sl].T
-            dqkv[:, 100 + 25 * hd:125 + 25 * hd] = Ph.T @ dctx[:, sl]
+            ma = mk["attn"][hd] if np.ndim(mk["attn"]) else mk["attn"]
+            dP = (dctx[:, sl] @ c["v"][:, sl].T) * ma
+            dqkv[:, 100 + 25 * hd:125 + 25 * hd] = c["Pd"][hd].T @ dctx[:, sl]
             dS = Ph * (dP - (Ph * dP).sum(axis=1, keepdims=True))
             dqkv[:, sl] = dS @ c["k"][:, sl] / 5.0
             dqkv[:, 50 + 25 * hd:75 + 25 * hd] = dS.T @ c["q"][:, sl] / 5.0
