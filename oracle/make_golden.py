@@ -183,6 +183,56 @@ def gen_values_other_weights(base, tag):
     np.savez_compressed(os.path.join(OUT, "values_%s.npz" % tag), **out)
 
 
+def gen_update_memory():
+    """Explorer.update_memory (crowd_nav/utils/explorer.py:114-151) of the UNMODIFIED reference on one recorded episode: the
+    imitation-learning targets (discounted Monte-Carlo return, :126-130) and the RL targets (r + gamma_bar V_target(s'),
+    :132-139), with the (rotated state, value) pairs the reference pushes into its ReplayMemory."""
+    import torch
+    _, seed, pb = WEIGHT_SETS[0]
+    policy = ref_shim.make_policy(seed=0)               # installs the shim: the reference packages import from here on
+    from crowd_nav.utils.explorer import Explorer
+    from crowd_nav.utils.memory import ReplayMemory
+    from crowd_sim.envs.utils.state import JointState
+    load_weights(policy, wts.synthetic_weights(seed, pb))
+    env, robot, _ = ref_shim.make_env(human_num=5)
+    robot.set_policy(policy)
+    policy.set_env(env)
+    ob = env.reset("test", 3)
+    if policy.action_space is None:
+        policy.build_action_space(robot.v_pref)
+    joint, rewards = [], []
+    for step in range(14):
+        state = JointState(robot.get_full_state(), ob)
+        joint.append(state)
+        action = robot.act(ob)
+        ob, reward, done, info = env.step(action)
+        rewards.append(float(reward))
+        if done:
+            break
+    # the environment's rewards of a quiet episode are all zero: the targets are checked on a synthetic reward sequence
+    rewards = [float(np.round(0.1 * np.sin(1.7 * i), 3)) for i in range(len(joint))]
+    rewards[-1] = 1.0
+    rb = np.array([[s.self_state.px, s.self_state.py, s.self_state.vx, s.self_state.vy, s.self_state.radius, s.self_state.gx,
+                    s.self_state.gy, s.self_state.v_pref, s.self_state.theta] for s in joint])
+    hs = np.array([[[h.px, h.py, h.vx, h.vy, h.radius] for h in s.human_states] for s in joint])
+    out = dict(robot=rb, humans_obs=hs, rewards=np.array(rewards), weight_seed=np.array(seed), gamma=np.array(policy.gamma),
+               time_step=np.array(robot.time_step), v_pref=np.array(robot.v_pref))
+    for il in (True, False):
+        memory = ReplayMemory(1000)
+        ex = Explorer(env, robot, torch.device("cpu"), memory, policy.gamma, target_policy=policy)
+        ex.update_target_model(policy.get_model())
+        ex.target_model.eval()
+        states = joint if il else [policy.transform(s) for s in joint]
+        ex.update_memory(states, [None] * len(states), rewards, imitation_learning=il)
+        tag = "il" if il else "rl"
+        out[tag + "_states"] = np.stack([m[0].numpy() for m in memory.memory])
+        out[tag + "_values"] = np.array([float(m[1]) for m in memory.memory])
+    np.savez_compressed(os.path.join(OUT, "update_memory.npz"), **out)
+    print("  update_memory: %d steps, IL values %.4f .. %.4f, RL values %.4f .. %.4f" % (
+        len(rewards), out["il_values"].min(), out["il_values"].max(), out["rl_values"].min(), out["rl_values"].max()))
+    return out
+
+
 def gen_action_rotate():
     policy = ref_shim.make_policy(seed=0)
     policy.build_action_space(1.0)
@@ -299,6 +349,9 @@ def main():
     if want("reward"):
         gen_reward()
         print("reward done %.1fs" % (time.time() - t0))
+    if want("memory"):
+        gen_update_memory()
+        print("update_memory done %.1fs" % (time.time() - t0))
     if want("n5"):
         d5 = gen_decisions("circle5", 5, "circle_crossing", [0, 1, 2, 3], "k2", 200, 4)
         gen_values_other_weights(d5, "circle5")

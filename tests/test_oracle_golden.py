@@ -132,3 +132,46 @@ def test_mixed_rule_and_randomized_attributes_match_reference(golden_dir, tag, r
     if rule == "mixed":
         with pytest.raises(NotImplementedError):
             scenarios.generate_pool("test", 0, 4, 5, "mixed")
+
+
+def test_explorer_update_memory_targets_match_the_reference(golden_dir):
+    """Explorer.update_memory of the drop-in mirror (crowd_nav/utils/explorer.py:114-151) against the pairs the UNMODIFIED
+    reference pushed into its ReplayMemory for the same episode (oracle/make_golden.py gen_update_memory): imitation targets
+    (discounted Monte-Carlo return) and RL targets (r + gamma_bar V_target(s')), rotated states included.  Runs on the CPU: the
+    torch restatement of the value network carries the target forward there."""
+    import torch
+    from aemcarl_b200 import weights as wts
+    from aemcarl_b200.crowd_nav.common.value_network import ValueNetworkTransformerAndGRU
+    from aemcarl_b200.crowd_nav.policy.actenvcarl import rotate
+    from aemcarl_b200.crowd_nav.utils.explorer import Explorer
+    from aemcarl_b200.crowd_nav.utils.memory import ReplayMemory
+    from aemcarl_b200.crowd_sim.envs.utils.state import FullState, JointState, ObservableState
+    g = np.load(os.path.join(golden_dir, "update_memory.npz"))
+    model = ValueNetworkTransformerAndGRU().eval()
+    model.load_flat_weights(wts.synthetic_weights(int(g["weight_seed"])))
+
+    class _Policy(object):                       # the two members update_memory uses of the target policy
+        gamma = float(g["gamma"])
+
+        def transform(self, state):
+            rows = [list(state.self_state.as_tuple()) + list(h.as_tuple()) for h in state.human_states]
+            return rotate(torch.tensor(rows, dtype=torch.float32), "holonomic")
+
+    class _Robot(object):
+        time_step, v_pref = float(g["time_step"]), float(g["v_pref"])
+
+    joint = [JointState(FullState(*[float(v) for v in rb]), [ObservableState(*[float(v) for v in h]) for h in hs])
+             for rb, hs in zip(g["robot"], g["humans_obs"])]
+    rewards = [float(r) for r in g["rewards"]]
+    for il, tag in ((True, "il"), (False, "rl")):
+        memory = ReplayMemory(1000)
+        ex = Explorer(None, _Robot(), torch.device("cpu"), memory, _Policy.gamma, target_policy=_Policy())
+        ex.target_model = model
+        states = joint if il else [_Policy().transform(s) for s in joint]
+        ex.update_memory(states, [None] * len(states), rewards, imitation_learning=il)
+        got_s = np.stack([m[0].numpy() for m in memory.memory])
+        got_v = np.array([float(m[1]) for m in memory.memory])
+        assert got_s.shape == g[tag + "_states"].shape
+        assert np.abs(got_s - g[tag + "_states"]).max() < 5e-6
+        assert np.abs(got_v - g[tag + "_values"]).max() < 5e-6, (tag, np.abs(got_v - g[tag + "_values"]).max())
+    assert np.abs(g["il_values"]).max() > 0.5 and np.abs(g["rl_values"]).max() > 0.5
