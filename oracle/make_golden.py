@@ -227,6 +227,19 @@ def gen_update_memory():
         tag = "il" if il else "rl"
         out[tag + "_states"] = np.stack([m[0].numpy() for m in memory.memory])
         out[tag + "_values"] = np.array([float(m[1]) for m in memory.memory])
+    # Trainer (crowd_nav/utils/trainer.py:22-86) of the reference on the RL pairs above: one optimize_batch step whose batch is
+    # the whole memory (so the DataLoader's shuffle only permutes it), for the three optimizers it offers
+    from crowd_nav.utils.trainer import Trainer
+    import copy
+    for opt in ("Adam", "SGD", "RMSprop"):
+        model = copy.deepcopy(policy.get_model())
+        model.eval()
+        tr = Trainer(model, memory, torch.device("cpu"), len(memory.memory))
+        tr.set_learning_rate(0.001, opt)
+        torch.manual_seed(0)
+        loss = tr.optimize_batch(1)
+        out["trainer_%s_loss" % opt] = np.array(float(loss))
+        out["trainer_%s_params" % opt] = wts.flatten_state_dict(model.state_dict())[::8].copy()    # every 8th parameter: small fixture
     np.savez_compressed(os.path.join(OUT, "update_memory.npz"), **out)
     print("  update_memory: %d steps, IL values %.4f .. %.4f, RL values %.4f .. %.4f" % (
         len(rewards), out["il_values"].min(), out["il_values"].max(), out["rl_values"].min(), out["rl_values"].max()))

@@ -175,3 +175,39 @@ def test_explorer_update_memory_targets_match_the_reference(golden_dir):
         assert np.abs(got_s - g[tag + "_states"]).max() < 5e-6
         assert np.abs(got_v - g[tag + "_values"]).max() < 5e-6, (tag, np.abs(got_v - g[tag + "_values"]).max())
     assert np.abs(g["il_values"]).max() > 0.5 and np.abs(g["rl_values"]).max() > 0.5
+
+
+@pytest.mark.parametrize("optimizer", ["Adam", "SGD", "RMSprop"])
+def test_trainer_step_matches_the_reference(golden_dir, optimizer):
+    """One Trainer.optimize_batch step (crowd_nav/utils/trainer.py:22-86) of the drop-in mirror against the UNMODIFIED reference on the
+    same memory (the batch is the whole memory, so the shuffle only permutes it): loss and the parameters after the update
+    (every 8th parameter is recorded), for the three optimizers set_learning_rate offers.  CPU, the eager torch path -- the
+    fused CUDA step is compared with this path in tests/test_gpu_train.py."""
+    import torch
+    from aemcarl_b200 import weights as wts
+    from aemcarl_b200.crowd_nav.common.value_network import ValueNetworkTransformerAndGRU
+    from aemcarl_b200.crowd_nav.utils.memory import ReplayMemory
+    from aemcarl_b200.crowd_nav.utils.trainer import Trainer
+    g = np.load(os.path.join(golden_dir, "update_memory.npz"))
+    model = ValueNetworkTransformerAndGRU().eval()
+    model.load_flat_weights(wts.synthetic_weights(int(g["weight_seed"])))
+    memory = ReplayMemory(1000)
+    for s, v in zip(g["rl_states"], g["rl_values"]):
+        memory.push((torch.from_numpy(s.copy()), torch.tensor([float(v)])))
+    tr = Trainer(model, memory, torch.device("cpu"), len(memory.memory))
+    tr.set_learning_rate(0.001, optimizer)
+    torch.manual_seed(0)
+    loss = tr.optimize_batch(1)
+    assert loss == pytest.approx(float(g["trainer_%s_loss" % optimizer]), rel=1e-5)
+    after = model.flat_weights()[::8]
+    ref = g["trainer_%s_params" % optimizer]
+    before = wts.synthetic_weights(int(g["weight_seed"]))[::8]
+    step = np.abs(ref - before).max()
+    assert step > 1e-5                                                        # the update moved the parameters
+    err = np.abs(after - ref)
+    print("%s: largest update %.3e, largest deviation from the reference %.3e" % (optimizer, step, err.max()))
+    if optimizer == "RMSprop":
+        # the first RMSprop step is lr * g / (|g| sqrt(1 - alpha) + eps): where |g| is at rounding level its sign is noise
+        assert (err > 1e-3 * step).mean() < 0.01 and err.max() <= 2.5 * step
+    else:
+        assert err.max() <= 1e-3 * step, (err.max(), step)
