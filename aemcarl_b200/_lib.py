@@ -86,6 +86,7 @@ SYMBOLS = {
     "aem_rmsprop_step": (ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                         ctypes.c_double, _VP]),
     "aem_launch_count": (ctypes.c_longlong, [_VP]),
+    "aem_train_scratch_generation": (ctypes.c_longlong, [_VP]),
 }
 
 _lib = None
@@ -95,10 +96,11 @@ def load():
     """dlopen the in-tree library and type every entry point.  Raises if it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("AEM_LIB_PATH") or LIB_PATH      # AEM_LIB_PATH: an experiment build (build.py --variant)
+        if not os.path.exists(path):
             raise AemError("libaemcarl_b200.so is missing (%s); run `python -m aemcarl_b200.build` -- there is no "
-                           "CPU fallback" % LIB_PATH)
-        lib = ctypes.CDLL(LIB_PATH)
+                           "CPU fallback" % path)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype = res

@@ -21,7 +21,6 @@ SOURCES = {
     "lookahead.cu": [],
     "lookahead_tc.cu": [],
     "lookahead_h16.cu": [],
-    "lookahead_q16.cu": [],
     "train.cu": ["-DAEM_TRAIN_TIMELINE"] if os.environ.get("AEM_TRAIN_TIMELINE") else [],
     "scenario.cu": ["-fmad=false"],   # Python float arithmetic of the scenario draw, op by op
     "env.cu": ["-fmad=false"],   # FP64 env arithmetic is a sequence of individually rounded Python float ops
@@ -42,6 +41,26 @@ def _stale(target, deps):
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_variant(name, defines, verbose=False):
+    """A debug / experiment variant of the library (e.g. the timeline build of lookahead_h16.cu):
+    tools/bin/libaemcarl_b200_<name>.so, selected at run time with AEM_LIB_PATH (aemcarl_b200/_lib.py)."""
+    obj = os.path.join(CSRC, "_obj_" + name)
+    out_dir = os.path.join(HERE, "..", "tools", "bin")
+    os.makedirs(obj, exist_ok=True)
+    os.makedirs(out_dir, exist_ok=True)
+    objs = []
+    for src, extra in SOURCES.items():
+        o = os.path.join(obj, src.replace(".cu", ".o"))
+        objs.append(o)
+        cmd = [nvcc()] + COMMON + extra + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", o]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    lib = os.path.abspath(os.path.join(out_dir, "libaemcarl_b200_%s.so" % name))
+    subprocess.check_call([nvcc(), "-shared", "-o", lib] + objs + ARCH + ["-cudart", "static"])
+    return lib
 
 
 def build(force=False, verbose=False):
@@ -67,4 +86,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--variant" in sys.argv:          # python -m aemcarl_b200.build --variant tl AEM_H16_TIMELINE
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:], verbose="--verbose" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -152,15 +152,22 @@ class FusedStep(object):
         self.export_state()
 
     def export_state(self):
-        """make the torch optimizer's state describe the flat vectors (views, no copies)"""
+        """make the torch optimizer's state describe the flat vectors (views, no copies).  The step count is ONE shared
+        tensor that sync_step() keeps current, and the SGD momentum buffer is always the live view (a zero buffer before the
+        first step gives buf = grad, torch's first-step rule), so optimizer.state_dict() and a later fall-back to the torch
+        step see the state the kernels left."""
+        self._step_t = torch.tensor(float(self.step))
         for p, off, n, shape in self._params:
             m, v = self.exp_avg[off:off + n].view(shape), self.exp_avg_sq[off:off + n].view(shape)
             if self.kind == "adam":
-                self.optimizer.state[p] = {"step": torch.tensor(float(self.step)), "exp_avg": m, "exp_avg_sq": v}
+                self.optimizer.state[p] = {"step": self._step_t, "exp_avg": m, "exp_avg_sq": v}
             elif self.kind == "sgd":
-                self.optimizer.state[p] = {"momentum_buffer": m if self.step > 0 else None}
+                self.optimizer.state[p] = {"momentum_buffer": m}
             else:
-                self.optimizer.state[p] = {"step": torch.tensor(float(self.step)), "square_avg": v}
+                self.optimizer.state[p] = {"step": self._step_t, "square_avg": v}
+
+    def sync_step(self):
+        self._step_t.fill_(float(self.step))
 
     def run_batches(self, memory, batch_size, num_batches, use_graph=False):
         """num_batches iterations of optimize_batch (trainer.py:66-86) on a DeviceReplayMemory with Adam on ONE rank: every
@@ -190,10 +197,13 @@ class FusedStep(object):
 
         done = 0
         if use_graph and num_batches > 2:
-            key = (len(memory), k, n, g["lr"], tuple(g["betas"]), g["eps"], memory.states.data_ptr(), memory.sample_seed)
+            one()                                           # (re)allocates the library's scratch outside any capture
+            done += 1
+            # the graph holds the ring, the batch buffers AND the engine's scratch pointers: the scratch generation is part
+            # of the key, so a larger batch / n that went through this (process-wide) engine in between forces a re-capture
+            key = (len(memory), k, n, g["lr"], tuple(g["betas"]), g["eps"], memory.states.data_ptr(), memory.sample_seed,
+                   self.engine.train_scratch_generation())
             if self._graph_key != key:
-                one()                                       # allocates the library's scratch outside the capture
-                done += 1
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     one()
@@ -206,6 +216,7 @@ class FusedStep(object):
             for _ in range(num_batches):
                 one()
         self.step += num_batches
+        self.sync_step()
         memory._samples_drawn += num_batches
         self.model.note_external_update()
         return self._loss_sum[0] / num_batches
@@ -220,7 +231,13 @@ class FusedStep(object):
         world = 1
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             world = dist.get_world_size()
+            ev = getattr(self, "allreduce_events", None)          # bench.py --config 4: CUDA events around the NCCL call
+            if ev is not None:
+                ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                ev[-1][0].record()
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+            if ev is not None:
+                ev[-1][1].record()
         self.step += 1
         if self.kind == "adam":
             self.engine.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"], g["eps"], self.step,
@@ -229,6 +246,7 @@ class FusedStep(object):
             self.engine.sgd_step(self.flat, self.grad, self.exp_avg, g["lr"], g["momentum"], self.step, 1.0 / world)
         else:
             self.engine.rmsprop_step(self.flat, self.grad, self.exp_avg_sq, g["lr"], g["alpha"], g["eps"], 1.0 / world)
+        self.sync_step()
         self.model.note_external_update()
         return self.loss[0].clone()
 

@@ -65,11 +65,7 @@ enum { TL_Z1S = 0, TL_QS = 1, TL_Z1 = 2, TL_Z2 = 3, TL_R1 = 4, TL_R2 = 5, TL_Q =
        TL_ENC = 7,      // + 7 * l : INA, INB, OUT, F1A, F1B, F2A, F2B
        TL_A0 = 28, TL_A2 = 29, TL_NUM = 30 };
 constexpr int TC_PBLK_FLOATS = 3200;
-constexpr int H16_PBLK_FLOATS = 704;       // LayerNorm 600, ponder 51, action_mlp.4 51 (biases ride in the weight images)
-constexpr int Q16_PBLK_FLOATS = 2880;
-// layers of lookahead_q16.cu (four threads per row)
-enum { QL_Z1 = 0, QL_Z1R1 = 1, QL_Z2 = 2, QL_R2 = 3, QL_Q = 4, QL_ENC = 5 /* + 4 * l : IN, OUT, F1, F2 */, QL_A0 = 17,
-       QL_A2 = 18, QL_NUM = 19 };
+constexpr int H16_PBLK_FLOATS = 800;       // LayerNorm 672, ponder 57, action_mlp.4 57 as rows of 28 (capi.cu pack_h16)
 
 struct NetParams {
     const float *raw;      // raw blob (biases, LayerNorm, ponder, last action layer)
@@ -88,11 +84,6 @@ struct NetParams {
     const float *h16_pblk;
     int h16_pblk_floats;
     const TcLayer *h16_layers_d;
-    // FP16x3, four threads per row (lookahead_q16.cu)
-    const __half *q16_img;
-    const float *q16_pblk;
-    int q16_pblk_floats;
-    const TcLayer *q16_layers_d;
 };
 
 // tile sizes of the packed layers (shared by the host packer and the kernel)
@@ -117,10 +108,6 @@ struct aem_handle_s {
     float *h16_pblk_d;
     aem::TcLayer *h16_layers_d;
     size_t h16_img_halves;
-    __half *q16_img_d;
-    float *q16_pblk_d;
-    aem::TcLayer *q16_layers_d;
-    size_t q16_img_halves;
     size_t tc_img_floats;
     int precision;       // 0 = FP32 FFMA kernel, 1 = tcgen05 3xTF32 kernel, 2 = tcgen05 FP16x3 kernel (2 tiles / SM)
     aem::NetParams net;
@@ -141,6 +128,7 @@ struct aem_handle_s {
     int *tr_flags;
     int tr_grid, tr_B;
     size_t tr_stash_floats, tr_gru_floats;
+    long long tr_generation;   // bumped whenever the training scratch is reallocated (captured graphs hold its pointers)
 };
 
 #define AEM_CUDA_CHECK(expr)                                                      \
@@ -158,7 +146,6 @@ struct LookaheadArgs;
 cudaError_t launch_lookahead(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
 cudaError_t launch_lookahead_tc(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
 cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
-cudaError_t launch_lookahead_q16(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
 cudaError_t launch_transform(const double *robot, const double *humans, int B, int n, float *out, cudaStream_t st);
 cudaError_t launch_select(const double *values, const double *robot, int B, int A, int32_t *best, cudaStream_t st);
 cudaError_t launch_orca(int B, int n, const double *humans, const double *robot, const aem_env_params &p,
@@ -207,7 +194,7 @@ struct LookaheadArgs {
     float *net_values;
     uint8_t *steps;
     float *gru_out;        // mode 2: [S*T][50]
-    long long *dbg;        // optional timeline buffer (AEM_Q16_TIMELINE=1): clock64 stamps of CTA 0, first tile
+    long long *dbg;        // optional debug buffer (lookahead_h16.cu: AEM_H16_TIMELINE / AEM_H16_WATCHDOG builds)
     int stagger_ns;        // lookahead_h16: start-up delay of the second CTA of every SM (anti-phase the two tiles)
 };
 }  // namespace aem

@@ -184,34 +184,6 @@ struct H16Pack {
             }
         L.bias_off = (N * K * 2 > 12288) ? 2 : 1;     // h16 tables: k-halves per image (ring slots are 12 KB)
     }
-    // layout with a separate bias block in the parameter block (lookahead_q16.cu)
-    template <class OM, class IM>
-    void add(int id, const float *W, int in_dim, const float *bias, int N, int K, OM om, IM im, int expect_bias_off)
-    {
-        aem::TcLayer &L = layers[id];
-        L.N = N; L.ksteps = K / 16; L.bytes = N * K * 2;
-        L.off_hi = (int)img.size();
-        img.resize(img.size() + (size_t)2 * N * K, __float2half(0.0f));
-        L.off_lo = L.off_hi + N * K;
-        for (int c = 0; c < N; ++c)
-            for (int k = 0; k < K; ++k) {
-                const int o = om(c), i = im(k);
-                const float w = (o >= 0 && i >= 0) ? W[(size_t)o * in_dim + i] : 0.0f;
-                const __half hi = __float2half_rn(w);
-                const __half lo = __float2half_rn(w - __half2float(hi));
-                const size_t at = ((size_t)(k / 8) * N + c) * 8 + (k % 8);
-                img[L.off_hi + at] = hi;
-                img[L.off_lo + at] = lo;
-            }
-        L.bias_off = (N * K * 2 > 12288) ? 2 : 1;     // h16 tables: k-halves per image (ring slots are 12 KB)
-        if (expect_bias_off >= 0) {
-            if ((int)pblk.size() != expect_bias_off) { fprintf(stderr, "pack_h16: bias layout mismatch at layer %d\n", id); abort(); }
-            for (int c = 0; c < N; ++c) {
-                const int o = om(c);
-                pblk.push_back((o >= 0 && bias) ? bias[o] : 0.0f);
-            }
-        }
-    }
 };
 
 void pack_h16(const float *w, H16Pack &P)
@@ -241,89 +213,31 @@ void pack_h16(const float *w, H16Pack &P)
     }
     P.add(TL_A0, w + OFF_A0W, 56, w + OFF_A0B, 128, 64, out100w, in_jointw, 63, 127);
     P.add(TL_A2, w + OFF_A2W, 100, w + OFF_A2B, 64, 128, out50, in100w, 127, -1);
-    // parameter block: LayerNorm (3 x 200), ponder (50 + 1), last action layer (50 + 1)
+    // parameter block (lookahead_h16.cu PB_*): every 50-vector as two rows of 28 floats (25 values + 3 zeros), one per
+    // thread half, so that a thread reads its values as 7 float4.
+    //   LayerNorm [layer][norm1 / norm2][half][gamma 28 | beta 28]  (672 floats)
+    //   ponder    [half][28] + bias + 3 zeros                       (at 672, bias at 728)
+    //   action_mlp.4 [half][28] + bias                              (at 732, bias at 788)
+    auto rows28 = [&P](const float *v) {
+        for (int hf = 0; hf < 2; ++hf)
+            for (int j = 0; j < 28; ++j) P.pblk.push_back(j < 25 ? v[25 * hf + j] : 0.0f);
+    };
     for (int l = 0; l < 3; ++l) {
         const float *E = w + OFF_ENC + l * ENC_SIZE;
-        P.pblk.insert(P.pblk.end(), E + ENC_N1G, E + ENC_N1G + 200);
+        for (int nm = 0; nm < 2; ++nm) {
+            const float *g = E + (nm ? ENC_N2G : ENC_N1G), *b = E + (nm ? ENC_N2B : ENC_N1B);
+            for (int hf = 0; hf < 2; ++hf) {
+                for (int j = 0; j < 28; ++j) P.pblk.push_back(j < 25 ? g[25 * hf + j] : 0.0f);
+                for (int j = 0; j < 28; ++j) P.pblk.push_back(j < 25 ? b[25 * hf + j] : 0.0f);
+            }
+        }
     }
-    P.pblk.insert(P.pblk.end(), w + OFF_PW, w + OFF_PW + 51);
-    P.pblk.insert(P.pblk.end(), w + OFF_A4W, w + OFF_A4W + 51);
+    rows28(w + OFF_PW);
+    P.pblk.push_back(w[OFF_PB]);
+    while (P.pblk.size() < 732) P.pblk.push_back(0.0f);
+    rows28(w + OFF_A4W);
+    P.pblk.push_back(w[OFF_A4B]);
     while (P.pblk.size() < (size_t)H16_PBLK_FLOATS) P.pblk.push_back(0.0f);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// FP16x3 images for lookahead_q16.cu: four threads per row, quarter q owns real columns [qstart, qstart + qsize) of 50
-// (13 / 12 / 13 / 12); 100-wide layers 25 per quarter; the 150 linear1 units 38 / 37 / 38 / 37.
-// ---------------------------------------------------------------------------------------------------------
-const int QSZ[4] = {13, 12, 13, 12}, QST[4] = {0, 13, 25, 38};
-int real50q(int qd, int j) { return j < QSZ[qd] ? QST[qd] + j : -1; }
-int out50q(int c) { return real50q(c / 16, c % 16); }                                   // N = 64  = 4 x 16
-int in50q(int k) { return real50q(k / 16, k % 16); }                                    // K = 64
-int out100q(int c) { int qd = c / 32, j = c % 32; return j < 25 ? 25 * qd + j : -1; }   // N = 128 = 4 x 32
-int in100q(int k) { return out100q(k); }                                                // K = 128
-int in_hxq(int k)      // [h quarter ; x slots]: x counts 3, 4, 3, 3
-{
-    const int XC[4] = {3, 4, 3, 3}, XS[4] = {0, 3, 7, 10};
-    int qd = k / 16, j = k % 16;
-    if (j < QSZ[qd]) return QST[qd] + j;
-    int i = j - QSZ[qd];
-    return i < XC[qd] ? 50 + XS[qd] + i : -1;
-}
-int in_jointq(int k)   // [env quarter ; self_state slots]: self counts 2, 1, 2, 1
-{
-    const int SC[4] = {2, 1, 2, 1}, SS[4] = {0, 2, 3, 5};
-    int qd = k / 16, j = k % 16;
-    if (j < QSZ[qd]) return 6 + QST[qd] + j;
-    int i = j - QSZ[qd];
-    return i < SC[qd] ? SS[qd] + i : -1;
-}
-int unit150q(int c)    // N = K = 192 = 4 x 48: 38 / 37 / 38 / 37 hidden units
-{
-    const int US[4] = {38, 37, 38, 37}, UST[4] = {0, 38, 75, 113};
-    int qd = c / 48, j = c % 48;
-    return j < US[qd] ? UST[qd] + j : -1;
-}
-int in_projq(int c)    // N = 192: head = c / 96, block (q, k, v) = (c % 96) / 32, half of the head = (c % 32) / 16
-{
-    int hd = c / 96, s3 = (c % 96) / 32, sub = (c % 32) / 16, j = c % 16;
-    int r = real50q(2 * hd + sub, j);
-    return r >= 0 ? s3 * 50 + r : -1;
-}
-
-void pack_q16(const float *w, H16Pack &P)
-{
-    using namespace aem;
-    auto nsplit_fix = [&P](int id) { P.layers[id].bias_off = (P.layers[id].bytes > 16384) ? 2 : 1; };
-    // fused z1 | r1: rows 0..99 = convz.0, rows 100..199 = convr.0
-    std::vector<float> zr(200 * HXD), zrb(200);
-    memcpy(zr.data(), w + OFF_Z1W, sizeof(float) * 100 * HXD);
-    memcpy(zr.data() + 100 * HXD, w + OFF_R1W, sizeof(float) * 100 * HXD);
-    memcpy(zrb.data(), w + OFF_Z1B, sizeof(float) * 100);
-    memcpy(zrb.data() + 100, w + OFF_R1B, sizeof(float) * 100);
-    auto out200 = [](int c) { int r = out100q(c % 128); return r >= 0 ? 100 * (c / 128) + r : -1; };
-    P.add(QL_Z1R1, zr.data(), HXD, zrb.data(), 256, 64, out200, in_hxq, 0);
-    P.add(QL_Z2, w + OFF_Z2W, 100, w + OFF_Z2B, 64, 128, out50q, in100q, 256);
-    P.add(QL_R2, w + OFF_R2W, 100, w + OFF_R2B, 64, 128, out50q, in100q, 320);
-    P.add(QL_Q, w + OFF_QW, HXD, w + OFF_QB, 64, 64, out50q, in_hxq, 384);
-    P.add(QL_Z1, w + OFF_Z1W, HXD, nullptr, 128, 64, out100q, in_hxq, -1);        // step 1: z path only
-    for (int l = 0; l < 3; ++l) {
-        const float *E = w + OFF_ENC + l * ENC_SIZE;
-        const int LB = QL_ENC + 4 * l, PBL = 448 + 512 * l;
-        P.add(LB + 0, E + ENC_INW, HID, E + ENC_INB, 192, 64, in_projq, in50q, PBL);
-        P.add(LB + 1, E + ENC_OW, HID, E + ENC_OB, 64, 64, out50q, in50q, PBL + 192);
-        P.add(LB + 2, E + ENC_L1W, HID, E + ENC_L1B, 192, 64, unit150q, in50q, PBL + 256);
-        P.add(LB + 3, E + ENC_L2W, 150, E + ENC_L2B, 64, 192, out50q, unit150q, PBL + 448);
-    }
-    P.add(QL_A0, w + OFF_A0W, 56, w + OFF_A0B, 128, 64, out100q, in_jointq, 1984);
-    P.add(QL_A2, w + OFF_A2W, 100, w + OFF_A2B, 64, 128, out50q, in100q, 2112);
-    for (int i = 0; i < QL_NUM; ++i) nsplit_fix(i);
-    for (int l = 0; l < 3; ++l) {
-        const float *E = w + OFF_ENC + l * ENC_SIZE;
-        P.pblk.insert(P.pblk.end(), E + ENC_N1G, E + ENC_N1G + 200);
-    }
-    P.pblk.insert(P.pblk.end(), w + OFF_PW, w + OFF_PW + 51);
-    P.pblk.insert(P.pblk.end(), w + OFF_A4W, w + OFF_A4W + 51);
-    while (P.pblk.size() < (size_t)Q16_PBLK_FLOATS) P.pblk.push_back(0.0f);
 }
 
 cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -389,7 +303,7 @@ int aem_destroy(aem_handle h)
 {
     if (!h) return AEM_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->raw_d); cudaFree(h->packed_d); cudaFree(h->tc_img_d); cudaFree(h->tc_pblk_d); cudaFree(h->tc_layers_d); cudaFree(h->h16_img_d); cudaFree(h->h16_pblk_d); cudaFree(h->h16_layers_d); cudaFree(h->q16_img_d); cudaFree(h->q16_pblk_d); cudaFree(h->q16_layers_d); cudaFree(h->actions_d); cudaFree(h->lut_d);
+    cudaFree(h->raw_d); cudaFree(h->packed_d); cudaFree(h->tc_img_d); cudaFree(h->tc_pblk_d); cudaFree(h->tc_layers_d); cudaFree(h->h16_img_d); cudaFree(h->h16_pblk_d); cudaFree(h->h16_layers_d); cudaFree(h->actions_d); cudaFree(h->lut_d);
     cudaFree(h->s_robot); cudaFree(h->s_humans); cudaFree(h->s_time); cudaFree(h->s_newvel);
     cudaFree(h->s_rewards); cudaFree(h->s_dmin); cudaFree(h->s_hnext); cudaFree(h->s_values);
     cudaFree(h->s_oreward); cudaFree(h->s_info); cudaFree(h->s_best); cudaFree(h->s_odone); cudaFree(h->s_oinfo);
@@ -479,26 +393,6 @@ int aem_load_weights(aem_handle h, const float *w, size_t count)
         net.h16_pblk_floats = H16_PBLK_FLOATS;
         net.h16_layers_d = h->h16_layers_d;
     }
-    {   // FP16x3 images, four threads per row
-        H16Pack P;
-        pack_q16(w, P);
-        if (P.pblk.size() != (size_t)Q16_PBLK_FLOATS) return aem_set_error(AEM_ERR_INVALID, "q16 parameter block size");
-        if (P.img.size() > h->q16_img_halves) {
-            cudaFree(h->q16_img_d);
-            h->q16_img_d = nullptr;
-            AEM_CUDA_CHECK(cudaMalloc(&h->q16_img_d, sizeof(__half) * P.img.size()));
-            h->q16_img_halves = P.img.size();
-        }
-        if (!h->q16_pblk_d) AEM_CUDA_CHECK(cudaMalloc(&h->q16_pblk_d, sizeof(float) * Q16_PBLK_FLOATS));
-        if (!h->q16_layers_d) AEM_CUDA_CHECK(cudaMalloc(&h->q16_layers_d, sizeof(TcLayer) * TL_NUM));
-        AEM_CUDA_CHECK(cudaMemcpy(h->q16_img_d, P.img.data(), sizeof(__half) * P.img.size(), cudaMemcpyHostToDevice));
-        AEM_CUDA_CHECK(cudaMemcpy(h->q16_pblk_d, P.pblk.data(), sizeof(float) * Q16_PBLK_FLOATS, cudaMemcpyHostToDevice));
-        AEM_CUDA_CHECK(cudaMemcpy(h->q16_layers_d, P.layers, sizeof(TcLayer) * TL_NUM, cudaMemcpyHostToDevice));
-        net.q16_img = h->q16_img_d;
-        net.q16_pblk = h->q16_pblk_d;
-        net.q16_pblk_floats = Q16_PBLK_FLOATS;
-        net.q16_layers_d = h->q16_layers_d;
-    }
     h->weights_set = true;
     return AEM_OK;
 }
@@ -538,8 +432,8 @@ int aem_set_act_mode(aem_handle h, int act_fixed, int act_steps)
 int aem_set_precision(aem_handle h, int precision)
 {
     if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
-    if (precision < 0 || precision > 3)
-        return aem_set_error(AEM_ERR_INVALID, "precision must be 0 (fp32), 1 (tf32x3), 2 (fp16x3) or 3 (fp16x3q)");
+    if (precision < 0 || precision > 2)
+        return aem_set_error(AEM_ERR_INVALID, "precision must be 0 (fp32), 1 (tf32x3) or 2 (fp16x3)");
     h->precision = precision;
     return AEM_OK;
 }
@@ -602,8 +496,7 @@ int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const doubl
     a.gamma_bar = gamma_bar;
     a.robot = robot_d; a.humans_next = humans_next_d; a.actions = h->actions_d; a.rewards = rewards_d;
     a.values = values_d; a.net_values = net_values_d; a.steps = act_steps_d;
-    AEM_CUDA_CHECK(h->precision == 3 ? launch_lookahead_q16(h, a, as_stream(stream))
-                   : h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
+    AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
                    : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
                                        : launch_lookahead(h, a, as_stream(stream)));
     AEM_CUDA_CHECK(launch_select(values_d, robot_d, B, h->A, best_d, as_stream(stream)));
@@ -689,8 +582,7 @@ int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *
     a.total_samples = S;
     a.states = states_d;
     a.net_values = values_d; a.steps = steps_d;
-    AEM_CUDA_CHECK(h->precision == 3 ? launch_lookahead_q16(h, a, as_stream(stream))
-                   : h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
+    AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
                    : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
                                        : launch_lookahead(h, a, as_stream(stream)));
     h->launches += (S > 0);
@@ -727,8 +619,7 @@ int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint
     a.total_samples = S;
     a.states = x_d;
     a.gru_out = out_d; a.steps = steps_d;
-    AEM_CUDA_CHECK(h->precision == 3 ? launch_lookahead_q16(h, a, as_stream(stream))
-                   : h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
+    AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
                    : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
                                        : launch_lookahead(h, a, as_stream(stream)));
     h->launches += (S > 0);
@@ -909,5 +800,6 @@ int aem_rmsprop_step(aem_handle h, size_t count, float *params_d, const float *g
 }
 
 long long aem_launch_count(aem_handle h) { return h ? h->launches : 0; }
+long long aem_train_scratch_generation(aem_handle h) { return h ? h->tr_generation : 0; }
 
 }  // extern "C"

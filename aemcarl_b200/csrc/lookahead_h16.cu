@@ -1,5 +1,6 @@
 // lookahead_h16.cu -- tensor-core lookahead kernel, FP16x3 operands, TWO tiles in flight per SM (sm_100a).
-// The shipped default (aem_set_precision mode 2).  History and measurements: profiles/r01_lookahead_h16_final_ncu.md.
+// The shipped default (aem_set_precision mode 2).  History and measurements: profiles/r01_lookahead_h16_final_ncu.md,
+// profiles/r02_lookahead_h16_ncu.md.
 //
 // Same function as lookahead.cu / lookahead_tc.cu, laid out so that one 128-row tile needs only 256 TMEM columns,
 // 128 registers / thread and 114 KB of shared memory; two CTAs then share an SM and the hardware overlaps the MMA /
@@ -18,6 +19,16 @@
 //     epilogues of warps without such a row;
 //   * one copy of the gate (z / r), FFN-chunk and LayerNorm code (the two CTAs of an SM run half a tile apart: the
 //     instruction cache decides), attention with float4 key / value rows and a streaming softmax.
+// Round 2: the kernel was bound by the instruction issue of its epilogues (profiles/r01: 16.4 k warp instructions per
+// warp and tile, tensor pipe 35 % busy), so every epilogue now works on PAIRS of columns:
+//   * packed FP32 arithmetic (FFMA2 / FADD2 / FMUL2: __ffma2_rn ...) for the gate blend, the ACT accumulation, LayerNorm,
+//     the attention dot products / weighted sums and the residual of the hi / lo split (5 instructions per pair);
+//   * sigma / tanh from ex2.approx + rcp.approx without the range fix-ups of __expf / __fdividef (4 / 3.5 instructions per
+//     element instead of 8 / 9), softmax in the log2 domain (log2 e folded into the query scale);
+//   * the agent-centric rotation from (dx, dy) / |d| instead of atan2 -> cos / sin;
+//   * tcgen05.ld x16, the x slots of the GRU operands split once per tile, parameters as float4 rows;
+//   * the halting vote of a GRU step is ONE barrier (__syncthreads_or + per-step flags) that doubles as the group
+//     barrier of the next step; every thread counts its own sample's steps.
 // Layout of every layer (N / K permutation and padding) is defined in capi.cu pack_h16.
 #include <cuda_fp16.h>
 #include <stdio.h>
@@ -54,29 +65,102 @@ constexpr uint32_t DF2 = 0;             // linear2 accumulators N = 64 (aliases 
 constexpr uint32_t DA0 = 64;            // action_mlp.0 accumulators N = 128, converted in place
 constexpr uint32_t DA2 = 192;           // action_mlp.2 accumulators N = 64
 
-// parameter block offsets (floats): LayerNorm 3 x [g1 b1 g2 b2], ponder weights + bias, action_mlp.4 weights + bias.
-// The biases of the MMA layers ride in the weight images (capi.cu pack_h16): every operand keeps one padding K slot
-// (slot 31 of half 1) at exactly 1.0.
-constexpr int PB_LN = 0, PB_PW = 600, PB_A4 = 651;
-static_assert(PB_A4 + 51 <= H16_PBLK_FLOATS, "parameter block");
+// parameter block (floats, capi.cu pack_h16): every 50-vector is stored as two rows of 28 (25 + 3 zeros), one per thread
+// half, so that a thread reads its 25 values as 7 float4.  LayerNorm: [layer][norm1 / norm2][half][gamma 28 | beta 28];
+// ponder weights [half][28] + bias; action_mlp.4 weights [half][28] + bias.
+// The biases of the MMA layers ride in the weight images: every operand keeps one padding K slot (slot 31 of half 1) at
+// exactly 1.0.
+constexpr int PB_LN = 0, PB_PW = 672, PB_PWB = 728, PB_A4 = 732, PB_A4B = 788;
+static_assert(PB_A4B + 1 <= H16_PBLK_FLOATS, "parameter block");
 
 constexpr size_t SMEM_BYTES = (size_t)NBUF * WBUF_BYTES + 128 * KV_PITCH * 4 + PBLK_MAX * 4 + 4 * 128 * 4 +
                               (96 + 4) * 4 + (NBUF + NEV) * 8 + 16;
 
+constexpr float LOG2E = 1.4426950408889634f;
+
 __device__ __forceinline__ void pair_sync(int q4) { asm volatile("bar.sync %0, 64;" ::"r"(q4 + 1) : "memory"); }
 
-__device__ __forceinline__ void ld8f(uint32_t taddr, float *v)
+// ---- packed FP32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100) ----
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoidf_(float x) { return rcpf(1.0f + ex2f(-LOG2E * x)); }
+__device__ __forceinline__ float sigmoid_legacy(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_legacy(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+// sigma(relu(v)) of a pair: 1 / (1 + 2^min(-v log2 e, 0))
+template <int OPT>
+__device__ __forceinline__ float2 sigmoid_relu2(float2 v)
+{
+    if (OPT & 4) return f2(sigmoid_legacy(fmaxf(v.x, 0.0f)), sigmoid_legacy(fmaxf(v.y, 0.0f)));
+    const float2 t = mul2(v, bc2(-LOG2E));
+    const float2 d = add2(f2(ex2f(fminf(t.x, 0.0f)), ex2f(fminf(t.y, 0.0f))), bc2(1.0f));
+    return f2(rcpf(d.x), rcpf(d.y));
+}
+// tanh of a pair: 1 - 2 / (2^(2 v log2 e) + 1)
+template <int OPT>
+__device__ __forceinline__ float2 tanh2(float2 v)
+{
+    if (OPT & 4) return f2(tanh_legacy(v.x), tanh_legacy(v.y));
+    const float2 t = mul2(v, bc2(2.0f * LOG2E));
+    const float2 d = add2(f2(ex2f(t.x), ex2f(t.y)), bc2(1.0f));
+    return fma2(f2(rcpf(d.x), rcpf(d.y)), bc2(-2.0f), bc2(1.0f));
+}
+
+// ---- tensor-memory loads / stores of this thread's lane: columns as float pairs ----
+__device__ __forceinline__ void ld16p(uint32_t taddr, float2 *v)      // 16 columns -> 8 pairs
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+          "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void ld8p(uint32_t taddr, float2 *v)       // 8 columns -> 4 pairs
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y)
                  : "r"(taddr)
                  : "memory");
 }
-__device__ __forceinline__ void ld4u(uint32_t taddr, uint32_t *v)
+__device__ __forceinline__ void ld4p(uint32_t taddr, float2 *v)       // 4 columns -> 2 pairs
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y)
                  : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void ld2p(uint32_t taddr, float2 *v)       // 2 columns -> 1 pair
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(v[0].x), "=f"(v[0].y) : "r"(taddr) : "memory");
+}
+// the 26 leading columns of a 32-column block (25 real + the first padding column) -> 13 pairs
+template <int OPT>
+__device__ __forceinline__ void ld26p(uint32_t taddr, float2 *v)
+{
+    if (OPT & 8) {
+        float2 t[16];
+        ld8p(taddr, t); ld8p(taddr + 8, t + 4); ld8p(taddr + 16, t + 8); ld8p(taddr + 24, t + 12);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 13; ++i) v[i] = t[i];
+    } else {
+        ld16p(taddr, v);
+        ld8p(taddr + 16, v + 8);
+        ld2p(taddr + 24, v + 12);
+    }
+}
+__device__ __forceinline__ void st8u(uint32_t taddr, const uint32_t *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
 __device__ __forceinline__ void st4u(uint32_t taddr, const uint32_t *v)
@@ -85,58 +169,48 @@ __device__ __forceinline__ void st4u(uint32_t taddr, const uint32_t *v)
                  "r"(v[2]), "r"(v[3])
                  : "memory");
 }
-// (a, b) -> packed fp16 pair hi and the packed residual pair lo; a sits in the low half (even k)
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+__device__ __forceinline__ void st1u(uint32_t taddr, uint32_t v)
 {
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 f = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
-    hi = *reinterpret_cast<const uint32_t *>(&h);
-    lo = *reinterpret_cast<const uint32_t *>(&l);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
 }
-// 8 consecutive K slots -> 4 hi columns + 4 lo columns
-__device__ __forceinline__ void st8_pack(uint32_t hi_addr, uint32_t lo_addr, const float *v)
+
+// (a.x, a.y) -> packed fp16 pair hi and the packed residual pair lo; a.x sits in the low half (even k)
+__device__ __forceinline__ void split2(float2 a, uint32_t &hi, uint32_t &lo)
 {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-    st4u(hi_addr, h);
-    st4u(lo_addr, l);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(a.y), "f"(a.x));
+    const float2 r = sub2(a, __half22float2(*reinterpret_cast<const __half2 *>(&hi)));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
 }
-// NV slots (multiple of 8) starting at slot 0 of this thread's block
-template <int NV>
-__device__ __forceinline__ void st_pack(uint32_t hi_addr, uint32_t lo_addr, const float *v)
+// ReLU + split: hi = relu(a) rounded TOWARDS ZERO, so the residual of a positive value is never negative and the ReLU
+// can ride in both conversions (a negative value gives hi = 0, residual a < 0 -> lo = 0).
+__device__ __forceinline__ void split2_relu(float2 a, uint32_t &hi, uint32_t &lo)
 {
-#pragma unroll
-    for (int i = 0; i < NV; i += 8) st8_pack(hi_addr + i / 2, lo_addr + i / 2, v + i);
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(a.y), "f"(a.x));
+    const float2 r = sub2(a, __half22float2(*reinterpret_cast<const __half2 *>(&hi)));
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
 }
-// read back 8 slots (4 hi + 4 lo columns) as floats: value = hi + lo
-__device__ __forceinline__ void ld8_unpack(uint32_t hi_addr, uint32_t lo_addr, float *v)
+// Operand block of a thread: 16 columns hi at `hi_addr`, 16 columns lo 32 further; column j = K slots (2j, 2j + 1).
+// Columns 0..12 are split from the 13 pairs `v`; columns 13..15 (x slots / constants) arrive already split.
+template <int OPT>
+__device__ __forceinline__ void st16_split(uint32_t hi_addr, const float2 *v, uint32_t h13, uint32_t h14, uint32_t h15,
+                                           uint32_t l13, uint32_t l14, uint32_t l15)
 {
-    uint32_t h[4], l[4];
-    ld4u(hi_addr, h);
-    ld4u(lo_addr, l);
-    tmem_wait_ld();
+    uint32_t h[16], l[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 fh = __half22float2(*reinterpret_cast<const __half2 *>(&h[i]));
-        const float2 fl = __half22float2(*reinterpret_cast<const __half2 *>(&l[i]));
-        v[2 * i] = fh.x + fl.x;
-        v[2 * i + 1] = fh.y + fl.y;
+    for (int i = 0; i < 13; ++i) split2(v[i], h[i], l[i]);
+    h[13] = h13; h[14] = h14; h[15] = h15;
+    l[13] = l13; l[14] = l14; l[15] = l15;
+    if (OPT & 8) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { st4u(hi_addr + 4 * c, h + 4 * c); st4u(hi_addr + 32 + 4 * c, l + 4 * c); }
+    } else {
+        st8u(hi_addr, h);
+        st8u(hi_addr + 8, h + 8);
+        st8u(hi_addr + 32, l);
+        st8u(hi_addr + 40, l + 8);
     }
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
-
-// ReLU + fp16 hi/lo split of a pair: hi = relu(a) rounded TOWARDS ZERO, so the residual of a positive value is never
-// negative and the ReLU can ride in both conversions (a negative value gives hi = 0, residual a < 0 -> lo = 0).
-__device__ __forceinline__ void split2_relu(float a, float b, uint32_t &hi, uint32_t &lo)
-{
-    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
-    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - f.y), "f"(a - f.x));
-}
 // In-place ReLU conversion of this thread's W accumulator columns [base, base + W) into its operand block, 16 columns
 // at a time: accumulators [16c, 16c + 16) -> hi columns [16c, 16c + 8), lo columns [16c + 8, 16c + 16).  Every chunk is
 // read completely before it is overwritten and touches no other chunk, so the loop stays rolled (instruction-cache
@@ -146,26 +220,28 @@ __device__ __forceinline__ void relu_inplace(uint32_t base)
 {
 #pragma unroll 1
     for (int c = 0; c < W / 16; ++c) {
-        float v[16];
-        ld8f(base + 16 * c, v);
-        ld8f(base + 16 * c + 8, v + 8);
+        float2 v[8];
+        ld16p(base + 16 * c, v);
         tmem_wait_ld();
         uint32_t h[8], l[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split2_relu(v[2 * i], v[2 * i + 1], h[i], l[i]);
-        st4u(base + 16 * c, h);
-        st4u(base + 16 * c + 4, h + 4);
-        st4u(base + 16 * c + 8, l);
-        st4u(base + 16 * c + 12, l + 4);
+        for (int i = 0; i < 8; ++i) split2_relu(v[i], h[i], l[i]);
+        st8u(base + 16 * c, h);
+        st8u(base + 16 * c + 8, l);
     }
 }
 
-__device__ __forceinline__ void rotate13(const float *s, float *o)   // cadrl.py:239-274, see lookahead.cu
+// cadrl.py:239-274 (see lookahead.cu for the literal form).  cos / sin of rot = atan2(dy, dx) are dx / |d| and dy / |d|
+// (atan2(0, 0) = 0 -> 1, 0): the same rotation to ~1 ulp without the three transcendental calls.
+template <int OPT>
+__device__ __forceinline__ void rotate13(const float *s, float *o)
 {
     const float dx = s[5] - s[0], dy = s[6] - s[1];
-    const float rot = atan2f(dy, dx);
-    const float c = cosf(rot), sn = sinf(rot);
-    o[0] = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    const float dg = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    const float inv = dg > 0.0f ? 1.0f / dg : 0.0f;
+    float c = dg > 0.0f ? dx * inv : 1.0f, sn = dy * inv;
+    if (OPT & 2) { const float rot = atan2f(dy, dx); c = cosf(rot); sn = sinf(rot); }
+    o[0] = dg;
     o[1] = s[7];
     o[2] = 0.0f;
     o[3] = s[4];
@@ -313,6 +389,8 @@ __device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t rin
 #define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 16, 8, false, 2>(ir, wfull, ring, tm, a, d, false)   /* in-place 2 x 4 x [8|8] */
 #define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 16, 8, false, 1>(ir, wfull, ring, tm, a, d, acc) /* in-place 2 x 3 x [8|8] */
 
+// OPT bit 0: only warp 0 polls the commit mbarrier of a group, the other warps sleep on a hardware barrier
+template <int OPT>
 __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArgs args)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -320,11 +398,8 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     float *kv = reinterpret_cast<float *>(wbuf + (size_t)NBUF * WBUF_BYTES);
     float *pblk = kv + 128 * KV_PITCH;
     float *sx = pblk + PBLK_MAX;                                 // [4][128] exchange
-    int *s_cnt = reinterpret_cast<int *>(sx + 4 * 128);
-    int *s_act = s_cnt + 32;
-    int *s_need = s_act + 32;
-    int *s_flag = s_need + 32;
-    uint64_t *wfull = reinterpret_cast<uint64_t *>(s_flag + 4);
+    int *s_need = reinterpret_cast<int *>(sx + 4 * 128);         // [3 steps][32 samples]: the sample goes on after this step
+    uint64_t *wfull = reinterpret_cast<uint64_t *>(s_need + 96 + 4);
     uint64_t *evb = wfull + NBUF;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(evb + NEV);
     __shared__ Issuer s_iss;
@@ -379,10 +454,20 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         if (warp == 0) tc_fence_after();    \
     } while (0)
 #define COMMIT(e) mma_commit(&evb[(e) % NEV])
-#define WAIT_EVENT(e)                                                   \
+#define WAIT_EVENT_POLL(e)                                              \
     do {                                                                \
         mbar_wait(&evb[(e) % NEV], (uint32_t)(((e) / NEV) & 1));        \
         tc_fence_after();                                               \
+    } while (0)
+#define WAIT_EVENT(e)                                                                   \
+    do {                                                                                \
+        if (OPT & 1) {                                                                  \
+            if (warp == 0) { mbar_wait(&evb[(e) % NEV], (uint32_t)(((e) / NEV) & 1)); tc_fence_before(); } \
+            asm volatile("bar.sync 5, 256;" ::: "memory");                              \
+            tc_fence_after();                                                           \
+        } else {                                                                        \
+            WAIT_EVENT_POLL(e);                                                         \
+        }                                                                               \
     } while (0)
 #define ISSUE_BEGIN() \
     IssReg ir;        \
@@ -405,7 +490,13 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     } while (0)
 
     const float *PB = pblk;
-#ifdef AEM_H16_MARKS
+#if defined(AEM_H16_TIMELINE)
+    // clock64 stamps of three threads of CTA 0 (issuer warp, producer warp, last warp) over one steady-state tile
+    int tl_n = 0;
+    const int tl_slot = tid == 0 ? 0 : (tid == 32 ? 1 : (tid == 255 ? 2 : -1));
+#define MARK() do { if (args.dbg && tl_slot >= 0 && blockIdx.x == 0 && tile == (int)(2 * gridDim.x) && tl_n < 500) { \
+        args.dbg[tl_slot * 512 + tl_n++] = (clock64() << 12) | (long long)__LINE__; } } while (0)
+#elif defined(AEM_H16_MARKS)
 #define MARK() do { if (args.dbg && (tid == 0 || tid == 32)) { ((volatile long long *)args.dbg)[2 * blockIdx.x + (tid == 32)] = __LINE__ + 10000ll * tile; __threadfence_system(); } } while (0)
 #else
 #define MARK() do { } while (0)
@@ -417,11 +508,15 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         const int nsamp = min(S, args.total_samples - s0);
         const int nrows = nsamp * T;
 
-        float xh[7], selfs[3], ACC[25], hn[25], z[25];
+        // per-thread state: this thread's 25 hidden columns as 13 pairs (slot 25 is a padding column and stays 0)
+        float2 ACC[13], hn[13], z[13];
+        float selfs[3], xh0 = 0.0f;
+        uint32_t xph[3], xpl[3];                         // x slots 1..6 of this half as split pairs (columns 13..15 of the operand)
         float P = 0.0f;
         int samp = -1, tok = 0;
 #pragma unroll
-        for (int j = 0; j < 25; ++j) { ACC[j] = 0.0f; hn[j] = 0.0f; }
+        for (int j = 0; j < 13; ++j) { ACC[j] = bc2(0.0f); hn[j] = bc2(0.0f); }
+        MARK();
 
         // ---------------- phase 0: inputs -> A1 = [h = 0 ; x] ----------------
         {
@@ -450,7 +545,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     in14[7] = (float)rb[7]; in14[8] = (float)rb[8];
 #pragma unroll
                     for (int k = 0; k < 5; ++k) in14[9 + k] = (float)hb[k];
-                    rotate13(in14, o);
+                    rotate13<OPT>(in14, o);
                 } else if (args.mode == 1) {
                     const int hi = (tok == 0) ? 0 : tok - 1;
                     const float *src = args.states + ((size_t)gs * args.n + hi) * XD;
@@ -467,28 +562,40 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     o[6] = 0.0f; o[7] = 0.0f; o[8] = o[4]; o[9] = o[5]; o[10] = o[3]; o[11] = 0.0f; o[12] = o[3];
                 }
             }
+            float xh[7];
 #pragma unroll
             for (int i = 0; i < 7; ++i) xh[i] = half ? (i < 6 ? o[7 + (i < 6 ? i : 0)] : 1.0f) : o[i];   // slot 31 of half 1 = 1 (bias)
-            float v[32];
+            xh0 = xh[0];
 #pragma unroll
-            for (int j = 0; j < 25; ++j) v[j] = 0.0f;
+            for (int i = 0; i < 3; ++i) split2(f2(xh[1 + 2 * i], xh[2 + 2 * i]), xph[i], xpl[i]);
+            // A1 block: columns 0..11 = h = 0, column 12 = (h24 = 0, x0), columns 13..15 = x1..x6
+            const uint32_t a1 = tl + A1 + 16 * half;
+            float2 v[13];
 #pragma unroll
-            for (int i = 0; i < 7; ++i) v[25 + i] = xh[i];
-            st_pack<32>(tl + A1 + 16 * half, tl + A1 + 32 + 16 * half, v);
-            if (tid < 32) { s_cnt[tid] = 0; s_act[tid] = (tid < nsamp) ? 1 : 0; s_need[tid] = 0; }
+            for (int j = 0; j < 13; ++j) v[j] = bc2(0.0f);
+            v[12].y = xh0;
+            st16_split<OPT>(a1, v, xph[0], xph[1], xph[2], xpl[0], xpl[1], xpl[2]);
+            if (tid < 96) s_need[tid] = 0;
         }
 
         // ---------------- phase 1: GRU + adaptive computation time ----------------
         const int max_steps = net.act_fixed ? net.act_steps : 3;
+        bool active = samp >= 0;
+        int cnt = 0;
+        MARK(); GROUP_BARRIER();
 #pragma unroll 1
         for (int step = 1; step <= max_steps; ++step) {
             const bool kfull = step > 1;
             // ---- the two gates share one copy of the code (instruction-cache footprint): gate 0 = z, gate 1 = r
             //      layer 1 -> in place A2 (K = 128), layer 2 -> z, or r and [r*h ; x] -> A3.  The ring delivers the weight
             //      images in the order Z1, Z2, R1, R2; step 1 has h = 0 and needs z only.
-#pragma unroll 1
-            for (int gate = 0; gate < (kfull ? 2 : 1); ++gate) {
-                MARK(); GROUP_BARRIER();
+            //      The group barrier of gate 0 is the halting vote of the previous step (or the barrier above).
+            // (fully unrolled: with the loop rolled, ptxas 12.9 assigned the tcgen05.ld destinations of the second iteration
+            //  to registers that still held z of the first one -- round-2 finding, profiles/r02_lookahead_h16_ncu.md)
+#pragma unroll
+            for (int gate = 0; gate < 2; ++gate) {
+                if (gate == 1 && !kfull) break;
+                if (gate || (OPT & 16)) { MARK(); GROUP_BARRIER(); }
                 const int e_g1 = nev++;
                 if (warp == 0) {
                     ISSUE_BEGIN();
@@ -512,27 +619,17 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 __syncwarp();
                 MARK(); WAIT_EVENT(e_g2); MARK();
                 PRODUCE(e_g2); MARK();
+                float2 v[13];
+                ld26p<OPT>(tl + D2 + 32 * half, v);
+                tmem_wait_ld();
                 if (gate == 0) {
-                    float v[32];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) ld8f(tl + D2 + 32 * half + 8 * c, v + 8 * c);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 25; ++j) z[j] = sigmoidf_(fmaxf(v[j], 0.0f));
+                    for (int j = 0; j < 13; ++j) z[j] = sigmoid_relu2<OPT>(v[j]);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float v[8];
-                        ld8f(tl + D2 + 32 * half + 8 * c, v);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int s = 8 * c + j;
-                            if (s < 25) v[j] = __fmul_rn(sigmoidf_(fmaxf(v[j], 0.0f)), hn[s]);
-                            else v[j] = xh[s - 25];
-                        }
-                        st8_pack(tl + A3 + 16 * half + 4 * c, tl + A3 + 32 + 16 * half + 4 * c, v);
-                    }
+                    for (int j = 0; j < 13; ++j) v[j] = mul2(sigmoid_relu2<OPT>(v[j]), hn[j]);
+                    v[12].y = xh0;
+                    st16_split<OPT>(tl + A3 + 16 * half, v, xph[0], xph[1], xph[2], xpl[0], xpl[1], xpl[2]);
                 }
             }
             // ---- q, h = (1 - z) h + z q
@@ -549,57 +646,57 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             MARK(); WAIT_EVENT(e_q); MARK();
             PRODUCE(e_q); MARK();
             {
-                const float *pw = PB + PB_PW + 25 * half;
-                float pd = 0.0f;
+                float2 v[13];
+                ld26p<OPT>(tl + D2 + 32 * half, v);
+                tmem_wait_ld();
+                const float4 *pw = reinterpret_cast<const float4 *>(PB + PB_PW + 28 * half);
+                float2 pd = bc2(0.0f);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float v[8];
-                    ld8f(tl + D2 + 32 * half + 8 * c, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int s = 8 * c + j;
-                        if (s < 25) {
-                            const float qv = tanhf_(v[j]);
-                            hn[s] = __fadd_rn(__fmul_rn(1.0f - z[s], hn[s]), __fmul_rn(z[s], qv));
-                            pd = fmaf(hn[s], pw[s], pd);
-                            v[j] = hn[s];
-                        } else {
-                            v[j] = xh[s - 25];
-                        }
+                for (int j = 0; j < 13; ++j) {
+                    const float2 qv = tanh2<OPT>(v[j]);
+                    if (OPT & 32) {
+                        hn[j].x = __fadd_rn(__fmul_rn(1.0f - z[j].x, hn[j].x), __fmul_rn(z[j].x, qv.x));
+                        hn[j].y = __fadd_rn(__fmul_rn(1.0f - z[j].y, hn[j].y), __fmul_rn(z[j].y, qv.y));
+                    } else {
+                        hn[j] = fma2(z[j], sub2(qv, hn[j]), hn[j]);
                     }
-                    st8_pack(tl + A1 + 16 * half + 4 * c, tl + A1 + 32 + 16 * half + 4 * c, v);
+                    if (j == 12) hn[12].y = 0.0f;                  // padding column
+                    const float4 w4 = pw[j >> 1];
+                    pd = fma2(hn[j], (j & 1) ? f2(w4.z, w4.w) : f2(w4.x, w4.y), pd);
+                    v[j] = hn[j];
                 }
+                v[12].y = xh0;
+                st16_split<OPT>(tl + A1 + 16 * half, v, xph[0], xph[1], xph[2], xpl[0], xpl[1], xpl[2]);
                 if (!net.act_fixed) {
-                    sx[half * 128 + row] = pd;
+                    sx[half * 128 + row] = pd.x + pd.y;
                     pair_sync(q4);
-                    const bool active = samp >= 0 && s_act[samp];
                     if (active) {
-                        const float p = sigmoidf_(sx[row] + sx[128 + row] + PB[PB_PW + 50]);
+                        const float p = (OPT & 4) ? sigmoid_legacy(sx[row] + sx[128 + row] + PB[PB_PWB]) : sigmoidf_(sx[row] + sx[128 + row] + PB[PB_PWB]);
                         P += p;
 #pragma unroll
-                        for (int j = 0; j < 25; ++j) ACC[j] = __fadd_rn(ACC[j], __fmul_rn(p, hn[j]));
-                        if (half == 0 && P < 0.95f) s_need[samp] = 1;
+                        for (int j = 0; j < 13; ++j) ACC[j] = fma2(bc2(p), hn[j], ACC[j]);
+                        cnt = step;
+                        if (half == 0 && P < 0.95f) s_need[(step - 1) * 32 + samp] = 1;
                     }
+                } else {
+                    cnt = step;
                 }
             }
+            // ---- halting vote (components.py:132-134, per (env, action) sample): one barrier, which is also the group
+            //      barrier of the next step's first gate
+            MARK();
+            tmem_wait_st();
+            tc_fence_before();
             int cont;
             if (net.act_fixed) {
-                if (tid < 32 && tid < nsamp) s_cnt[tid] = step;
+                __syncthreads();
                 cont = step < max_steps;
             } else {
-                if (tid == 0) s_flag[0] = 0;
-                __syncthreads();
-                if (tid < 32 && s_act[tid]) {
-                    s_cnt[tid] = step;
-                    const int need = s_need[tid];
-                    s_act[tid] = need;
-                    s_need[tid] = 0;
-                    if (need) s_flag[0] = 1;
-                }
-                __syncthreads();
-                cont = s_flag[0] && step < max_steps;
+                const int any = __syncthreads_or(active && P < 0.95f);
+                cont = any && step < max_steps;
+                active = active && s_need[(step - 1) * 32 + samp] != 0;
             }
+            if (warp == 0) tc_fence_after();
             if (tid == 32 && s_iss.pf_stage == -1) {
                 int ns;
                 if (cont) ns = 1;
@@ -611,37 +708,33 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             }
             if (!cont) break;
         }
-        __syncthreads();
 
-        float xres[25];
+        float2 xres[13];
         {
-            const float cnt = (samp >= 0) ? (float)s_cnt[samp] : 1.0f;
-            const float rc = __fdividef(1.0f, cnt);
+            const float rc = rcpf((float)max(cnt, 1));
 #pragma unroll
-            for (int j = 0; j < 25; ++j) xres[j] = net.act_fixed ? hn[j] : (samp >= 0 ? ACC[j] * rc : 0.0f);
+            for (int j = 0; j < 13; ++j) xres[j] = net.act_fixed ? hn[j] : (samp >= 0 ? mul2(ACC[j], bc2(rc)) : bc2(0.0f));
         }
         if (args.mode == 2) {
             if (row < nrows) {
                 float *dst = args.gru_out + ((size_t)(s0 + samp) * T + tok) * HID + 25 * half;
 #pragma unroll
-                for (int j = 0; j < 25; ++j) dst[j] = xres[j];
-                if (args.steps && half == 0 && tok == 0) args.steps[s0 + samp] = (uint8_t)s_cnt[samp];
+                for (int j = 0; j < 12; ++j) { dst[2 * j] = xres[j].x; dst[2 * j + 1] = xres[j].y; }
+                dst[24] = xres[12].x;
+                if (args.steps && half == 0 && tok == 0) args.steps[s0 + samp] = (uint8_t)cnt;
             }
             __syncthreads();
             continue;
         }
+        // constant columns 13..15 of the encoder operands: zeros and the bias slot (slot 31 of half 1 = 1.0)
+        const uint32_t one_hi = half ? 0x3C000000u : 0u;
         {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = j < 25 ? xres[j] : 0.0f;
-            if (half) v[31] = 1.0f;                                   // constant slot (bias)
-            st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, v);
+            st16_split<OPT>(tl + AE + 16 * half, xres, 0u, 0u, one_hi, 0u, 0u, 0u);
         }
 
         // ---------------- phase 2: 3 x post-norm encoder layer ----------------
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
-            const float *LN = PB + PB_LN + l * 200 + 25 * half;
             MARK(); GROUP_BARRIER();
             const int e_in = nev++;
             if (warp == 0) {
@@ -657,70 +750,90 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             // exact saving: the last layer needs k / v of every token but q, out_proj, FFN and LayerNorm of
             // token 0 only: warps without a token-0 row skip those epilogues (their MMA rows compute garbage nobody reads)
             const bool live = l < 2 || q4 * 32 < nsamp;
-            float o[32];
+            float2 o[13];
             {
-                // q stays in registers (28 slots, the last 3 zero); k and v of this head go to shared memory as 7 float4
-                // each: row = [k head 0 (28) | k head 1 (28) | v head 0 (28) | v head 1 (28)].  Accumulator columns 25..31
-                // of every block are padding neurons and exactly zero.
-                float qh[28];
+                // q stays in registers (28 slots, the last 3 zero) scaled by log2(e) / sqrt(head_dim = 25); k and v of this
+                // head go to shared memory as 7 float4 each: row = [k head 0 (28) | k head 1 (28) | v head 0 (28) | v head 1
+                // (28)].  Accumulator columns 25..31 of every block are padding neurons and exactly zero.
+                float2 qh[14];
                 {
+                    const uint32_t din = tl + DIN + 96 * half;
                     float4 *dst = reinterpret_cast<float4 *>(kv + row * KV_PITCH + 28 * half);
+                    float2 t[14];
+                    ld16p(din + 32, t); ld8p(din + 48, t + 8); ld4p(din + 56, t + 12);          // k
+                    tmem_wait_ld();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {          // q | k | v blocks of 32 columns each
-                        float a[8], k[8], v[8];
-                        ld8f(tl + DIN + 96 * half + 8 * c, a);
-                        ld8f(tl + DIN + 96 * half + 32 + 8 * c, k);
-                        ld8f(tl + DIN + 96 * half + 64 + 8 * c, v);
-                        tmem_wait_ld();
+                    for (int c = 0; c < 7; ++c) dst[c] = make_float4(t[2 * c].x, t[2 * c].y, t[2 * c + 1].x, t[2 * c + 1].y);
+                    ld16p(din + 64, t); ld8p(din + 80, t + 8); ld4p(din + 88, t + 12);          // v
+                    tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (8 * c + j < 28) qh[8 * c + j] = a[j] * 0.2f;       // 1 / sqrt(head_dim = 25)
-                        dst[2 * c] = make_float4(k[0], k[1], k[2], k[3]);
-                        dst[14 + 2 * c] = make_float4(v[0], v[1], v[2], v[3]);
-                        if (c < 3) {
-                            dst[2 * c + 1] = make_float4(k[4], k[5], k[6], k[7]);
-                            dst[14 + 2 * c + 1] = make_float4(v[4], v[5], v[6], v[7]);
-                        }
-                    }
+                    for (int c = 0; c < 7; ++c) dst[14 + c] = make_float4(t[2 * c].x, t[2 * c].y, t[2 * c + 1].x, t[2 * c + 1].y);
+                    ld16p(din, qh); ld8p(din + 16, qh + 8); ld4p(din + 24, qh + 12);            // q
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 14; ++c) qh[c] = mul2(qh[c], bc2(0.2f * LOG2E));
                 }
                 tc_fence_before();
                 __syncthreads();       // every thread has consumed D_IN and published k / v
+                float2 oo[14];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = 0.0f;
+                for (int j = 0; j < 14; ++j) oo[j] = bc2(0.0f);
                 if (samp >= 0 && live) {
-                    // one pass over the T keys of the sample with a running maximum (streaming softmax);
+                    // one pass over the T keys of the sample with a running maximum (streaming softmax, log2 domain);
                     // key 0 is the sample's token-0 row, keys 1.. are its block of human rows
                     const float *kb = kv + samp * KV_PITCH + 28 * half;
-                    const float *kb_rest = kv + (nsamp + samp * (T - 1)) * KV_PITCH + 28 * half;
-                    float m = -INFINITY, sum = 0.0f;
-                    for (int j = 0; j < T; ++j, kb = (j == 1 ? kb_rest : kb + KV_PITCH)) {
+                    float m, sum = 1.0f;
+                    {
                         const float4 *kp = reinterpret_cast<const float4 *>(kb);
-                        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+                        float2 d0 = bc2(0.0f), d1 = bc2(0.0f);
 #pragma unroll
                         for (int c = 0; c < 7; ++c) {
                             const float4 k4 = kp[c];
-                            d0 = fmaf(qh[4 * c], k4.x, d0); d1 = fmaf(qh[4 * c + 1], k4.y, d1);
-                            d2 = fmaf(qh[4 * c + 2], k4.z, d2); d3 = fmaf(qh[4 * c + 3], k4.w, d3);
+                            d0 = fma2(qh[2 * c], f2(k4.x, k4.y), d0);
+                            d1 = fma2(qh[2 * c + 1], f2(k4.z, k4.w), d1);
                         }
-                        const float sc = (d0 + d1) + (d2 + d3);
-                        const float mn = fmaxf(m, sc);
-                        const float rescale = __expf(m - mn), p = __expf(sc - mn);
-                        m = mn;
-                        sum = fmaf(sum, rescale, p);
+                        d0 = add2(d0, d1);
+                        m = d0.x + d0.y;
 #pragma unroll
                         for (int c = 0; c < 7; ++c) {
                             const float4 v4 = kp[14 + c];
-                            o[4 * c] = fmaf(p, v4.x, o[4 * c] * rescale); o[4 * c + 1] = fmaf(p, v4.y, o[4 * c + 1] * rescale);
-                            o[4 * c + 2] = fmaf(p, v4.z, o[4 * c + 2] * rescale); o[4 * c + 3] = fmaf(p, v4.w, o[4 * c + 3] * rescale);
+                            oo[2 * c] = f2(v4.x, v4.y);
+                            oo[2 * c + 1] = f2(v4.z, v4.w);
                         }
                     }
-                    const float inv = __fdividef(1.0f, sum);
+                    kb = kv + (nsamp + samp * (T - 1)) * KV_PITCH + 28 * half;
+                    for (int j = 1; j < T; ++j, kb += KV_PITCH) {
+                        const float4 *kp = reinterpret_cast<const float4 *>(kb);
+                        float2 d0 = bc2(0.0f), d1 = bc2(0.0f);
 #pragma unroll
-                    for (int c = 0; c < 25; ++c) o[c] *= inv;
+                        for (int c = 0; c < 7; ++c) {
+                            const float4 k4 = kp[c];
+                            d0 = fma2(qh[2 * c], f2(k4.x, k4.y), d0);
+                            d1 = fma2(qh[2 * c + 1], f2(k4.z, k4.w), d1);
+                        }
+                        d0 = add2(d0, d1);
+                        const float sc = d0.x + d0.y;
+                        const float mn = fmaxf(m, sc);
+                        const float rescale = ex2f(m - mn), p = ex2f(sc - mn);
+                        m = mn;
+                        sum = fmaf(sum, rescale, p);
+                        const float2 r2 = bc2(rescale), p2 = bc2(p);
+#pragma unroll
+                        for (int c = 0; c < 7; ++c) {
+                            const float4 v4 = kp[14 + c];
+                            oo[2 * c] = fma2(p2, f2(v4.x, v4.y), mul2(oo[2 * c], r2));
+                            oo[2 * c + 1] = fma2(p2, f2(v4.z, v4.w), mul2(oo[2 * c + 1], r2));
+                        }
+                    }
+                    const float2 inv = bc2(rcpf(sum));
+#pragma unroll
+                    for (int c = 0; c < 13; ++c) oo[c] = mul2(oo[c], inv);
                 }
+#pragma unroll
+                for (int c = 0; c < 13; ++c) o[c] = oo[c];
+                o[12].y = 0.0f;
             }
-            if (half) o[31] = 1.0f;                                       // constant slot (bias)
-            if (live) st_pack<32>(tl + AATT + 16 * half, tl + AATT + 32 + 16 * half, o);
+            if (live) st16_split<OPT>(tl + AATT + 16 * half, o, 0u, 0u, one_hi, 0u, 0u, 0u);
             // ---- out_proj + residual + LayerNorm1
             MARK(); GROUP_BARRIER();
             const int e_out = nev++;
@@ -758,7 +871,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                         if (live) relu_inplace<48>(tl + (c ? DF1B : DF1A) + 48 * half);
                         MARK(); GROUP_BARRIER();
                         if (warp == 0) {
-                            if (c == 0) WAIT_EVENT(e_f1 + 1);   // F1B reads AE, which D_F2 aliases: complete before linear2 starts
+                            if (c == 0) WAIT_EVENT_POLL(e_f1 + 1);   // F1B reads AE, which D_F2 aliases: complete before linear2 starts
                             ISSUE_BEGIN();
                             ISSUE_K96(64, c ? DF1B : DF1A, DF2, c != 0);
                             if (c) ISSUE_COMMIT(e_f2);
@@ -770,21 +883,24 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     PRODUCE(e_f2); MARK();
                 }
                 if (!live) continue;
-                const float *g = LN + 100 * pass;
-                float s = 0.0f;
+                float2 s2 = bc2(0.0f);
                 {
-                    float v[32];
-                    const uint32_t dcol = tl + (pass ? DF2 : DOUT) + 32 * half;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) ld8f(dcol + 8 * c, v + 8 * c);
+                    float2 v[13];
+                    ld26p<OPT>(tl + (pass ? DF2 : DOUT) + 32 * half, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 25; ++j) { xres[j] += v[j]; s += xres[j]; }
+                    for (int j = 0; j < 13; ++j) { xres[j] = add2(xres[j], v[j]); s2 = add2(s2, xres[j]); }
                 }
+                const float s = s2.x + s2.y;                    // the padding column is zero
                 const float mh = s * 0.04f;
-                float ss = 0.0f;
+                float2 ss2 = bc2(0.0f);
 #pragma unroll
-                for (int j = 0; j < 25; ++j) { const float dd = xres[j] - mh; ss = fmaf(dd, dd, ss); }
+                for (int j = 0; j < 13; ++j) {
+                    float2 dd = sub2(xres[j], bc2(mh));
+                    if (j == 12) dd.y = 0.0f;
+                    ss2 = fma2(dd, dd, ss2);
+                }
+                const float ss = ss2.x + ss2.y;
                 sx[half * 128 + row] = s;
                 sx[256 + half * 128 + row] = ss;
                 tc_fence_before();
@@ -793,14 +909,21 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 const float mean = (s + so) * 0.02f;
                 const float dm = (s - so) * 0.04f;
                 const float rstd = rsqrtf((ss + sso + dm * dm * 12.5f) * 0.02f + 1e-5f);
-                float a[32];
+                const float4 *g4 = reinterpret_cast<const float4 *>(PB + PB_LN + (((l * 2 + pass) * 2 + half) * 56));
+                float2 a[13];
 #pragma unroll
-                for (int j = 0; j < 25; ++j) { xres[j] = (xres[j] - mean) * rstd * g[j] + g[50 + j]; a[j] = xres[j]; }
-#pragma unroll
-                for (int j = 25; j < 32; ++j) a[j] = 0.0f;
-                if (pass == 1 && l == 2) { a[25] = selfs[0]; a[26] = selfs[1]; a[27] = selfs[2]; }     // joint = [self_state ; env]
-                if (half) a[31] = 1.0f;                                   // constant slot (bias)
-                st_pack<32>(tl + AE + 16 * half, tl + AE + 32 + 16 * half, a);
+                for (int j = 0; j < 13; ++j) {
+                    const float4 gg = g4[j >> 1], bb = g4[7 + (j >> 1)];
+                    const float2 t = mul2(sub2(xres[j], bc2(mean)), bc2(rstd));
+                    xres[j] = fma2(t, (j & 1) ? f2(gg.z, gg.w) : f2(gg.x, gg.y), (j & 1) ? f2(bb.z, bb.w) : f2(bb.x, bb.y));
+                    a[j] = xres[j];
+                }
+                uint32_t h13 = 0u, l13 = 0u;
+                if (pass == 1 && l == 2) {                                    // joint = [self_state ; env]
+                    a[12].y = selfs[0];
+                    split2(f2(selfs[1], selfs[2]), h13, l13);
+                }
+                st16_split<OPT>(tl + AE + 16 * half, a, h13, 0u, one_hi, l13, 0u, 0u);
             }
         }
 
@@ -830,27 +953,27 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         MARK(); WAIT_EVENT(e_a2); MARK();
         PRODUCE(e_a2); MARK();
         if (live_a) {
-            const float *w4 = PB + PB_A4 + 25 * half;
-            float pd = 0.0f;
+            const float4 *w4 = reinterpret_cast<const float4 *>(PB + PB_A4 + 28 * half);
+            float2 pd = bc2(0.0f);
+            float2 v[13];
+            ld26p<OPT>(tl + DA2 + 32 * half, v);
+            tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float v[8];
-                ld8f(tl + DA2 + 32 * half + 8 * c, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (8 * c + j < 25) pd = fmaf(fmaxf(v[j], 0.0f), w4[8 * c + j], pd);
+            for (int j = 0; j < 13; ++j) {
+                const float4 ww = w4[j >> 1];
+                pd = fma2(f2(fmaxf(v[j].x, 0.0f), fmaxf(v[j].y, 0.0f)), (j & 1) ? f2(ww.z, ww.w) : f2(ww.x, ww.y), pd);
             }
-            sx[half * 128 + row] = pd;
+            sx[half * 128 + row] = pd.x + pd.y;
             pair_sync(q4);
             if (half == 0 && samp >= 0 && tok == 0) {
-                const float val = sx[row] + sx[128 + row] + PB[PB_A4 + 50];
+                const float val = sx[row] + sx[128 + row] + PB[PB_A4B];
                 const int gs = s0 + samp;
                 if (args.net_values) args.net_values[gs] = val;
                 if (args.values) args.values[gs] = __dadd_rn(args.rewards[gs], __dmul_rn(args.gamma_bar, (double)val));
-                if (args.steps) args.steps[gs] = (uint8_t)s_cnt[samp];
+                if (args.steps) args.steps[gs] = (uint8_t)cnt;
             }
         }
+        MARK();
         __syncthreads();
     }
 
@@ -868,6 +991,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #undef GROUP_BARRIER
 #undef COMMIT
 #undef WAIT_EVENT
+#undef WAIT_EVENT_POLL
 #undef ISSUE_BEGIN
 #undef ISSUE_COMMIT
 #undef ISSUE_END
@@ -879,10 +1003,30 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStream_t st)
 {
     static bool attr_set[64] = {false};
+    static int opt = -1;
+    if (opt < 0) {
+        const char *e = getenv("AEM_H16_OPT");
+        opt = e ? atoi(e) : 0;
+    }
+    void (*kern)(const LookaheadArgs) = h16::lookahead_h16_kernel<0>;
+    switch (opt) {
+    case 1: kern = h16::lookahead_h16_kernel<1>; break;
+    case 2: kern = h16::lookahead_h16_kernel<2>; break;
+    case 4: kern = h16::lookahead_h16_kernel<4>; break;
+    case 8: kern = h16::lookahead_h16_kernel<8>; break;
+    case 14: kern = h16::lookahead_h16_kernel<14>; break;
+    case 16: kern = h16::lookahead_h16_kernel<16>; break;
+    case 32: kern = h16::lookahead_h16_kernel<32>; break;
+    default: break;
+    }
     if (!attr_set[h->device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(h16::lookahead_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)h16::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
+        void (*all[])(const LookaheadArgs) = {h16::lookahead_h16_kernel<0>, h16::lookahead_h16_kernel<1>, h16::lookahead_h16_kernel<2>,
+                                              h16::lookahead_h16_kernel<4>, h16::lookahead_h16_kernel<8>, h16::lookahead_h16_kernel<14>,
+                                              h16::lookahead_h16_kernel<16>, h16::lookahead_h16_kernel<32>};
+        for (auto k : all) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h16::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+        }
         attr_set[h->device & 63] = true;
     }
     const int ntiles = (a.total_samples + a.S - 1) / a.S;
@@ -896,12 +1040,30 @@ cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStrea
         stagger = e ? atoi(e) : 0;
     }
     b.stagger_ns = stagger;
+#if defined(AEM_H16_TIMELINE)
+    if (const char *path = getenv("AEM_H16_TIMELINE")) {       // debug build: clock64 stamps of CTA 0, third tile -> file
+        long long *host = nullptr;
+        cudaHostAlloc((void **)&host, 3 * 512 * sizeof(long long), cudaHostAllocMapped);
+        for (int i = 0; i < 3 * 512; ++i) host[i] = 0;
+        b.dbg = host;
+        kern<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (FILE *f = fopen(path, "w")) {
+            for (int s = 0; s < 3; ++s)
+                for (int i = 0; i < 512 && host[s * 512 + i]; ++i)
+                    fprintf(f, "%d %lld %lld\n", s, host[s * 512 + i] & 4095, host[s * 512 + i] >> 12);
+            fclose(f);
+        }
+        cudaFreeHost(host);
+        return e;
+    }
+#endif
     if (getenv("AEM_H16_WATCHDOG")) {       // debug: report where CTA 0 is stuck instead of hanging
         long long *host = nullptr;
         cudaHostAlloc((void **)&host, 16 * 1024, cudaHostAllocMapped);
         for (int i = 0; i < 2048; ++i) host[i] = 0;
         b.dbg = host;
-        h16::lookahead_h16_kernel<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
+        kern<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
         for (int i = 0; i < 300; ++i) {
             if (cudaStreamQuery(st) != cudaErrorNotReady) { cudaFreeHost(host); return cudaGetLastError(); }
             struct timespec ts = {0, 10000000};
@@ -915,7 +1077,7 @@ cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStrea
         }
         _exit(3);
     }
-    h16::lookahead_h16_kernel<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
+    kern<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
     return cudaGetLastError();
 }
 

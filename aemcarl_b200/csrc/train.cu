@@ -1005,6 +1005,7 @@ cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, c
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
         cudaFree(h->tr_part); cudaFree(h->tr_sqerr); cudaFree(h->tr_flags); cudaFree(h->tr_stash); cudaFree(h->tr_gru);
         h->tr_part = h->tr_sqerr = h->tr_stash = h->tr_gru = nullptr; h->tr_flags = nullptr;
+        ++h->tr_generation;
         h->tr_grid = grid > h->tr_grid ? grid : h->tr_grid;
         h->tr_B = B > h->tr_B ? B : h->tr_B;
         if ((e = cudaMalloc(&h->tr_part, (size_t)h->tr_grid * NUM_WEIGHTS * sizeof(float))) != cudaSuccess) return e;

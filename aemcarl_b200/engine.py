@@ -69,9 +69,9 @@ class Engine:
         check(self.lib.aem_set_act_mode(self.h, int(bool(act_fixed)), int(act_steps)))
 
     def set_precision(self, precision):
-        """'fp32' (FFMA kernel, default), 'tf32x3' (tcgen05, one tile / SM), 'fp16x3' (tcgen05, two tiles / SM, two threads per
-        row: the fastest) or 'fp16x3q' (tcgen05, one tile / SM, four threads per row: experimental)"""
-        mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2, "fp16x3q": 3, 0: 0, 1: 1, 2: 2, 3: 3}[precision]
+        """'fp32' (FFMA kernel, default: the parity anchor), 'tf32x3' (tcgen05, one tile / SM, FP32-range containers) or
+        'fp16x3' (tcgen05, two tiles / SM: the fastest, bench.py's default)"""
+        mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2, 0: 0, 1: 1, 2: 2}[precision]
         check(self.lib.aem_set_precision(self.h, mode))
         self.precision = mode
 
@@ -280,6 +280,10 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.aem_launch_count(self.h))
+
+    def train_scratch_generation(self):
+        """changes whenever the library reallocated the training scratch: captured graphs of train_step_adam are stale then"""
+        return int(self.lib.aem_train_scratch_generation(self.h))
 
 
 _ENGINES = {}

@@ -1,8 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- lookahead env-steps/s (predict + step) of the AEMCARL hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs B] [--humans n] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1|2|3|4] [--envs B] [--humans n] [--impl ours|reference]
     (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+--config selects a BASELINE.json configs[] entry (default 1, the one the headline metric is quoted on):
+  1  batched lookahead inference, 4096 envs x 5 humans x 81 actions per GPU, random-init weights (weak scaling)
+  2  square_crossing, 10 humans, 65,536 envs IN TOTAL split over the N ranks (strong scaling)
+  3  circle_crossing, 18 humans, 32,768 envs per GPU (262,144 on 8 GPUs; weak scaling)
+  4  the train.py loop: vectorised collection + fused optimisation step + NCCL gradient all-reduce; reports optimizer
+     steps/s, the share of the all-reduce (CUDA events around the NCCL call) and the collection throughput
 
 One "step" = one pass of the hot path over the whole batch: for every environment ORCA for the humans, the
 per-action env lookahead (collision / goal / timeout / occupancy reward), the fused 81-action value lookahead
@@ -131,7 +138,7 @@ def run_reference(args, rank, world):
     ns = args.ref_envs
     params = po.default_params()
     gbar = pow(0.9, params.time_step * 1.0)
-    robot, humans = scenarios.generate_pool("train", 0, ns, n, "circle_crossing")
+    robot, humans = scenarios.generate_pool("train", 0, ns, n, args.rule)
     gt = np.zeros(ns)
     pool_r, pool_h = robot.copy(), humans.copy()
     times = []
@@ -149,26 +156,136 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": METRIC.replace("5 humans", "%d humans" % args.humans), "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "batched lookahead inference: %d envs x %d humans x 81 actions, random-init weights"
-                                  % (args.envs, n), "envs_per_step": ns},
+           "config": {"baseline_config": CONFIGS.get(args.config, CONFIGS[1])["name"],
+                      "workload": "batched lookahead inference: %d envs x %d humans x 81 actions, random-init weights, %s"
+                                  % (args.envs, n, args.rule), "envs_per_step": ns},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
 
+CONFIGS = {
+    1: dict(humans=5, rule="circle_crossing", envs_per_gpu=4096, scaling="weak",
+            name="configs[1]: batched lookahead inference: 4096 envs x 5 humans x 81 actions, random-init weights"),
+    2: dict(humans=10, rule="square_crossing", total_envs=65536, scaling="strong",
+            name="configs[2]: square_crossing 10 humans, 65536 envs in total, ORCA human step + value lookahead"),
+    3: dict(humans=18, rule="circle_crossing", envs_per_gpu=32768, scaling="weak",
+            name="configs[3]: 18-human circle scenario, 262144 envs over 8 GPUs = 32768 envs per GPU, GRU env model + "
+                 "adaptive reward"),
+}
+
+
+def run_training(args, rank, local_rank, world):
+    """--config 4: BASELINE configs[4], the train.py loop (crowd_nav/train.py:171-246, utils/trainer.py:47-58,70-82) in its
+    data-parallel form: every rank collects experience on its own environments (VecExplorer + device replay memory) and
+    all ranks take the same optimizer steps on the all-reduced gradient (aem_train_grad -> NCCL all-reduce of the flat
+    113,752-float gradient -> aem_adam_step)."""
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from aemcarl_b200.crowd_nav import train
+    V = args.train_envs
+    out = tempfile.mkdtemp(prefix="aem_bench_train_%d_" % rank)
+    t0 = time.perf_counter()
+    # the entry point itself: imitation episodes + 1 imitation epoch, then ONE RL wave of V episodes per rank with 10 steps
+    res = train.main(["--no_final_test", "--output_dir", out, "--il_episodes", str(512 * world), "--il_epochs", "1", "--train_episodes",
+                      str(V * world), "--vectorised", str(V), "--fused_step", "--updates_per_wave", "10"])
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    dev = torch.device("cuda", local_rank)
+    trainer, vec = res["trainer"], res["explorer"].vec
+    dmem = vec.memory
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- experience collection: `waves` waves of V episodes per rank, epsilon 0.1
+    waves = max(1, args.train_waves)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    env_steps = pushed = 0
+    for w in range(waves):
+        st = vec.run_k_episodes(V, "train", update_memory=True, episode=0, epsilon=0.1,
+                                first_case=1000000 + (w * world + rank) * V)
+        env_steps += st["env_steps"]
+        pushed += st["pushed"]
+    torch.cuda.synchronize(); barrier()
+    collect_s = maxr(time.perf_counter() - t0)
+    env_steps, pushed = sumr(env_steps), sumr(pushed)
+
+    # ---- optimizer steps: Trainer.optimize_batch (draw a mini-batch of 100 from the device ring, forward + MSE + backward,
+    #      all-reduce, Adam); N = 1 uses the single-call / CUDA-graph path, N > 1 the all-reduced path
+    K, Wm = args.steps, max(args.warmup, 3)
+    trainer.optimize_batch(Wm)
+    fs = trainer._fused
+    fs.allreduce_events = [] if world > 1 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    e0.record()
+    loss = trainer.optimize_batch(K)
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    step_ms = maxr(e0.elapsed_time(e1)) / K
+    ar_ms = None
+    if world > 1:
+        ar_ms = maxr(float(np.mean([a.elapsed_time(b) for a, b in fs.allreduce_events])))
+        fs.allreduce_events = None
+    flat = fs.flat.clone()
+    same = True
+    if world > 1:
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+    if rank == 0:
+        out = {"metric": "train.py loop: optimizer steps/sec (batch 100 per rank, fused step + NCCL grad all-reduce)",
+               "value": 1e3 / step_ms, "unit": "optimizer-steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
+               "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 "
+               "mma.sync products, FP32 accumulate)", "data": "synthetic",
+               "config": {"workload": "configs[4]: full train.py loop (imitation warm-up + RL episodes) with NCCL value-net grad "
+                                      "all-reduce; batch 100 per rank (effective %d), %d collection envs per rank, 5 humans"
+                                      % (100 * world, V), "parallelism": "data-parallel x%d" % world},
+               "samples_per_s": 1e3 / step_ms * 100 * world,
+               "allreduce_ms": ar_ms, "allreduce_share_of_step": (ar_ms / step_ms) if ar_ms else None,
+               "allreduce_bytes": 113752 * 4, "loss": float(loss), "replicas_identical": bool(same),
+               "collection": {"episodes_per_s": waves * V * world / collect_s, "env_steps_per_s": env_steps / collect_s,
+                              "waves": waves, "envs_per_rank": V, "pairs_pushed": int(pushed), "seconds": collect_s},
+               "entry_point_setup_s": setup_s, "replay_pairs_rank0": len(dmem)}
+        print(json.dumps(out), flush=True)
+    if world > 1 and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="BASELINE.json configs[] entry (see the module docstring)")
+    ap.add_argument("--train-envs", type=int, default=512, help="--config 4: collection environments per rank")
+    ap.add_argument("--train-waves", type=int, default=2, help="--config 4: timed collection waves")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
-    ap.add_argument("--humans", type=int, default=5)
-    ap.add_argument("--rule", default="circle_crossing", choices=["circle_crossing", "square_crossing"])
+    ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default: the --config's)")
+    ap.add_argument("--humans", type=int, default=None)
+    ap.add_argument("--rule", default=None, choices=["circle_crossing", "square_crossing"])
     ap.add_argument("--pool", type=int, default=0, help="scenario pool size (default min(envs, 8192))")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-envs", type=int, default=256, help="--impl reference: envs per step (bounded sample)")
-    ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3", "fp16x3q"],
+    ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3"],
                     help="value-network GEMM arithmetic: tcgen05 FP16x3 with two tiles per SM (default), tcgen05 3xTF32, "
                          "or the FP32 FFMA kernel")
     ap.add_argument("--weights", default=None,
@@ -180,8 +297,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = CONFIGS.get(args.config, CONFIGS[1])
+    if args.humans is None:
+        args.humans = cfg["humans"]
+    if args.rule is None:
+        args.rule = cfg["rule"]
+    if args.envs is None:
+        args.envs = cfg["envs_per_gpu"] if "envs_per_gpu" in cfg else cfg["total_envs"] // world
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.config == 4:
+        if args.steps == 40:
+            args.steps = 2000
+        run_training(args, rank, local_rank, world)
         return
 
     import torch
@@ -296,7 +425,6 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "kernel": {"tf32x3": "lookahead_tc_kernel", "fp16x3": "lookahead_h16_kernel",
-                           "fp16x3q": "lookahead_q16_kernel",
                            "fp32": "lookahead_kernel"}[args.precision],
                 "kernel_ms": kernel_ms,
                 "kernel_share_of_step": float(look_ms.sum() / step_ms.sum()),
@@ -304,7 +432,6 @@ def main():
                 "pipe": {"tf32x3": "tcgen05 kind::tf32, 3xTF32 split (3 MMAs per product, FP32 accumulate in TMEM)",
                          "fp16x3": "tcgen05 kind::f16, FP16 hi/lo split (3 MMAs per product, FP32 accumulate in TMEM), "
                                    "2 tiles in flight per SM",
-                         "fp16x3q": "tcgen05 kind::f16, FP16 hi/lo split, four threads per row, fused gate groups",
                          "fp32": "fp32_ffma (no tensor-core math)"}[args.precision],
 
                 "fp32_pipe_peak_tflops": fp32_peak, "frac_fp32_pipe": achieved / fp32_peak,
@@ -348,13 +475,13 @@ def main():
     if rank == 0:
         out = {"metric": METRIC.replace("5 humans", "%d humans" % args.humans), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None,
+               "scaling": cfg["scaling"], "vs_baseline": None,
                "dtype": {"tf32x3": "tf32x3 (fp32-equivalent split, fp32 accumulate)",
                          "fp16x3": "fp16x3 (fp16 hi/lo split = 22 mantissa bits, fp32 accumulate)",
-                         "fp16x3q": "fp16x3 (fp16 hi/lo split = 22 mantissa bits, fp32 accumulate)",
                          "fp32": "f32"}[args.precision],
                "data": "synthetic",
-               "config": {"workload": "batched lookahead inference: %d envs x %d humans x 81 actions per GPU, "
+               "config": {"baseline_config": cfg["name"],
+                          "workload": "batched lookahead inference: %d envs x %d humans x 81 actions per GPU, "
                                       "%s, %s train-stream "
                                       "scenarios, predict + step" % (B, n, "random-init weights (synthetic_weights seed 0)"
                                                                      if not args.weights else "weights from " + args.weights,

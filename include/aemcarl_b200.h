@@ -228,6 +228,11 @@ int aem_decide_step_host(aem_handle h, int B, int n, double gamma_bar, double *r
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 long long aem_launch_count(aem_handle h);
 
+/* The scratch of aem_train_grad / aem_train_step_adam belongs to the handle and grows with the largest (batch, n) seen;
+ * this counter increments whenever it is reallocated.  A caller that captured aem_train_step_adam into a CUDA graph must
+ * re-capture when the value has changed (the graph holds the old pointers): crowd_nav/utils/trainer.py FusedStep. */
+long long aem_train_scratch_generation(aem_handle h);
+
 #ifdef __cplusplus
 }
 #endif

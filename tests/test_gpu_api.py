@@ -188,7 +188,7 @@ def test_train_entry_point_il_and_rl(tmp_path):
     """train.py flow end to end at a tiny size: IL episodes with the ORCA teacher fill the memory, the IL epochs reduce
     the loss, RL episodes run with epsilon-greedy predict, checkpoints carry the reference's state_dict keys."""
     from aemcarl_b200.crowd_nav import train
-    out = train.main(["--output_dir", str(tmp_path), "--il_episodes", "12", "--il_epochs", "8", "--train_episodes", "2"])
+    out = train.main(["--no_final_test", "--output_dir", str(tmp_path), "--il_episodes", "12", "--il_epochs", "8", "--train_episodes", "2"])
     assert out["memory"] > 100
     sd = torch.load(str(tmp_path / "il_model.pth"), map_location="cpu")
     assert "in_mlp.rnn_cell.convz.0.weight" in sd and "encoder_layer.linear1.weight" in sd and len(sd) == 66

@@ -97,7 +97,7 @@ def test_train_entry_point_with_the_vectorised_rl_phase(tmp_path):
     fill the device memory, the optimizer runs on device-gathered mini-batches, the target network is refreshed across a
     wave boundary."""
     from aemcarl_b200.crowd_nav import train
-    out = train.main(["--output_dir", str(tmp_path), "--il_episodes", "6", "--il_epochs", "2", "--train_episodes", "64",
+    out = train.main(["--no_final_test", "--output_dir", str(tmp_path), "--il_episodes", "6", "--il_epochs", "2", "--train_episodes", "64",
                       "--vectorised", "32", "--updates_per_wave", "4", "--cuda_graph"])
     ex = out["explorer"]
     assert out["memory"] == len(ex.device_memory) > 50         # imitation + RL experience, all in the device memory
@@ -111,7 +111,7 @@ def test_train_entry_point_with_the_fused_optimisation_step(tmp_path):
     """train.py --fused_step: imitation epochs and RL updates run through aem_train_grad + aem_adam_step (csrc/train.cu);
     the policy's lookahead engine keeps seeing the updated weights, the checkpoint holds the trained parameters."""
     from aemcarl_b200.crowd_nav import train
-    out = train.main(["--output_dir", str(tmp_path), "--il_episodes", "6", "--il_epochs", "2", "--train_episodes", "64",
+    out = train.main(["--no_final_test", "--output_dir", str(tmp_path), "--il_episodes", "6", "--il_epochs", "2", "--train_episodes", "64",
                       "--vectorised", "32", "--updates_per_wave", "4", "--fused_step"])
     model = out["model"]
     assert all(torch.isfinite(p).all() for p in model.parameters())

@@ -11,7 +11,7 @@ from aemcarl_b200 import scenarios
 from aemcarl_b200.crowd_nav.utils.explorer import run_vectorised_test
 from aemcarl_b200.engine import Engine, make_env_params
 from aemcarl_b200.vec_env import VecCrowdSim
-from test_gpu_episodes import oracle_episodes
+from test_gpu_episodes import run_case_set
 
 pytestmark = pytest.mark.gpu
 
@@ -19,29 +19,13 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def trained_flat(tmp_path_factory):
     from aemcarl_b200.crowd_nav import train
-    out = train.main(["--output_dir", str(tmp_path_factory.mktemp("trained")), "--il_episodes", "2048", "--il_epochs", "20",
+    out = train.main(["--no_final_test", "--output_dir", str(tmp_path_factory.mktemp("trained")), "--il_episodes", "2048", "--il_epochs", "20",
                       "--train_episodes", "16384", "--vectorised", "2048", "--updates_per_wave", "2000", "--fused_step"])
     return out["model"].flat_weights().copy()
 
 
 def test_trained_policy_outcomes_match_oracle(oracle, actions, trained_flat):
-    B, n = 500, 5
-    robot, humans = scenarios.generate_pool("test", 0, B, n, "circle_crossing")
-    codes, length = oracle_episodes(oracle, trained_flat, actions, robot, humans)
-    assert (codes >= 2).all()
-    assert (codes == 2).mean() > 0.5, "the short training run should already reach the goal in most cases"
+    """500 / 500 identical outcomes (or every differing case traced to a near-tie decision by the lock-step probe)."""
     for precision in ("fp32", "fp16x3"):
-        eng = Engine(0)
-        eng.set_action_space(actions)
-        eng.set_env_params(make_env_params())
-        eng.load_weights(trained_flat)
-        eng.set_precision(precision)
-        venv = VecCrowdSim(eng, B, n, "circle_crossing", "test", first_case=0, pool_size=B)
-        out = run_vectorised_test(venv, B)
-        same = out["codes"] == codes
-        # identical outcomes; trajectories may part at an argmax near-tie (documented), which can change an outcome
-        assert same.mean() >= 0.99, (precision, same.mean(), np.nonzero(~same)[0][:10])
-        assert abs(out["env_steps"] - int(length.sum())) <= 0.01 * length.sum()
-        print("[%s] trained weights: success %d collision %d timeout %d, identical cases %.1f%%"
-              % (precision, out["success"], out["collision"], out["timeout"], 100 * same.mean()))
-        eng.close()
+        out, codes, probe = run_case_set(oracle, actions, trained_flat, precision, 500, 5, "circle_crossing")
+        assert (codes == 2).mean() > 0.5, "the short training run should already reach the goal in most cases"

@@ -16,7 +16,7 @@ ap.add_argument("--mode", default="fused", choices=["fused", "graph", "eager"])
 a = ap.parse_args()
 rank = int(os.environ.get("RANK", "0"))
 out = tempfile.mkdtemp(prefix="aem_dp_%d_" % rank)
-argv = ["--output_dir", out, "--il_episodes", str(a.il_episodes), "--il_epochs", "2", "--train_episodes", str(a.train_episodes),
+argv = ["--no_final_test", "--output_dir", out, "--il_episodes", str(a.il_episodes), "--il_epochs", "2", "--train_episodes", str(a.train_episodes),
         "--vectorised", str(a.vectorised), "--updates_per_wave", str(a.updates_per_wave)]
 argv += {"fused": ["--fused_step"], "graph": ["--cuda_graph"], "eager": []}[a.mode]
 torch.cuda.synchronize() if torch.cuda.is_initialized() else None

@@ -3,7 +3,7 @@ import sys, tempfile, os
 sys.path.insert(0, ".")
 from aemcarl_b200.crowd_nav import train, test
 out = tempfile.mkdtemp()
-res = train.main(["--output_dir", out, "--il_episodes", "32", "--il_epochs", "2", "--train_episodes", "128", "--vectorised", "64",
+res = train.main(["--no_final_test", "--output_dir", out, "--il_episodes", "32", "--il_epochs", "2", "--train_episodes", "128", "--vectorised", "64",
                   "--updates_per_wave", "20", "--fused_step", "--cuda_graph"])
 ckpt = os.path.join(out, "rl_model.pth")
 a = test.main(["--model_weights", ckpt, "--cases", "3"])

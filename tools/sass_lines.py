@@ -1,5 +1,5 @@
 """SASS instruction count per source line of a kernel object (built with -lineinfo).
-usage: python tools/sass_lines.py aemcarl_b200/csrc/_obj/lookahead_q16.o [top]"""
+usage: python tools/sass_lines.py aemcarl_b200/csrc/_obj/lookahead_h16.o [top]"""
 import collections, os, re, subprocess, sys, tempfile
 obj = os.path.abspath(sys.argv[1]); top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 with tempfile.TemporaryDirectory() as d:
