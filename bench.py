@@ -118,9 +118,26 @@ def cpu_baseline(robot, humans, gt, W, actions, gbar, budget_s=12.0):
     t0 = time.perf_counter()
     oracle_step(po, W, r, h, t, actions, params, gbar, cores)
     dt = time.perf_counter() - t0
-    return {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of the %d envs of this workload, one full env-step (ORCA + env lookahead + 81-action value "
-                      "lookahead + step) by oracle/aem_oracle.c on %d threads, %.1f s" % (ns, B, cores, dt)}
+    out = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "%d of the %d envs of this workload, one full env-step (ORCA + env lookahead + 81-action value "
+                     "lookahead + step) by oracle/aem_oracle.c on %d threads, %.1f s" % (ns, B, cores, dt)}
+    out["reference_python"] = reference_python_baseline(cores, humans.shape[1])
+    return out
+
+
+def reference_python_baseline(cores, n, seconds=12.0):
+    """The AS-SHIPPED Python reference (oracle/_ref: an uncommitted copy made by oracle/make_ref.py, run under
+    oracle/ref_shim.py) on the same host cores, one single-thread process per core -- context next to the C port."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref, "crowd_nav")):
+        return {"unavailable": "oracle/_ref is absent (python oracle/make_ref.py in the build container)"}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--procs", str(cores), "--seconds",
+                            str(seconds), "--humans", str(n)], env=dict(os.environ, AEM_REFERENCE=ref), capture_output=True,
+                           text=True, timeout=seconds * 6 + 120)
+        return json.loads(r.stdout.strip().split("\n")[-1])
+    except Exception as e:                                     # context only: never fail the bench line
+        return {"unavailable": "oracle/ref_bench.py failed: %r" % (e,)}
 
 
 def run_reference(args, rank, world):
