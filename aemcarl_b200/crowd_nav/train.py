@@ -62,6 +62,9 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--resume", default=False, action="store_true")   # train.py:171-177
     ap.add_argument("--visible", default=False, action="store_true")  # train.py:46
+    ap.add_argument("--dropout", action="store_true",
+                    help="optimise in train() mode like the reference (it never calls eval(): the encoder layers' dropout, "
+                         "p = 0.1 at 4 sites per layer, is live in every optimisation step; qnetwork_factory.py:628)")
     ap.add_argument("--no_final_test", action="store_true",
                     help="skip the reference's episode-0 validation and closing run_k_episodes(test) (train.py:229-230,246) "
                          "-- benchmarks / unit tests only")
@@ -100,6 +103,8 @@ def main(argv=None):
         memory = DeviceReplayMemory(tcfg.getint("train", "capacity"), args.human_num, device)
     else:
         memory = ReplayMemory(tcfg.getint("train", "capacity"))
+    if args.dropout:
+        model.train()             # the optimisation steps see dropout; the lookahead kernels act without it (documented)
     trainer = Trainer(model, memory, device, batch_size, cuda_graph=args.cuda_graph, fused=args.fused_step)
     explorer = Explorer(env, robot, device, memory, policy.gamma, target_policy=policy)
 

@@ -2,7 +2,11 @@
 RMSprop exactly as configured in the reference.  The one addition is the data-parallel hook: when
 torch.distributed is initialised, the flat gradient (113,752 live floats, one bucket) is all-reduced (NCCL over
 NVLink on GPUs, gloo in the CPU tests) and averaged between loss.backward() and optimizer.step() -- the only
-collective of the whole system.  Three implementations of one optimisation step, same arithmetic contract:
+collective of the whole system.  Dropout: the reference never calls eval(), so it optimises with the four dropout
+sites of every encoder layer live (p = 0.1); here the module's mode decides -- model.train() gives that regime in all three
+implementations (torch's masks in the eager step, counter-based masks in the fused kernels), model.eval() (what
+ACTENVCARL.configure leaves, because the lookahead kernels have no dropout) trains without it; train.py --dropout selects
+the reference's regime.  Three implementations of one optimisation step, same arithmetic contract:
 eager torch (the reference's code path), GraphedStep (the torch step replayed from CUDA graphs) and FusedStep (the hand-written
 kernels of csrc/train.cu on one flat parameter vector: aem_train_grad + all-reduce + aem_adam_step / aem_sgd_step /
 aem_rmsprop_step), selected by Trainer(cuda_graph=..., fused=...).  With a DeviceReplayMemory the mini-batches come from
@@ -119,6 +123,8 @@ class FusedStep(object):
         self.kind = {optim.Adam: "adam", optim.SGD: "sgd", optim.RMSprop: "rmsprop"}[type(optimizer)]
         self.engine = get_engine(dev.index or 0, role="trainer")
         self.engine.set_act_mode(model.act_fixed, model.act_steps)
+        self.dropout_seed = int(torch.initial_seed()) & (2 ** 63 - 1)
+        self._drop_p = None
         named = dict(model.named_parameters())
         self.flat = torch.empty(wts.NUM_WEIGHTS, dtype=torch.float32, device=dev)
         self.grad = torch.zeros_like(self.flat)
@@ -151,6 +157,14 @@ class FusedStep(object):
                 self._params.append((p, off, n, shape))
         self.export_state()
 
+    def sync_dropout(self):
+        """train() mode = the reference's training regime: nn.TransformerEncoderLayer's dropout (p of the module, 0.1) is live
+        in the fused step too (aem_set_train_dropout: counter-based masks, one fresh set per step); eval() mode switches it off"""
+        p = float(self.model.encoder_layer.dropout.p) if self.model.training else 0.0
+        if p != self._drop_p:
+            self.engine.set_train_dropout(p, self.dropout_seed)
+            self._drop_p = p
+
     def export_state(self):
         """make the torch optimizer's state describe the flat vectors (views, no copies).  The step count is ONE shared
         tensor that sync_step() keeps current, and the SGD momentum buffer is always the live view (a zero buffer before the
@@ -176,6 +190,7 @@ class FusedStep(object):
         graph that call was captured into (re-captured when the ring size or the learning rate changes)."""
         g = self.optimizer.param_groups[0]
         dev = self.flat.device
+        self.sync_dropout()
         k = min(int(batch_size), len(memory))
         n = memory.states.shape[1]
         if getattr(self, "_dev_state", None) is None:
@@ -202,7 +217,7 @@ class FusedStep(object):
             # the graph holds the ring, the batch buffers AND the engine's scratch pointers: the scratch generation is part
             # of the key, so a larger batch / n that went through this (process-wide) engine in between forces a re-capture
             key = (len(memory), k, n, g["lr"], tuple(g["betas"]), g["eps"], memory.states.data_ptr(), memory.sample_seed,
-                   self.engine.train_scratch_generation())
+                   self.engine.train_scratch_generation(), self._drop_p)
             if self._graph_key != key:
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
@@ -227,6 +242,7 @@ class FusedStep(object):
         targets = values.detach().to(torch.float32).reshape(-1).contiguous()
         if self.values is None or self.values.numel() != inputs.shape[0]:
             self.values = torch.empty(inputs.shape[0], dtype=torch.float32, device=inputs.device)
+        self.sync_dropout()
         self.engine.train_grad(self.flat, inputs, targets, self.grad, self.loss, self.values, self.steps)
         world = 1
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -282,9 +298,9 @@ class Trainer(object):
     def _step(self, inputs, values):
         """one optimisation step; returns the loss as a 0-dim tensor (the callers synchronise once per call, not per step)"""
         if self.fused:
-            if self.model.training or getattr(self.model, "act_fixed", False):
-                raise NotImplementedError("the fused training step covers the eval()-mode adaptive network "
-                                          "(dropout inactive, act_fixed = False)")
+            if getattr(self.model, "act_fixed", False):
+                raise NotImplementedError("the fused training step covers the adaptive-computation-time network "
+                                          "(act_fixed = False); use the eager / graphed step for act_fixed")
             if self._fused is None:
                 self._fused = FusedStep(self.model, self.optimizer, inputs.device)
             return self._fused(inputs, values)
@@ -330,7 +346,7 @@ class Trainer(object):
         fast = self._device_memory()
         if fast and self.fused and isinstance(self.optimizer, optim.Adam) and self.memory.device.type == "cuda" \
                 and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) \
-                and not self.model.training and not getattr(self.model, "act_fixed", False):
+                and not getattr(self.model, "act_fixed", False):
             if self._fused is None:
                 self._fused = FusedStep(self.model, self.optimizer, self.memory.device)
             average_loss = float(self._fused.run_batches(self.memory, self.batch_size, num_batches, use_graph=self.cuda_graph))

@@ -128,6 +128,8 @@ struct aem_handle_s {
     int *tr_flags;
     int tr_grid, tr_B;
     size_t tr_stash_floats, tr_gru_floats;
+    double drop_p;                 // dropout of the fused training step (aem_set_train_dropout); 0 = eval() mode
+    unsigned long long drop_seed, drop_ctr;
     long long tr_generation;   // bumped whenever the training scratch is reallocated (captured graphs hold its pointers)
 };
 
@@ -168,7 +170,8 @@ cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double
 cudaError_t launch_scenarios(int rule, uint32_t first_seed, int count, int n, const aem_scenario_params &p, double *robot,
                              double *humans, cudaStream_t st);
 cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, const float *states, const float *targets,
-                              float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st, float *loss_sum = nullptr);
+                              float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st, float *loss_sum = nullptr,
+                              const unsigned long long *drop_ctr_dev = nullptr);
 cudaError_t launch_train_step_adam(aem_handle h, int N, int k, int n, const float *ring_states, const float *ring_values, uint64_t seed,
                                    unsigned long long *dev_state, float *adam_scal, float *params, float *grad, float *m, float *v,
                                    double lr, double b1, double b2, double eps, float *batch_states, float *batch_values, float *loss,

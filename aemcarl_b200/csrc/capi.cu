@@ -726,6 +726,16 @@ int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const floa
     return AEM_OK;
 }
 
+int aem_set_train_dropout(aem_handle h, double p, uint64_t seed)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    if (!(p >= 0.0 && p < 1.0)) return aem_set_error(AEM_ERR_INVALID, "dropout probability must be in [0, 1)");
+    h->drop_p = p;
+    h->drop_seed = seed;
+    h->drop_ctr = 0;
+    return AEM_OK;
+}
+
 int aem_sample_batch(aem_handle h, int N, int k, int n, const float *states_d, const float *values_d, uint64_t seed,
                      uint64_t counter, float *out_states_d, float *out_values_d, int64_t *out_index_d, void *stream)
 {

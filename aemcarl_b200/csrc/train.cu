@@ -485,7 +485,41 @@ struct TrainArgs {
     float *gru_g;       // [B][layout.enc]: the probe's GRU-ACT intermediates (x, h_0..3, three step blocks) handed to the
                         // forward / backward kernel, or null (the probe keeps one step block, the main kernel recomputes)
     int B, n;
+    // dropout of nn.TransformerEncoderLayer (qnetwork_factory.py:628: p = 0.1 at 4 sites per layer, live because the reference
+    // never calls eval()): inverted-dropout masks from a counter-based generator, recomputed in the backward pass
+    float drop_p;                              // 0 = eval() mode
+    unsigned long long drop_seed, drop_ctr;    // ctr = one value per optimisation step
+    const unsigned long long *drop_ctr_dev;    // or read it from the device step state (aem_train_step_adam: dev_state[1])
 };
+
+// Dropout mask of one element: 0 or 1 / (1 - p).  key = (sample, layer, site, element index); sites: 0 = attention weights
+// [2][T][T], 1 = attention branch before the residual [T][50], 2 = FFN hidden after the ReLU [T][150], 3 = FFN branch before
+// the residual [T][50].  tests/test_gpu_train.py regenerates the same masks on the host (dropout_masks_host) and feeds them
+// to the float64 derivation (tests/manual_backward.py = torch autograd with injected masks).
+struct DropGen {
+    unsigned long long base;
+    unsigned int thresh;        // keep iff (hash >> 40) >= thresh, thresh = p * 2^24
+    float scale;
+    __device__ __forceinline__ float operator()(int b, int l, int site, int idx) const
+    {
+        if (thresh == 0u) return 1.0f;
+        unsigned long long z = base + ((((unsigned long long)b * 12ull + (unsigned long long)(l * 4 + site)) << 16) | (unsigned long long)idx) *
+                                          0xD1B54A32D192ED03ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return (unsigned int)(z >> 40) >= thresh ? scale : 0.0f;
+    }
+};
+__device__ __forceinline__ DropGen make_dropgen(const TrainArgs &a)
+{
+    DropGen g;
+    const unsigned long long ctr = a.drop_ctr_dev ? a.drop_ctr_dev[1] : a.drop_ctr;
+    g.base = a.drop_seed * 0x9E3779B97F4A7C15ull + ctr * 0xC2B2AE3D27D4EB4Full;
+    g.thresh = a.drop_p > 0.0f ? (unsigned int)(a.drop_p * 16777216.0f) : 0u;
+    g.scale = a.drop_p > 0.0f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+    return g;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TR_THREADS, 1) train_probe_kernel(TrainArgs a)
@@ -547,6 +581,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
     const int K = a.flags[0] == 0 ? 1 : (a.flags[1] == 0 ? 2 : 3);
     const float invK = 1.0f / (float)K;
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    const DropGen drop = make_dropgen(a);
 
     if (blockIdx.x >= a.B) {                       // more CTAs than samples: a zero slice
         for (int e = tid; e < NUM_WEIGHTS; e += nt) G[e] = 0.0f;
@@ -618,24 +653,30 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
                 if (lane < T) p[lane] = e0 * inv;
                 if (lane + 32 < T) p[lane + 32] = e1 * inv;
                 __syncwarp();
-                if (lane < 25) {
+                if (lane < 25) {                                    // ctx = dropout(P) v  (the stash keeps the undropped P)
                     float s = 0.0f;
-                    for (int cc = 0; cc < T; ++cc) s = fmaf(p[cc], c.qkv[cc * 150 + 100 + 25 * hd + lane], s);
+                    for (int cc = 0; cc < T; ++cc) s = fmaf(p[cc] * drop(b, l, 0, hr * T + cc), c.qkv[cc * 150 + 100 + 25 * hd + lane], s);
                     c.ctx[r * 50 + 25 * hd + lane] = s;
                 }
             }
             psync();
             Ws = pipe.take();
             pipe.issue(E + ENC_L1W, 150, 50);
-            lin_fwd<50, 50>(Ws, E + ENC_OB, c.ctx, 50, T, [=](int r, int o, float v) { s1[r * 50 + o] = v + c.X[r * 50 + o]; });
+            lin_fwd<50, 50>(Ws, E + ENC_OB, c.ctx, 50, T, [=](int r, int o, float v) {
+                s1[r * 50 + o] = fmaf(v, drop(b, l, 1, r * 50 + o), c.X[r * 50 + o]);
+            });
             ln_fwd(s1, E + ENC_N1G, E + ENC_N1B, c.y1, c.xh1, c.rs1, T);
             Ws = pipe.take();
             pipe.issue(E + ENC_L2W, 50, 150);
-            lin_fwd<150, 50>(Ws, E + ENC_L1B, c.y1, 50, T, [=](int r, int o, float v) { c.f1[r * 150 + o] = fmaxf(v, 0.0f); });
+            lin_fwd<150, 50>(Ws, E + ENC_L1B, c.y1, 50, T, [=](int r, int o, float v) {
+                c.f1[r * 150 + o] = fmaxf(v, 0.0f) * drop(b, l, 2, r * 150 + o);
+            });
             Ws = pipe.take();
             if (l < 2) pipe.issue(E + ENC_SIZE + ENC_INW, 150, 50);
             else pipe.issue(w + OFF_A0W, 100, 56);
-            lin_fwd<50, 150>(Ws, E + ENC_L2B, c.f1, 150, T, [=](int r, int o, float v) { s2[r * 50 + o] = v + c.y1[r * 50 + o]; });
+            lin_fwd<50, 150>(Ws, E + ENC_L2B, c.f1, 150, T, [=](int r, int o, float v) {
+                s2[r * 50 + o] = fmaf(v, drop(b, l, 3, r * 50 + o), c.y1[r * 50 + o]);
+            });
             ln_fwd(s2, E + ENC_N2G, E + ENC_N2B, Xn, c.xh2, c.rs2, T);
         }
         float *X3 = st + L.fin, *ain = X3 + T * 50, *a1 = ain + 56, *a2 = a1 + 100;
@@ -685,21 +726,27 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
             const float *E = w + OFF_ENC + l * ENC_SIZE;
             float *GE = G + OFF_ENC + l * ENC_SIZE;
             EncStash c = enc_stash(st + L.enc + l * L.enc_layer, T);
-            float *ds2 = t2, *df1 = t3, *dy1 = t4, *ds1 = t2, *dctx = t4, *dqkv = t3, *dS = t5;
+            float *ds2 = t2, *df1 = t3, *dy1 = t4, *ds1 = t2, *dctx = t4, *dqkv = t3, *dS = t5, *df2 = t6, *dao = t7;
+            const float dscale = drop.scale;
             ln_bwd(dX, c.xh2, c.rs2, E + ENC_N2G, ds2, GE + ENC_N2G, GE + ENC_N2B, T, acc);
+            for (int e = tid; e < T * 50; e += nt) df2[e] = ds2[e] * drop(b, l, 3, e);      // through the FFN-branch dropout
+            psync();
             Ws = pipe.take();
             pipe.issue(E + ENC_L1W, 150, 50);
-            lin_bwd_w<50, 150>(GE + ENC_L2W, GE + ENC_L2B, ds2, 50, c.f1, 150, T, acc);
-            lin_bwd_x<50, 150, 150>(Ws, ds2, 50, T, [=](int r, int i, float v) { df1[r * 150 + i] = c.f1[r * 150 + i] > 0.0f ? v : 0.0f; });
+            lin_bwd_w<50, 150>(GE + ENC_L2W, GE + ENC_L2B, df2, 50, c.f1, 150, T, acc);
+            // f1 carries its mask and the ReLU: a kept, positive unit passes the gradient scaled by 1 / (1 - p)
+            lin_bwd_x<50, 150, 150>(Ws, df2, 50, T, [=](int r, int i, float v) { df1[r * 150 + i] = c.f1[r * 150 + i] > 0.0f ? v * dscale : 0.0f; });
             Ws = pipe.take();
             pipe.issue(E + ENC_OW, 50, 50);
             lin_bwd_w<150, 50>(GE + ENC_L1W, GE + ENC_L1B, df1, 150, c.y1, 50, T, acc);
             lin_bwd_x<150, 50, 50>(Ws, df1, 150, T, [=](int r, int i, float v) { dy1[r * 50 + i] = ds2[r * 50 + i] + v; });
             ln_bwd(dy1, c.xh1, c.rs1, E + ENC_N1G, ds1, GE + ENC_N1G, GE + ENC_N1B, T, acc);
+            for (int e = tid; e < T * 50; e += nt) dao[e] = ds1[e] * drop(b, l, 1, e);      // through the attention-branch dropout
+            psync();
             Ws = pipe.take();
             pipe.issue(E + ENC_INW, 150, 50);
-            lin_bwd_w<50, 50>(GE + ENC_OW, GE + ENC_OB, ds1, 50, c.ctx, 50, T, acc);
-            lin_bwd_x<50, 50, 50>(Ws, ds1, 50, T, [=](int r, int i, float v) { dctx[r * 50 + i] = v; });
+            lin_bwd_w<50, 50>(GE + ENC_OW, GE + ENC_OB, dao, 50, c.ctx, 50, T, acc);
+            lin_bwd_x<50, 50, 50>(Ws, dao, 50, T, [=](int r, int i, float v) { dctx[r * 50 + i] = v; });
             // attention: dP = dctx v^T ; dS = P (dP - sum_c P dP) ; then dq = dS k / 5 ; dk = dS^T q / 5 ; dv = P^T dctx
             for (int hr = warp; hr < 2 * T; hr += nw) {
                 const int hd = hr / T, r = hr - hd * T;
@@ -714,6 +761,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
                         float x = 0.0f;
 #pragma unroll
                         for (int d = 0; d < 25; ++d) x = fmaf(dc[d], v[d], x);
+                        x *= drop(b, l, 0, hr * T + cc);            // d/dP of ctx = (P * mask) v
                         dp[u] = x;
                         s = fmaf(p[cc], x, s);
                     }
@@ -732,8 +780,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
                 } else if (part == 1) {     // dk[r] = sum_q dS[q][r] q[q] / 5
                     for (int qq = 0; qq < T; ++qq) s = fmaf(dS[(hd * T + qq) * T + r], c.qkv[qq * 150 + jj], s);
                     s *= 0.2f;
-                } else {                    // dv[r] = sum_q P[q][r] dctx[q]
-                    for (int qq = 0; qq < T; ++qq) s = fmaf(c.P[(hd * T + qq) * T + r], dctx[qq * 50 + jj], s);
+                } else {                    // dv[r] = sum_q (P * mask)[q][r] dctx[q]
+                    for (int qq = 0; qq < T; ++qq)
+                        s = fmaf(c.P[(hd * T + qq) * T + r] * drop(b, l, 0, (hd * T + qq) * T + r), dctx[qq * 50 + jj], s);
                 }
                 dqkv[e] = s;
             }
@@ -992,7 +1041,8 @@ size_t probe_smem_bytes(int T, bool handoff)
 }
 
 cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, const float *states, const float *targets,
-                              float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st, float *loss_sum)
+                              float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st, float *loss_sum,
+                              const unsigned long long *drop_ctr_dev)
 {
     const int T = n + 1;
     const TrLayout L = tr_layout(T);
@@ -1022,6 +1072,9 @@ cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, c
     a.stash_g = in_smem ? nullptr : h->tr_stash;
     a.gru_g = handoff ? h->tr_gru : nullptr;
     a.B = B; a.n = n;
+    a.drop_p = (float)h->drop_p; a.drop_seed = h->drop_seed;
+    a.drop_ctr_dev = drop_ctr_dev;
+    a.drop_ctr = drop_ctr_dev ? 0ull : h->drop_ctr++;          // a fresh set of masks per optimisation step
     if ((e = cudaMemsetAsync(h->tr_flags, 0, 2 * sizeof(int), st)) != cudaSuccess) return e;
     const size_t psm = probe_smem_bytes(T, handoff), fsm = train_smem_bytes(T, in_smem);
     if (psm > smem_limit) return cudaErrorInvalidValue;
@@ -1056,7 +1109,7 @@ cudaError_t launch_train_step_adam(aem_handle h, int N, int k, int n, const floa
                                                          nullptr, dev_state, adam_scal, lr, b1, b2);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if ((e = launch_train_grad(h, k, n, params, batch_states, batch_values, grad, loss, nullptr, steps, st, loss_sum)) != cudaSuccess)
+    if ((e = launch_train_grad(h, k, n, params, batch_states, batch_values, grad, loss, nullptr, steps, st, loss_sum, dev_state)) != cudaSuccess)
         return e;
     adam_kernel<<<(NUM_WEIGHTS + 255) / 256, 256, 0, st>>>((size_t)NUM_WEIGHTS, params, grad, m, v, 0.0f, (float)b1, (float)b2, (float)eps,
                                                           1.0f, 1.0f, adam_scal);

@@ -281,6 +281,10 @@ class Engine:
     def launch_count(self):
         return int(self.lib.aem_launch_count(self.h))
 
+    def set_train_dropout(self, p, seed=0):
+        """dropout of the fused training step (nn.TransformerEncoderLayer's four sites); 0 = the eval()-mode network"""
+        check(self.lib.aem_set_train_dropout(self.h, float(p), ctypes.c_uint64(int(seed) & (2 ** 64 - 1))))
+
     def train_scratch_generation(self):
         """changes whenever the library reallocated the training scratch: captured graphs of train_step_adam are stale then"""
         return int(self.lib.aem_train_scratch_generation(self.h))

@@ -187,6 +187,14 @@ int aem_transform(aem_handle h, int B, int n, const double *robot_d, const doubl
 int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const float *states_d, const float *targets_d,
                    float *grad_d, float *loss_d, float *values_d, int32_t *steps_d, void *stream);
 
+/* Dropout of the fused training step.  The reference never calls eval(): nn.TransformerEncoderLayer(50, 2, 150) trains
+ * with p = 0.1 at four sites per layer (attention weights, attention branch, FFN hidden, FFN branch;
+ * crowd_nav/common/qnetwork_factory.py:628-629, trainer.py:65-86).  p > 0 makes aem_train_grad / aem_train_step_adam draw
+ * inverted-dropout masks from a counter-based generator (one fresh set per call: seed, call counter -- for
+ * aem_train_step_adam the device step count --, sample, layer, site, element) and use the same masks in the backward
+ * pass; p = 0 (default) is the eval()-mode network.  Calling it resets the call counter. */
+int aem_set_train_dropout(aem_handle h, double p, uint64_t seed);
+
 /* One mini-batch of the replay memory (memory.py:4-28 read through DataLoader(memory, batch_size, shuffle=True), trainer.py:70-72):
  * k of the N stored pairs, uniformly at random WITHOUT replacement (Floyd's algorithm on a counter-based generator: the same
  * (seed, counter) gives the same batch).  states_d [N][n][13] f32, values_d [N] f32 -> out_states_d [k][n][13], out_values_d [k],
