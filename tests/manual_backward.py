@@ -198,14 +198,41 @@ def sample_forward_backward(flat, state, target, K, batch, masks=None):
     return value, np.concatenate([G[k].reshape(-1) for k, _ in wts.WEIGHT_SPEC])
 
 
-def batch_forward_backward(flat, states, targets):
-    """-> (loss, grad[113752] float64, values[B], K)"""
+def dropout_masks_host(seed, ctr, b, T, p):
+    """The inverted-dropout masks aem_train_grad draws for sample b (csrc/train.cu DropGen: splitmix64 finaliser of
+    seed / call counter / (sample, layer, site, element)), regenerated on the host: a list of three dicts
+    {"attn" [2, T, T], "ao" [T, 50], "f1" [T, 150], "f2" [T, 50]} with entries 0 or 1 / (1 - p)."""
+    M = (1 << 64) - 1
+    base = (int(seed) * 0x9E3779B97F4A7C15 + int(ctr) * 0xC2B2AE3D27D4EB4F) & M
+    thresh = int(np.float32(p) * np.float32(16777216.0))
+    scale = float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+
+    def site_mask(l, site, count):
+        with np.errstate(over="ignore"):
+            idx = np.arange(count, dtype=np.uint64)
+            key = (np.uint64(((b * 12 + l * 4 + site) << 16) & M) | idx)
+            z = np.uint64(base) + key * np.uint64(0xD1B54A32D192ED03)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+        keep = (z >> np.uint64(40)).astype(np.int64) >= thresh
+        return np.where(keep, scale, 0.0)
+
+    out = []
+    for l in range(3):
+        out.append(dict(attn=site_mask(l, 0, 2 * T * T).reshape(2, T, T), ao=site_mask(l, 1, T * 50).reshape(T, 50),
+                        f1=site_mask(l, 2, T * 150).reshape(T, 150), f2=site_mask(l, 3, T * 50).reshape(T, 50)))
+    return out
+
+
+def batch_forward_backward(flat, states, targets, masks_of=None):
+    """-> (loss, grad[113752] float64, values[B], K); masks_of(b) (optional) = the dropout masks of sample b"""
     B = len(states)
     K = batch_steps(flat, states)
     grad = np.zeros(wts.NUM_WEIGHTS)
     values = np.zeros(B)
     for b in range(B):
-        values[b], g = sample_forward_backward(flat, states[b], targets[b], K, B)
+        values[b], g = sample_forward_backward(flat, states[b], targets[b], K, B, masks_of(b) if masks_of else None)
         grad += g
     loss = float(((values - np.asarray(targets, dtype=np.float64).reshape(-1)) ** 2).mean())
     return loss, grad, values, K

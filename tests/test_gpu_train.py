@@ -35,13 +35,14 @@ def run_kernel(eng, flat, states, targets):
     return float(loss[0]), g.cpu().numpy().astype(np.float64), values.cpu().numpy().astype(np.float64), int(steps[0])
 
 
-def check_grad(grad, ref):
+def check_grad(grad, ref, atol=0.0):
+    """atol: float32 noise floor for batches whose 1 / B scaling makes whole tensors' gradients ~1e-4 and smaller"""
     assert np.isfinite(grad).all()
     for key, (off, shape) in wts.weight_offsets().items():
         n = int(np.prod(shape))
         a, b = grad[off:off + n], ref[off:off + n]
         scale = max(np.abs(b).max(), 1e-4)
-        assert np.abs(a - b).max() <= GRAD_RTOL * scale, (key, np.abs(a - b).max(), scale)
+        assert np.abs(a - b).max() <= GRAD_RTOL * scale + atol, (key, np.abs(a - b).max(), scale)
 
 
 @pytest.mark.parametrize("ponder_bias,expect_K", [(4.0, 1), (None, 2), (-2.0, 3)])
@@ -59,6 +60,65 @@ def test_train_grad_matches_autograd(eng, ponder_bias, expect_K, B, n):
     assert np.abs(values - val_r).max() < VALUE_ATOL
     assert loss == pytest.approx(loss_r, rel=1e-4)
     check_grad(grad, grad_r)
+
+
+@pytest.mark.parametrize("p,B,n,ponder_bias", [(0.1, 24, 5, None), (0.1, 9, 10, -2.0), (0.3, 16, 5, 4.0), (0.1, 200, 5, None)])
+def test_train_grad_with_live_dropout_matches_the_masked_derivation(eng, p, B, n, ponder_bias):
+    """The reference trains with nn.TransformerEncoderLayer's dropout live (qnetwork_factory.py:628, trainer.py:65-86).
+    aem_set_train_dropout(p, seed) switches the four sites on; the kernel's counter-based masks are regenerated on the host
+    (manual_backward.dropout_masks_host) and injected into the float64 derivation, which equals torch autograd of the masked
+    forward (tests/test_train_math.py): same gradients, values and loss; a second call draws fresh masks; p = 0 is eval()."""
+    import manual_backward as mb
+    flat = wts.synthetic_weights(6, ponder_bias=ponder_bias)
+    states, targets = random_batch(40 + B + n, B, n)
+    states = states.astype(np.float32).astype(np.float64)
+    targets = targets.astype(np.float32).astype(np.float64)
+    seed = 1234567
+    T = n + 1
+    try:
+        eng.set_train_dropout(p, seed)
+        out = [run_kernel(eng, flat, states, targets) for _ in range(2)]          # call counters 0 and 1
+        for ctr, (loss, grad, values, K) in enumerate(out):
+            loss_r, grad_r, val_r, K_r = mb.batch_forward_backward(
+                flat, states, targets, masks_of=lambda b: mb.dropout_masks_host(seed, ctr, b, T, p))
+            assert K == K_r
+            assert np.abs(values - val_r).max() < VALUE_ATOL
+            assert loss == pytest.approx(loss_r, rel=1e-4)
+            check_grad(grad, grad_r, atol=1e-7)
+        assert not np.array_equal(out[0][1], out[1][1])                           # fresh masks per step
+        keep = np.concatenate([m["f1"].ravel() for b in range(B) for m in mb.dropout_masks_host(seed, 0, b, T, p)])
+        assert abs((keep == 0).mean() - p) < 0.02                                 # the drop rate is p
+    finally:
+        eng.set_train_dropout(0.0, 0)
+    loss0, grad0, values0, K0 = run_kernel(eng, flat, states, targets)
+    loss_r, grad_r, val_r, K_r = mb.batch_forward_backward(flat, states, targets)
+    check_grad(grad0, grad_r, atol=1e-7)
+
+
+def test_fused_trainer_follows_the_module_mode(eng):
+    """Trainer(fused=True) in train() mode optimises with dropout (the reference's regime), in eval() mode without"""
+    from aemcarl_b200.crowd_nav.default_configs import policy_config
+    from aemcarl_b200.crowd_nav.policy.policy_factory import policy_factory
+    from aemcarl_b200.crowd_nav.utils.trainer import Trainer
+    dev = torch.device("cuda:0")
+    policy = policy_factory["actenvcarl"]()
+    policy.configure(policy_config())
+    policy.set_device(dev)
+    model = policy.get_model()
+    x = torch.randn((100, 5, 13), device=dev)
+    v = torch.randn((100, 1), device=dev)
+    tr = Trainer(model, None, dev, 100, fused=True)
+    tr.set_learning_rate(1e-3, "Adam")
+    model.eval()
+    l_eval = [float(tr._step(x, v)) for _ in range(3)]
+    assert tr._fused._drop_p == 0.0
+    model.train()
+    l_train = [float(tr._step(x, v)) for _ in range(3)]
+    assert tr._fused._drop_p == pytest.approx(0.1)
+    model.eval()
+    float(tr._step(x, v))
+    assert tr._fused._drop_p == 0.0
+    assert all(np.isfinite(l_eval + l_train))
 
 
 def test_train_grad_is_deterministic(eng):
