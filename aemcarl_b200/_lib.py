@@ -73,6 +73,7 @@ SYMBOLS = {
     "aem_transform": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),
     "aem_generate_scenarios": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(ScenarioParams), _VP, _VP, _VP]),
+    "aem_set_active_counts": (ctypes.c_int, [_VP, _VP, _VP]),
     "aem_set_train_dropout": (ctypes.c_int, [_VP, ctypes.c_double, ctypes.c_uint64]),
     "aem_train_grad": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 8),
     "aem_sample_batch": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP, ctypes.c_uint64, ctypes.c_uint64,

@@ -128,6 +128,8 @@ struct aem_handle_s {
     int *tr_flags;
     int tr_grid, tr_B;
     size_t tr_stash_floats, tr_gru_floats;
+    int32_t *nact_d;               // per-environment human counts (aem_set_active_counts), or null: every env has n humans
+    const int32_t *pool_nact_d;    // the same for the scenario pool of aem_env_reset_done
     double drop_p;                 // dropout of the fused training step (aem_set_train_dropout); 0 = eval() mode
     unsigned long long drop_seed, drop_ctr;
     long long tr_generation;   // bumped whenever the training scratch is reallocated (captured graphs hold its pointers)
@@ -151,21 +153,22 @@ cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStrea
 cudaError_t launch_transform(const double *robot, const double *humans, int B, int n, float *out, cudaStream_t st);
 cudaError_t launch_select(const double *values, const double *robot, int B, int A, int32_t *best, cudaStream_t st);
 cudaError_t launch_orca(int B, int n, const double *humans, const double *robot, const aem_env_params &p,
-                        double *new_vel, cudaStream_t st);
+                        double *new_vel, cudaStream_t st, const int32_t *nact = nullptr);
 cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const double *humans,
                                  const double *new_vel, const double *global_time, const double *actions,
                                  int action_env_stride, const double *lut, const aem_env_params &p, double amax, double *rewards,
-                                 int32_t *info, double *dmin, double *humans_next, cudaStream_t st);
+                                 int32_t *info, double *dmin, double *humans_next, cudaStream_t st, const int32_t *nact = nullptr);
 cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans, const double *new_vel,
                              double *global_time, const double *actions, int action_env_stride,
                              const int32_t *chosen,
                              const double *rewards, const int32_t *info, const double *dmin, double time_step,
                              double *out_reward, int32_t *out_done, int32_t *out_info, double *out_dmin,
-                             cudaStream_t st);
+                             cudaStream_t st, const int32_t *nact = nullptr);
 
 cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double *global_time, const int32_t *done,
                              const int32_t *info, const double *pool_robot, const double *pool_humans, int P,
-                             int32_t *case_idx, int case_stride, unsigned long long *outcome_counts, cudaStream_t st);
+                             int32_t *case_idx, int case_stride, unsigned long long *outcome_counts, cudaStream_t st,
+                             int32_t *nact = nullptr, const int32_t *pool_nact = nullptr);
 
 cudaError_t launch_scenarios(int rule, uint32_t first_seed, int count, int n, const aem_scenario_params &p, double *robot,
                              double *humans, cudaStream_t st);
@@ -197,6 +200,7 @@ struct LookaheadArgs {
     float *net_values;
     uint8_t *steps;
     float *gru_out;        // mode 2: [S*T][50]
+    const int32_t *n_active;   // mode 0, optional: humans of every environment [B] ('mixed' scenes); token rows beyond it are padding
     long long *dbg;        // optional debug buffer (lookahead_h16.cu: AEM_H16_TIMELINE / AEM_H16_WATCHDOG builds)
     int stagger_ns;        // lookahead_h16: start-up delay of the second CTA of every SM (anti-phase the two tiles)
 };

@@ -449,7 +449,7 @@ int aem_orca(aem_handle h, int B, int n, const double *humans_d, const double *r
     if (B == 0) return AEM_OK;      // empty batch: nothing to do (buffers may be null)
     if (!humans_d || !robot_d || !new_vel_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
-    AEM_CUDA_CHECK(launch_orca(B, n, humans_d, robot_d, h->params, new_vel_d, as_stream(stream)));
+    AEM_CUDA_CHECK(launch_orca(B, n, humans_d, robot_d, h->params, new_vel_d, as_stream(stream), h->nact_d));
     h->launches += (B > 0);
     return AEM_OK;
 }
@@ -467,7 +467,7 @@ int aem_env_lookahead(aem_handle h, int B, int n, const double *robot_d, const d
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     AEM_CUDA_CHECK(launch_env_lookahead(B, n, h->A, robot_d, humans_d, new_vel_d, global_time_d, h->actions_d, 0,
                                         h->lut_d, h->params, action_amax(h), rewards_d, info_d, dmin_d,
-                                        humans_next_d, as_stream(stream)));
+                                        humans_next_d, as_stream(stream), h->nact_d));
     h->launches += (B > 0);
     return AEM_OK;
 }
@@ -496,6 +496,9 @@ int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const doubl
     a.gamma_bar = gamma_bar;
     a.robot = robot_d; a.humans_next = humans_next_d; a.actions = h->actions_d; a.rewards = rewards_d;
     a.values = values_d; a.net_values = net_values_d; a.steps = act_steps_d;
+    a.n_active = h->nact_d;
+    if (h->nact_d && h->precision == 1)
+        return aem_set_error(AEM_ERR_STATE, "per-environment human counts need precision 0 (fp32) or 2 (fp16x3)");
     AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
                    : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
                                        : launch_lookahead(h, a, as_stream(stream)));
@@ -518,7 +521,7 @@ int aem_env_apply(aem_handle h, int B, int n, double *robot_d, double *humans_d,
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     AEM_CUDA_CHECK(launch_env_apply(B, n, h->A, robot_d, humans_d, new_vel_d, global_time_d, h->actions_d, 0, chosen_d,
                                     rewards_d, info_d, dmin_d, h->params.time_step, out_reward_d, out_done_d,
-                                    out_info_d, out_dmin_d, as_stream(stream)));
+                                    out_info_d, out_dmin_d, as_stream(stream), h->nact_d));
     h->launches += (B > 0);
     return AEM_OK;
 }
@@ -538,10 +541,10 @@ int aem_env_step_xy(aem_handle h, int B, int n, double *robot_d, double *humans_
     double *rew = scratch_d, *dmn = scratch_d + B;
     int32_t *inf = reinterpret_cast<int32_t *>(scratch_d + 2 * (size_t)B);
     AEM_CUDA_CHECK(launch_env_lookahead(B, n, 1, robot_d, humans_d, new_vel_d, global_time_d, actions_d, 2, h->lut_d,
-                                        h->params, max_speed, rew, inf, dmn, nullptr, as_stream(stream)));
+                                        h->params, max_speed, rew, inf, dmn, nullptr, as_stream(stream), h->nact_d));
     AEM_CUDA_CHECK(launch_env_apply(B, n, 1, robot_d, humans_d, new_vel_d, global_time_d, actions_d, 2, nullptr, rew, inf,
                                     dmn, h->params.time_step, out_reward_d, out_done_d, out_info_d, out_dmin_d,
-                                    as_stream(stream)));
+                                    as_stream(stream), h->nact_d));
     h->launches += 2;
     return AEM_OK;
 }
@@ -558,7 +561,8 @@ int aem_env_reset_done(aem_handle h, int B, int n, double *robot_d, double *huma
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     AEM_CUDA_CHECK(launch_env_reset(B, n, robot_d, humans_d, global_time_d, done_d, info_d, pool_robot_d,
-                                    pool_humans_d, P, case_idx_d, case_stride, outcome_counts_d, as_stream(stream)));
+                                    pool_humans_d, P, case_idx_d, case_stride, outcome_counts_d, as_stream(stream),
+                                    h->nact_d, h->pool_nact_d));
     h->launches += (B > 0);
     return AEM_OK;
 }
@@ -663,6 +667,7 @@ int aem_decide_step_host(aem_handle h, int B, int n, double gamma_bar, double *r
 {
     int rc = check_ready(h, true, true);
     if (rc) return rc;
+    if (h->nact_d) return aem_set_error(AEM_ERR_STATE, "aem_decide_step_host takes uniform batches: clear aem_set_active_counts first");
     if (B < 1 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
     if (!robot_h || !humans_h || !global_time_h || !chosen_h || !reward_h || !done_h || !info_h)
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
@@ -723,6 +728,14 @@ int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const floa
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     AEM_CUDA_CHECK(launch_train_grad(h, B, n, params_d, states_d, targets_d, grad_d, loss_d, values_d, steps_d, as_stream(stream)));
     h->launches += 3;
+    return AEM_OK;
+}
+
+int aem_set_active_counts(aem_handle h, int32_t *n_active_d, const int32_t *pool_n_active_d)
+{
+    if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
+    h->nact_d = n_active_d;
+    h->pool_nact_d = pool_n_active_d;
     return AEM_OK;
 }
 

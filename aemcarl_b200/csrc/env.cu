@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
     const double *__restrict__ new_vel, const double *__restrict__ global_time, const double *__restrict__ actions_all,
     int action_env_stride, const double *__restrict__ lut, const aem_env_params p, double amax, int tile_cap,
     double *__restrict__ rewards, int32_t *__restrict__ info, double *__restrict__ dmin_out,
-    double *__restrict__ humans_next)
+    double *__restrict__ humans_next, const int32_t *__restrict__ nact)
 {
     extern __shared__ __align__(16) double dsm[];
     double *tile = dsm;                         // [tile_cap]
@@ -117,9 +117,11 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
+    const int nstride = n;                      // row pitch of the human arrays
+    if (nact) n = min(max(nact[b], 0), n);      // per-environment human count ('mixed' rule): rows >= n are padding
     // shared action table (stride 0) or one private table per environment (arbitrary ActionXY per env, stride 2 A)
     const double *__restrict__ actions = actions_all + (size_t)b * action_env_stride;
-    for (int i = tid; i < n * 8; i += ENV_THREADS) sh[i] = humans[(size_t)b * n * 8 + i];
+    for (int i = tid; i < n * 8; i += ENV_THREADS) sh[i] = humans[(size_t)b * nstride * 8 + i];
     if (tid < 9) sr9[tid] = robot[(size_t)b * 9 + tid];
     if (tid < AEM_MAX_ACTIONS) prob[tid] = 0.0;
     __syncthreads();
@@ -213,9 +215,13 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
         if (info) info[(size_t)b * A + a] = code;
         if (dmin_out) dmin_out[(size_t)b * A + a] = dmin;
     }
+    if (humans_next && tid >= n && tid < nstride) {        // padding rows: defined values
+        double *o = humans_next + ((size_t)b * nstride + tid) * 5;
+        o[0] = o[1] = o[2] = o[3] = o[4] = 0.0;
+    }
     if (humans_next && tid < n) {                          // agent.py:63-74
-        const double vx = new_vel[((size_t)b * n + tid) * 2], vy = new_vel[((size_t)b * n + tid) * 2 + 1];
-        double *o = humans_next + ((size_t)b * n + tid) * 5;
+        const double vx = new_vel[((size_t)b * nstride + tid) * 2], vy = new_vel[((size_t)b * nstride + tid) * 2 + 1];
+        double *o = humans_next + ((size_t)b * nstride + tid) * 5;
         o[0] = sh[tid * 8] + vx * p.time_step;
         o[1] = sh[tid * 8 + 1] + vy * p.time_step;
         o[2] = vx; o[3] = vy; o[4] = sh[tid * 8 + 4];
@@ -229,10 +235,11 @@ __global__ void env_apply_kernel(int B, int n, int A, double *__restrict__ robot
                                  const double *__restrict__ rewards, const int32_t *__restrict__ info,
                                  const double *__restrict__ dmin, double time_step, double *__restrict__ out_reward,
                                  int32_t *__restrict__ out_done, int32_t *__restrict__ out_info,
-                                 double *__restrict__ out_dmin)
+                                 double *__restrict__ out_dmin, const int32_t *__restrict__ nact)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const int na = nact ? min(max(nact[b], 0), n) : n;
     int a = chosen ? chosen[b] : 0;
     if (a < 0 || a >= A) a = 0;
     const double *__restrict__ actions = actions_all + (size_t)b * action_env_stride;
@@ -248,7 +255,7 @@ __global__ void env_apply_kernel(int B, int n, int A, double *__restrict__ robot
     rb[0] = rb[0] + ax * time_step;
     rb[1] = rb[1] + ay * time_step;
     rb[2] = ax; rb[3] = ay;
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < na; ++i) {
         double *hh = humans + ((size_t)b * n + i) * 8;
         const double vx = new_vel[((size_t)b * n + i) * 2], vy = new_vel[((size_t)b * n + i) * 2 + 1];
         hh[0] = hh[0] + vx * time_step;
@@ -263,7 +270,7 @@ static int g_tile_cap[64] = {0};     // per device: cudaFuncSetAttribute is a pe
 cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const double *humans,
                                     const double *new_vel, const double *global_time, const double *actions,
                                     int action_env_stride, const double *lut, const aem_env_params &p, double amax, double *rewards,
-                                    int32_t *info, double *dmin, double *humans_next, cudaStream_t st)
+                                    int32_t *info, double *dmin, double *humans_next, cudaStream_t st, const int32_t *nact)
 {
     if (B <= 0) return cudaSuccess;
     const int side = 2 * (int)ceil(1.5 * p.human_timestep / GRID_RES) + 3;
@@ -280,7 +287,7 @@ cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const
     }
     env_lookahead_kernel<<<B, ENV_THREADS, smem, st>>>(B, n, A, robot, humans, new_vel, global_time, actions,
                                                        action_env_stride, lut, p,
-                                                       amax, tile_cap, rewards, info, dmin, humans_next);
+                                                       amax, tile_cap, rewards, info, dmin, humans_next, nact);
     return cudaGetLastError();
 }
 
@@ -289,14 +296,14 @@ cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans,
                              const int32_t *chosen,
                              const double *rewards, const int32_t *info, const double *dmin, double time_step,
                              double *out_reward, int32_t *out_done, int32_t *out_info, double *out_dmin,
-                             cudaStream_t st)
+                             cudaStream_t st, const int32_t *nact)
 {
     if (B <= 0) return cudaSuccess;
     const int threads = 128;
     env_apply_kernel<<<(B + threads - 1) / threads, threads, 0, st>>>(B, n, A, robot, humans, new_vel, global_time,
                                                                       actions, action_env_stride, chosen, rewards, info,
                                                                       dmin, time_step,
-                                                                      out_reward, out_done, out_info, out_dmin);
+                                                                      out_reward, out_done, out_info, out_dmin, nact);
     return cudaGetLastError();
 }
 
@@ -307,7 +314,8 @@ __global__ void env_reset_kernel(int B, int n, double *__restrict__ robot, doubl
                                  double *__restrict__ global_time, const int32_t *__restrict__ done,
                                  const int32_t *__restrict__ info, const double *__restrict__ pool_robot,
                                  const double *__restrict__ pool_humans, int P, int32_t *__restrict__ case_idx,
-                                 int case_stride, unsigned long long *__restrict__ outcome_counts)
+                                 int case_stride, unsigned long long *__restrict__ outcome_counts,
+                                 int32_t *__restrict__ nact, const int32_t *__restrict__ pool_nact)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B || !done[b]) return;
@@ -315,6 +323,7 @@ __global__ void env_reset_kernel(int B, int n, double *__restrict__ robot, doubl
     const int src = ((c % P) + P) % P;
     for (int k = 0; k < 9; ++k) robot[(size_t)b * 9 + k] = pool_robot[(size_t)src * 9 + k];
     for (int k = 0; k < n * 8; ++k) humans[(size_t)b * n * 8 + k] = pool_humans[(size_t)src * n * 8 + k];
+    if (nact && pool_nact) nact[b] = pool_nact[src];      // the new scenario's human count ('mixed' rule)
     global_time[b] = 0.0;
     case_idx[b] = c + case_stride;
     if (outcome_counts && info) {
@@ -325,13 +334,14 @@ __global__ void env_reset_kernel(int B, int n, double *__restrict__ robot, doubl
 
 cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double *global_time, const int32_t *done,
                              const int32_t *info, const double *pool_robot, const double *pool_humans, int P,
-                             int32_t *case_idx, int case_stride, unsigned long long *outcome_counts, cudaStream_t st)
+                             int32_t *case_idx, int case_stride, unsigned long long *outcome_counts, cudaStream_t st,
+                             int32_t *nact, const int32_t *pool_nact)
 {
     if (B <= 0) return cudaSuccess;
     const int threads = 128;
     env_reset_kernel<<<(B + threads - 1) / threads, threads, 0, st>>>(B, n, robot, humans, global_time, done, info,
                                                                       pool_robot, pool_humans, P, case_idx,
-                                                                      case_stride, outcome_counts);
+                                                                      case_stride, outcome_counts, nact, pool_nact);
     return cudaGetLastError();
 }
 

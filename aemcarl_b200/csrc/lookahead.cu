@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lookahead_kernel(const LookaheadA
     int *s_act = s_cnt + 32;                              // [32] sample still pondering
     int *s_need = s_act + 32;                             // [32]
     int *s_flag = s_need + 32;                            // [0] any sample active
+    __shared__ int s_tact[32];                            // tokens of every sample that are real ('mixed' scenes), else T
 
     const NetParams &net = args.net;
     const float *__restrict__ raw = net.raw;
@@ -265,6 +266,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lookahead_kernel(const LookaheadA
                 const int gs = s0 + samp;
                 if (args.mode == 0) {
                     const int b = gs / args.A, a = gs - b * args.A;
+                    const int tact = args.n_active ? 1 + min(max(args.n_active[b], 1), args.n) : T;
+                    if (t == 0) s_tact[samp] = tact;
                     const double *rb = args.robot + (size_t)b * 9;
                     const double ax = args.actions[2 * a], ay = args.actions[2 * a + 1];
                     const int hi = (t == 0) ? 0 : t - 1;
@@ -278,12 +281,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) lookahead_kernel(const LookaheadA
 #pragma unroll
                     for (int k = 0; k < 5; ++k) in14[9 + k] = (float)hb[k];
                     rotate13(in14, o);
+                    if (t >= tact) {                 // padding row: not a token of this sample
+#pragma unroll
+                        for (int k = 0; k < XD; ++k) o[k] = 0.0f;
+                        samp = -1;
+                    }
                 } else if (args.mode == 1) {
+                    if (t == 0) s_tact[samp] = T;
                     const int hi = (t == 0) ? 0 : t - 1;
                     const float *src = args.states + ((size_t)gs * args.n + hi) * XD;
 #pragma unroll
                     for (int k = 0; k < XD; ++k) o[k] = src[k];
                 } else {
+                    if (t == 0) s_tact[samp] = T;
                     const float *src = args.states + ((size_t)gs * T + t) * XD;
 #pragma unroll
                     for (int k = 0; k < XD; ++k) o[k] = src[k];
@@ -417,9 +427,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lookahead_kernel(const LookaheadA
                     const int sp = row_sample[r];
                     if (sp >= 0) {
                         const int rb = sp * T;
+                        const int Tk = s_tact[sp];               // keys = the sample's real tokens
                         const float *qp = bufH + (hd * 25) * RP + r;
                         float m = -INFINITY;
-                        for (int j = 0; j < T; ++j) {
+                        for (int j = 0; j < Tk; ++j) {
                             const float *kp = bufH + (HID + hd * 25) * RP + rb + j;
                             float d = 0.0f;
 #pragma unroll 5
@@ -430,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lookahead_kernel(const LookaheadA
 #pragma unroll
                         for (int k = 0; k < 25; ++k) o[k] = 0.0f;
                         float sum = 0.0f;
-                        for (int j = 0; j < T; ++j) {
+                        for (int j = 0; j < Tk; ++j) {
                             const float *kp = bufH + (HID + hd * 25) * RP + rb + j;
                             const float *vp = bufH + (2 * HID + hd * 25) * RP + rb + j;
                             float d = 0.0f;
@@ -485,9 +496,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lookahead_kernel(const LookaheadA
                 if (tid < 2 * nsamp) {
                     const int sp = tid >> 1, hd = tid & 1;
                     const int rb = sp * T;
+                    const int Tk = s_tact[sp];
                     const float *qp = bufH + (hd * 25) * RP + rb;
                     float m = -INFINITY;
-                    for (int j = 0; j < T; ++j) {
+                    for (int j = 0; j < Tk; ++j) {
                         const float *kp = bufH + (HID + hd * 25) * RP + rb + j;
                         float d = 0.0f;
                         for (int k = 0; k < 25; ++k) d = fmaf(qp[k * RP], kp[k * RP], d);
@@ -497,7 +509,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lookahead_kernel(const LookaheadA
 #pragma unroll
                     for (int k = 0; k < 25; ++k) o[k] = 0.0f;
                     float sum = 0.0f;
-                    for (int j = 0; j < T; ++j) {
+                    for (int j = 0; j < Tk; ++j) {
                         const float *kp = bufH + (HID + hd * 25) * RP + rb + j;
                         const float *vp = bufH + (2 * HID + hd * 25) * RP + rb + j;
                         float d = 0.0f;

@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         float selfs[3], xh0 = 0.0f;
         uint32_t xph[3], xpl[3];                         // x slots 1..6 of this half as split pairs (columns 13..15 of the operand)
         float P = 0.0f;
-        int samp = -1, tok = 0;
+        int samp = -1, tok = 0, tact = T;                 // tact: real tokens of this row's sample ('mixed' scenes), else T
 #pragma unroll
         for (int j = 0; j < 13; ++j) { ACC[j] = bc2(0.0f); hn[j] = bc2(0.0f); }
         MARK();
@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 const int gs = s0 + samp;
                 if (args.mode == 0) {
                     const int b = gs / args.A, a = gs - b * args.A;
+                    if (args.n_active) tact = 1 + min(max(args.n_active[b], 1), args.n);
                     const double *rb = args.robot + (size_t)b * 9;
                     const double ax = args.actions[2 * a], ay = args.actions[2 * a + 1];
                     const int hi = (tok == 0) ? 0 : tok - 1;
@@ -546,6 +547,10 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #pragma unroll
                     for (int k = 0; k < 5; ++k) in14[9 + k] = (float)hb[k];
                     rotate13<OPT>(in14, o);
+                    if (tok >= tact) {               // padding row: not a token of its sample (no vote, no key, no value)
+#pragma unroll
+                        for (int k = 0; k < XD; ++k) o[k] = 0.0f;
+                    }
                 } else if (args.mode == 1) {
                     const int hi = (tok == 0) ? 0 : tok - 1;
                     const float *src = args.states + ((size_t)gs * args.n + hi) * XD;
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 
         // ---------------- phase 1: GRU + adaptive computation time ----------------
         const int max_steps = net.act_fixed ? net.act_steps : 3;
-        bool active = samp >= 0;
+        bool active = samp >= 0 && tok < tact;
         int cnt = 0;
         MARK(); GROUP_BARRIER();
 #pragma unroll 1
@@ -694,7 +699,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             } else {
                 const int any = __syncthreads_or(active && P < 0.95f);
                 cont = any && step < max_steps;
-                active = active && s_need[(step - 1) * 32 + samp] != 0;
+                active = active && s_need[(step - 1) * 32 + samp] != 0;      // (padding rows stay inactive)
             }
             if (warp == 0) tc_fence_after();
             if (tid == 32 && s_iss.pf_stage == -1) {
@@ -802,7 +807,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                         }
                     }
                     kb = kv + (nsamp + samp * (T - 1)) * KV_PITCH + 28 * half;
-                    for (int j = 1; j < T; ++j, kb += KV_PITCH) {
+                    for (int j = 1; j < tact; ++j, kb += KV_PITCH) {
                         const float4 *kp = reinterpret_cast<const float4 *>(kb);
                         float2 d0 = bc2(0.0f), d1 = bc2(0.0f);
 #pragma unroll

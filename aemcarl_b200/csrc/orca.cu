@@ -143,6 +143,7 @@ constexpr int ORCA_WARPS = 4;
 __global__ void __launch_bounds__(ORCA_WARPS * 32) orca_kernel(int B, int n, const double *__restrict__ humans,
                                                                const double *__restrict__ robot, float time_step,
                                                                double safety, int robot_visible,
+                                                               const int32_t *__restrict__ nact,
                                                                double *__restrict__ new_vel)
 {
     __shared__ Line s_lines[ORCA_WARPS][32];
@@ -151,6 +152,12 @@ __global__ void __launch_bounds__(ORCA_WARPS * 32) orca_kernel(int B, int n, con
     const long long agent = (long long)blockIdx.x * ORCA_WARPS + wib;
     if (agent >= (long long)B * n) return;
     const int b = (int)(agent / n), i = (int)(agent - (long long)b * n);
+    // per-environment human count (the 'mixed' scenario rule, crowd_sim.py:337-386): rows >= na are padding
+    const int na = nact ? min(max(nact[b], 0), n) : n;
+    if (i >= na) {
+        if (lane == 0) { new_vel[agent * 2] = 0.0; new_vel[agent * 2 + 1] = 0.0; }
+        return;
+    }
     const double *hb = humans + (size_t)b * n * 8;
     const double *me = hb + i * 8;
     Line *lines = s_lines[wib];
@@ -166,13 +173,13 @@ __global__ void __launch_bounds__(ORCA_WARPS * 32) orca_kernel(int B, int n, con
     const V2 pref = mk((float)pvx, (float)pvy);
 
     // candidate j: other humans in index order, then the robot if visible (crowd_sim.py:565-567)
-    const int m = n - 1 + (robot_visible ? 1 : 0);
+    const int m = na - 1 + (robot_visible ? 1 : 0);
     V2 op = mk(0.f, 0.f), ov = mk(0.f, 0.f);
     float orad = 0.f, distSq = INFINITY;
     bool valid = false;
     if (lane < m) {
         const double *o;
-        if (lane < n - 1) o = hb + (lane < i ? lane : lane + 1) * 8;
+        if (lane < na - 1) o = hb + (lane < i ? lane : lane + 1) * 8;
         else o = robot + (size_t)b * 9;
         op = mk((float)o[0], (float)o[1]);
         ov = mk((float)o[2], (float)o[3]);
@@ -244,13 +251,13 @@ __global__ void __launch_bounds__(ORCA_WARPS * 32) orca_kernel(int B, int n, con
 }
 
 cudaError_t launch_orca(int B, int n, const double *humans, const double *robot, const aem_env_params &p,
-                        double *new_vel, cudaStream_t st)
+                        double *new_vel, cudaStream_t st, const int32_t *nact)
 {
     const long long agents = (long long)B * n;
     if (agents <= 0) return cudaSuccess;
     const int blocks = (int)((agents + ORCA_WARPS - 1) / ORCA_WARPS);
     orca_kernel<<<blocks, ORCA_WARPS * 32, 0, st>>>(B, n, humans, robot, (float)p.time_step, p.orca_safety_space,
-                                                    p.robot_visible, new_vel);
+                                                    p.robot_visible, nact, new_vel);
     return cudaGetLastError();
 }
 

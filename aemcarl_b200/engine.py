@@ -281,6 +281,15 @@ class Engine:
     def launch_count(self):
         return int(self.lib.aem_launch_count(self.h))
 
+    def set_active_counts(self, n_active=None, pool_n_active=None):
+        """per-environment human counts [B] int32 ('mixed' scenes); None = uniform batches.  The tensors must stay alive."""
+        if n_active is not None:
+            self._chk(n_active, I32)
+        if pool_n_active is not None:
+            self._chk(pool_n_active, I32)
+        self._active_counts = (n_active, pool_n_active)
+        check(self.lib.aem_set_active_counts(self.h, _ptr(n_active), _ptr(pool_n_active)))
+
     def set_train_dropout(self, p, seed=0):
         """dropout of the fused training step (nn.TransformerEncoderLayer's four sites); 0 = the eval()-mode network"""
         check(self.lib.aem_set_train_dropout(self.h, float(p), ctypes.c_uint64(int(seed) & (2 ** 64 - 1))))

@@ -142,11 +142,30 @@ def generate_case(phase, case, human_num, rule, circle_radius=4.0, square_width=
     return rb, hs.reshape(human_num, 8)
 
 
+MIXED_MAX_HUMANS = 5       # the largest count either distribution of the 'mixed' rule can draw
+
+
+def generate_mixed_pool(phase, first_case, count, **kw):
+    """'mixed' scenarios stacked for a batch: robot [count][9], humans [count][5][8] (rows beyond a case's human count are
+    padding: parked far away, zero velocity) and n_active [count] int32 -- the per-environment human count the kernels take
+    through aem_set_active_counts."""
+    n = MIXED_MAX_HUMANS
+    robots = np.empty((count, 9), dtype=np.float64)
+    humans = np.zeros((count, n, 8), dtype=np.float64)
+    humans[:, :, 0:2] = humans[:, :, 5:7] = [0.0, -100.0]
+    humans[:, :, 4] = kw.get("human_radius", 0.3)
+    counts = np.zeros(count, dtype=np.int32)
+    for i in range(count):
+        robots[i], hs = generate_case(phase, first_case + i, n, "mixed", **kw)
+        counts[i] = hs.shape[0]
+        humans[i, :hs.shape[0]] = hs
+    return robots, humans, counts
+
+
 def generate_pool(phase, first_case, count, human_num, rule, **kw):
     """Scenarios first_case .. first_case+count-1 stacked: robot [count][9], humans [count][n][8]."""
     if rule == "mixed":
-        raise NotImplementedError("'mixed' draws a different number of humans per case; batches need one n "
-                                  "(play mixed scenes through the serial CrowdSim)")
+        raise ValueError("'mixed' draws a different number of humans per case: use generate_mixed_pool (padded rows + counts)")
     robots = np.empty((count, 9), dtype=np.float64)
     humans = np.empty((count, human_num, 8), dtype=np.float64)
     for i in range(count):

@@ -27,7 +27,17 @@ class VecCrowdSim:
         self.first_case = first_case
         self.case_stride = int(case_stride if case_stride is not None else num_envs)
         kw = dict(scenario_kw or {})
-        if device_scenarios:
+        self.n_active = self.pool_n_active = None
+        if rule == "mixed":
+            # per-environment human count (crowd_sim.py:337-386): padded rows + counts, aem_set_active_counts
+            self.n = scenarios.MIXED_MAX_HUMANS
+            pr, ph, pc = scenarios.generate_mixed_pool(phase, first_case, self.pool_size, **kw)
+            self.pool_robot_h, self.pool_humans_h = pr, ph
+            self.pool_robot = torch.from_numpy(pr).to(self.device)
+            self.pool_humans = torch.from_numpy(ph).to(self.device)
+            self.pool_n_active = torch.from_numpy(pc).to(self.device)
+            self.n_active = torch.zeros((self.B,), dtype=I32, device=self.device)
+        elif device_scenarios:
             # aem_generate_scenarios: the same seeded MT19937 draws on the device (square rule bit-exact, circle rule
             # within an ulp of cos / sin); the host generator stays the bit-exact path of the evaluation phases
             self.pool_robot, self.pool_humans = engine.generate_scenarios(phase, first_case, self.pool_size, self.n, rule, **kw)
@@ -67,6 +77,8 @@ class VecCrowdSim:
         idx = torch.arange(self.B, device=self.device) % self.pool_size
         self.robot.copy_(self.pool_robot[idx])
         self.humans.copy_(self.pool_humans[idx])
+        if self.n_active is not None:
+            self.n_active.copy_(self.pool_n_active[idx])
         self.global_time.zero_()
         self.case_idx.copy_((torch.arange(self.B, device=self.device) + self.case_stride).to(I32))
         self.outcomes.zero_()
@@ -76,11 +88,14 @@ class VecCrowdSim:
         idx = (torch.arange(self.B, device=self.device) + int(first)) % self.pool_size
         self.robot.copy_(self.pool_robot[idx])
         self.humans.copy_(self.pool_humans[idx])
+        if self.n_active is not None:
+            self.n_active.copy_(self.pool_n_active[idx])
         self.global_time.zero_()
 
     def lookahead(self):
         """predict(): ORCA for the humans, per-action env lookahead, fused value lookahead, argmax."""
         e = self.engine
+        e.set_active_counts(self.n_active, self.pool_n_active)          # None, None for uniform batches
         e.orca(self.humans, self.robot, out=self.new_vel)
         e.env_lookahead(self.robot, self.humans, self.new_vel, self.global_time,
                         out=(self.rewards, self.info, self.dmin, self.humans_next))
@@ -91,6 +106,7 @@ class VecCrowdSim:
     def apply(self, chosen=None, auto_reset=True):
         """env.step(action) for the chosen action index of every env; returns (reward, done, info, dmin) [B]."""
         e = self.engine
+        e.set_active_counts(self.n_active, self.pool_n_active)
         chosen = self.best if chosen is None else chosen
         out = e.env_apply(self.robot, self.humans, self.new_vel, self.global_time, chosen, self.rewards, self.info,
                           self.dmin)
@@ -111,7 +127,7 @@ class VecCrowdSim:
         v = copy.copy(self)
         v.B = int(n)
         for name in ("robot", "humans", "global_time", "case_idx", "new_vel", "rewards", "info", "dmin", "humans_next", "values",
-                     "net_values", "act_steps", "best"):
+                     "net_values", "act_steps", "best") + (("n_active",) if self.n_active is not None else ()):
             setattr(v, name, getattr(self, name)[:n])
         v.last = None
         return v

@@ -187,6 +187,14 @@ int aem_transform(aem_handle h, int B, int n, const double *robot_d, const doubl
 int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const float *states_d, const float *targets_d,
                    float *grad_d, float *loss_d, float *values_d, int32_t *steps_d, void *stream);
 
+/* Per-environment human counts: the 'mixed' scenario rule of CrowdSim.reset draws 1..5 humans per case
+ * (crowd_sim/envs/crowd_sim.py:337-386).  n_active_d[B] (int32, device; 1 <= count <= n) makes aem_orca, aem_env_lookahead,
+ * aem_lookahead (precision 0 or 2), aem_env_apply and aem_env_step_xy treat rows >= count of every [B][n][..] array as
+ * padding: no ORCA agent, no collision / occupancy contribution, no token of the value network (attention keys, halting vote).
+ * pool_n_active_d[P] (optional) are the counts of the scenario pool: aem_env_reset_done copies the new case's count.
+ * The pointers are remembered until the next call; NULL restores uniform batches. */
+int aem_set_active_counts(aem_handle h, int32_t *n_active_d, const int32_t *pool_n_active_d);
+
 /* Dropout of the fused training step.  The reference never calls eval(): nn.TransformerEncoderLayer(50, 2, 150) trains
  * with p = 0.1 at four sites per layer (attention weights, attention branch, FFN hidden, FFN branch;
  * crowd_nav/common/qnetwork_factory.py:628-629, trainer.py:65-86).  p > 0 makes aem_train_grad / aem_train_step_adam draw

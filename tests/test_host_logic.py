@@ -238,9 +238,14 @@ def test_fused_training_step_fails_loudly_without_cuda():
     with pytest.raises(Exception) as e:
         tr._step(torch.zeros((4, 5, 13)), torch.zeros((4, 1)))
     assert "CUDA" in str(e.value) or "cuda" in str(e.value)
-    model.train()                                   # dropout-active training is outside the fused kernel's contract
-    with pytest.raises(NotImplementedError):
+    model.train()                                   # dropout-active training is part of the fused kernel's contract now:
+    with pytest.raises(RuntimeError, match="CUDA"):  # the same loud failure without a GPU, no silent autograd path
         tr._step(torch.zeros((4, 5, 13)), torch.zeros((4, 1)))
+    fixed = ValueNetworkTransformerAndGRU(act_fixed=True, act_steps=2).eval()
+    tr2 = Trainer(fixed, None, torch.device("cpu"), 4, fused=True)
+    tr2.set_learning_rate(1e-3, "Adam")
+    with pytest.raises(NotImplementedError):         # act_fixed stays outside the fused kernels
+        tr2._step(torch.zeros((4, 5, 13)), torch.zeros((4, 1)))
 
 
 def test_device_scenario_params_struct_matches_header():

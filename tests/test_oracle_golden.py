@@ -130,8 +130,13 @@ def test_mixed_rule_and_randomized_attributes_match_reference(golden_dir, tag, r
         if rule == "mixed":        # an empty static scene keeps human_num = 0 but carries the parked dummy human
             assert hnum[case] == (0 if (count[case] == 1 and hs[0, 1] == -10 and hs[0, 0] == 0) else count[case])
     if rule == "mixed":
-        with pytest.raises(NotImplementedError):
+        with pytest.raises(ValueError):                     # batches of mixed scenes carry per-environment counts:
             scenarios.generate_pool("test", 0, 4, 5, "mixed")
+        ncase = len(count)
+        pr, ph, pc = scenarios.generate_mixed_pool("test", 0, ncase, randomize_attributes=rand)
+        assert ph.shape == (ncase, 5, 8) and pc.dtype == np.int32 and np.array_equal(pc, count)
+        for i in range(ncase):                              # padded pool rows = the reference's cases, bit for bit
+            assert np.array_equal(ph[i, :pc[i]][:, [0, 1, 5, 6, 4, 7]], rows[i, :pc[i]])
 
 
 def test_explorer_update_memory_targets_match_the_reference(golden_dir):
