@@ -77,7 +77,7 @@ def main(argv=None):
                     help="the optimisation step as hand-written kernels (csrc/train.cu: aem_train_grad + aem_adam_step)")
     ap.add_argument("--updates_per_wave", type=int, default=None,
                     help="optimizer steps after each wave of B episodes (default: train_batches x B, the reference's ratio)")
-    ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3"],
+    ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3", "fp16x1"],
                     help="arithmetic of the lookahead kernel in the vectorised RL phase")
     args = ap.parse_args(argv)
 

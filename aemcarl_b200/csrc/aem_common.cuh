@@ -109,7 +109,7 @@ struct aem_handle_s {
     aem::TcLayer *h16_layers_d;
     size_t h16_img_halves;
     size_t tc_img_floats;
-    int precision;       // 0 = FP32 FFMA kernel, 1 = tcgen05 3xTF32 kernel, 2 = tcgen05 FP16x3 kernel (2 tiles / SM)
+    int precision;       // 0 = FP32 FFMA kernel, 1 = tcgen05 3xTF32 kernel, 2 = tcgen05 FP16x3 kernel (2 tiles / SM), 3 = its single-pass mode
     aem::NetParams net;
     bool weights_set, actions_set, params_set;
     double *actions_d;   // [A][2]
@@ -149,7 +149,7 @@ namespace aem {
 struct LookaheadArgs;
 cudaError_t launch_lookahead(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
 cudaError_t launch_lookahead_tc(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
-cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStream_t st);
+cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStream_t st, bool single_pass = false);
 cudaError_t launch_transform(const double *robot, const double *humans, int B, int n, float *out, cudaStream_t st);
 cudaError_t launch_select(const double *values, const double *robot, int B, int A, int32_t *best, cudaStream_t st);
 cudaError_t launch_orca(int B, int n, const double *humans, const double *robot, const aem_env_params &p,

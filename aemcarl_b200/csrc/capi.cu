@@ -432,8 +432,8 @@ int aem_set_act_mode(aem_handle h, int act_fixed, int act_steps)
 int aem_set_precision(aem_handle h, int precision)
 {
     if (!h) return aem_set_error(AEM_ERR_INVALID, "null handle");
-    if (precision < 0 || precision > 2)
-        return aem_set_error(AEM_ERR_INVALID, "precision must be 0 (fp32), 1 (tf32x3) or 2 (fp16x3)");
+    if (precision < 0 || precision > 3)
+        return aem_set_error(AEM_ERR_INVALID, "precision must be 0 (fp32), 1 (tf32x3), 2 (fp16x3) or 3 (fp16x1: single pass, opt-in)");
     h->precision = precision;
     return AEM_OK;
 }
@@ -499,7 +499,7 @@ int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const doubl
     a.n_active = h->nact_d;
     if (h->nact_d && h->precision == 1)
         return aem_set_error(AEM_ERR_STATE, "per-environment human counts need precision 0 (fp32) or 2 (fp16x3)");
-    AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
+    AEM_CUDA_CHECK(h->precision >= 2 ? launch_lookahead_h16(h, a, as_stream(stream), h->precision == 3)
                    : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
                                        : launch_lookahead(h, a, as_stream(stream)));
     AEM_CUDA_CHECK(launch_select(values_d, robot_d, B, h->A, best_d, as_stream(stream)));
@@ -586,7 +586,7 @@ int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *
     a.total_samples = S;
     a.states = states_d;
     a.net_values = values_d; a.steps = steps_d;
-    AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
+    AEM_CUDA_CHECK(h->precision >= 2 ? launch_lookahead_h16(h, a, as_stream(stream), h->precision == 3)
                    : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
                                        : launch_lookahead(h, a, as_stream(stream)));
     h->launches += (S > 0);
@@ -623,7 +623,7 @@ int aem_gru_act(aem_handle h, int S, int T, const float *x_d, float *out_d, uint
     a.total_samples = S;
     a.states = x_d;
     a.gru_out = out_d; a.steps = steps_d;
-    AEM_CUDA_CHECK(h->precision == 2 ? launch_lookahead_h16(h, a, as_stream(stream))
+    AEM_CUDA_CHECK(h->precision >= 2 ? launch_lookahead_h16(h, a, as_stream(stream), h->precision == 3)
                    : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
                                        : launch_lookahead(h, a, as_stream(stream)));
     h->launches += (S > 0);

@@ -92,22 +92,16 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoidf_(float x) { return rcpf(1.0f + ex2f(-LOG2E * x)); }
-__device__ __forceinline__ float sigmoid_legacy(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_legacy(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 // sigma(relu(v)) of a pair: 1 / (1 + 2^min(-v log2 e, 0))
-template <int OPT>
 __device__ __forceinline__ float2 sigmoid_relu2(float2 v)
 {
-    if (OPT & 4) return f2(sigmoid_legacy(fmaxf(v.x, 0.0f)), sigmoid_legacy(fmaxf(v.y, 0.0f)));
     const float2 t = mul2(v, bc2(-LOG2E));
     const float2 d = add2(f2(ex2f(fminf(t.x, 0.0f)), ex2f(fminf(t.y, 0.0f))), bc2(1.0f));
     return f2(rcpf(d.x), rcpf(d.y));
 }
 // tanh of a pair: 1 - 2 / (2^(2 v log2 e) + 1)
-template <int OPT>
 __device__ __forceinline__ float2 tanh2(float2 v)
 {
-    if (OPT & 4) return f2(tanh_legacy(v.x), tanh_legacy(v.y));
     const float2 t = mul2(v, bc2(2.0f * LOG2E));
     const float2 d = add2(f2(ex2f(t.x), ex2f(t.y)), bc2(1.0f));
     return fma2(f2(rcpf(d.x), rcpf(d.y)), bc2(-2.0f), bc2(1.0f));
@@ -142,20 +136,11 @@ __device__ __forceinline__ void ld2p(uint32_t taddr, float2 *v)       // 2 colum
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(v[0].x), "=f"(v[0].y) : "r"(taddr) : "memory");
 }
 // the 26 leading columns of a 32-column block (25 real + the first padding column) -> 13 pairs
-template <int OPT>
 __device__ __forceinline__ void ld26p(uint32_t taddr, float2 *v)
 {
-    if (OPT & 8) {
-        float2 t[16];
-        ld8p(taddr, t); ld8p(taddr + 8, t + 4); ld8p(taddr + 16, t + 8); ld8p(taddr + 24, t + 12);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 13; ++i) v[i] = t[i];
-    } else {
-        ld16p(taddr, v);
-        ld8p(taddr + 16, v + 8);
-        ld2p(taddr + 24, v + 12);
-    }
+    ld16p(taddr, v);
+    ld8p(taddr + 16, v + 8);
+    ld2p(taddr + 24, v + 12);
 }
 __device__ __forceinline__ void st8u(uint32_t taddr, const uint32_t *v)
 {
@@ -191,21 +176,22 @@ __device__ __forceinline__ void split2_relu(float2 a, uint32_t &hi, uint32_t &lo
 }
 // Operand block of a thread: 16 columns hi at `hi_addr`, 16 columns lo 32 further; column j = K slots (2j, 2j + 1).
 // Columns 0..12 are split from the 13 pairs `v`; columns 13..15 (x slots / constants) arrive already split.
-template <int OPT>
+// X1 (single-pass mode, aem_set_precision 3): only the hi columns exist.
+template <bool X1>
 __device__ __forceinline__ void st16_split(uint32_t hi_addr, const float2 *v, uint32_t h13, uint32_t h14, uint32_t h15,
                                            uint32_t l13, uint32_t l14, uint32_t l15)
 {
     uint32_t h[16], l[16];
 #pragma unroll
-    for (int i = 0; i < 13; ++i) split2(v[i], h[i], l[i]);
+    for (int i = 0; i < 13; ++i) {
+        if (X1) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(v[i].y), "f"(v[i].x));
+        else split2(v[i], h[i], l[i]);
+    }
     h[13] = h13; h[14] = h14; h[15] = h15;
-    l[13] = l13; l[14] = l14; l[15] = l15;
-    if (OPT & 8) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { st4u(hi_addr + 4 * c, h + 4 * c); st4u(hi_addr + 32 + 4 * c, l + 4 * c); }
-    } else {
-        st8u(hi_addr, h);
-        st8u(hi_addr + 8, h + 8);
+    st8u(hi_addr, h);
+    st8u(hi_addr + 8, h + 8);
+    if (!X1) {
+        l[13] = l13; l[14] = l14; l[15] = l15;
         st8u(hi_addr + 32, l);
         st8u(hi_addr + 40, l + 8);
     }
@@ -215,7 +201,7 @@ __device__ __forceinline__ void st16_split(uint32_t hi_addr, const float2 *v, ui
 // at a time: accumulators [16c, 16c + 16) -> hi columns [16c, 16c + 8), lo columns [16c + 8, 16c + 16).  Every chunk is
 // read completely before it is overwritten and touches no other chunk, so the loop stays rolled (instruction-cache
 // footprint) and needs no staging registers.  k-step ks of the operand = chunk ks: hi at 16 ks, lo at 16 ks + 8.
-template <int W>
+template <int W, bool X1>
 __device__ __forceinline__ void relu_inplace(uint32_t base)
 {
 #pragma unroll 1
@@ -225,22 +211,23 @@ __device__ __forceinline__ void relu_inplace(uint32_t base)
         tmem_wait_ld();
         uint32_t h[8], l[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split2_relu(v[i], h[i], l[i]);
+        for (int i = 0; i < 8; ++i) {
+            if (X1) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(v[i].y), "f"(v[i].x));
+            else split2_relu(v[i], h[i], l[i]);
+        }
         st8u(base + 16 * c, h);
-        st8u(base + 16 * c + 8, l);
+        if (!X1) st8u(base + 16 * c + 8, l);
     }
 }
 
 // cadrl.py:239-274 (see lookahead.cu for the literal form).  cos / sin of rot = atan2(dy, dx) are dx / |d| and dy / |d|
 // (atan2(0, 0) = 0 -> 1, 0): the same rotation to ~1 ulp without the three transcendental calls.
-template <int OPT>
 __device__ __forceinline__ void rotate13(const float *s, float *o)
 {
     const float dx = s[5] - s[0], dy = s[6] - s[1];
     const float dg = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
     const float inv = dg > 0.0f ? 1.0f / dg : 0.0f;
-    float c = dg > 0.0f ? dx * inv : 1.0f, sn = dy * inv;
-    if (OPT & 2) { const float rot = atan2f(dy, dx); c = cosf(rot); sn = sinf(rot); }
+    const float c = dg > 0.0f ? dx * inv : 1.0f, sn = dy * inv;
     o[0] = dg;
     o[1] = s[7];
     o[2] = 0.0f;
@@ -282,7 +269,7 @@ __device__ __forceinline__ int layer_at(int st, int idx)
     return idx < 21 ? TL_ENC + idx : (idx == 21 ? TL_A0 : TL_A2);
 }
 // chunk table entry: offset into the image in units of 8 halves (16 B) | bytes / 16 << 20
-__device__ __noinline__ void build_chunk_table(const TcLayer *layers, uint32_t *chunks, int *stage_beg)
+__device__ __noinline__ void build_chunk_table(const TcLayer *layers, uint32_t *chunks, int *stage_beg, int nparts)
 {
     int n = 0;
     for (int st = 0; st < 3; ++st) {
@@ -291,7 +278,7 @@ __device__ __noinline__ void build_chunk_table(const TcLayer *layers, uint32_t *
             const TcLayer L = layers[layer_at(st, i)];
             const int nsplit = L.bias_off;                 // h16 tables carry the k-split count in this field
             const int bytes = L.bytes / nsplit;
-            for (int part = 0; part < 2; ++part)
+            for (int part = 0; part < nparts; ++part)       // hi images, then lo images (single-pass mode: hi only)
                 for (int sub = 0; sub < nsplit; ++sub)
                     chunks[n++] = (uint32_t)(((part ? L.off_lo : L.off_hi) + sub * (bytes / 2)) >> 3) | ((uint32_t)(bytes >> 4) << 20);
         }
@@ -346,7 +333,7 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 // One layer: KS k-steps (16 K values = 8 operand columns each) per pass.  Operand column of k-step ks:
 //   a_base + HSTRIDE * (ks / KSH) + KSTR * (ks % KSH), lo part LO columns further.  SPECIAL: step-1 images use the
 //   k-steps {1, 3} of A1 (the x slots).
-template <int N, int KS, int KSH, int HSTRIDE, int KSTR, int LO, bool SPECIAL, int SPLIT>
+template <int N, int KS, int KSH, int HSTRIDE, int KSTR, int LO, bool SPECIAL, int SPLIT, bool X1>
 __device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t ring, uint32_t tm, uint32_t a_base, uint32_t d,
                                         bool accumulate)
 {
@@ -357,7 +344,7 @@ __device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t rin
     static_assert(KS % SPLIT == 0, "split");
     const bool leader = elect_one();
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {               // part 0: W_hi (A_hi and A_lo passes), part 1: W_lo (A_hi pass)
+    for (int part = 0; part < (X1 ? 1 : 2); ++part) {    // part 0: W_hi (A_hi and A_lo passes), part 1: W_lo (A_hi pass)
 #pragma unroll
         for (int sub = 0; sub < SPLIT; ++sub) {
             mbar_wait(&wfull[r.buf], r.par);         // all lanes, uniform
@@ -373,7 +360,7 @@ __device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t rin
                 if (leader) {
                     if (part == 0) {
                         mma_f16_ts(tm + d, tm + a_base + acol, bd, IDESC, (ks == 0 && !accumulate) ? 0u : 1u);
-                        mma_f16_ts(tm + d, tm + a_base + acol + LO, bd, IDESC, 1u);
+                        if (!X1) mma_f16_ts(tm + d, tm + a_base + acol + LO, bd, IDESC, 1u);
                     } else {
                         mma_f16_ts(tm + d, tm + a_base + acol, bd, IDESC, 1u);
                     }
@@ -384,13 +371,13 @@ __device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t rin
 }
 // shorthand for the three operand layouts
 // (images larger than one ring slot -- N * K = 8192 -- are streamed as two k-halves: SPLIT = 2)
-#define ISSUE_K64(N, a, d, acc) issue_t<N, 4, 4, 0, 8, 32, false, ((N) * 64 > 6144 ? 2 : 1)>(ir, wfull, ring, tm, a, d, acc)
-#define ISSUE_K64S(N, a, d) issue_t<N, 2, 4, 0, 8, 32, true, 1>(ir, wfull, ring, tm, a, d, false)        /* step-1 images   */
-#define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 16, 8, false, 2>(ir, wfull, ring, tm, a, d, false)   /* in-place 2 x 4 x [8|8] */
-#define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 16, 8, false, 1>(ir, wfull, ring, tm, a, d, acc) /* in-place 2 x 3 x [8|8] */
+#define ISSUE_K64(N, a, d, acc) issue_t<N, 4, 4, 0, 8, 32, false, ((N) * 64 > 6144 ? 2 : 1), X1>(ir, wfull, ring, tm, a, d, acc)
+#define ISSUE_K64S(N, a, d) issue_t<N, 2, 4, 0, 8, 32, true, 1, X1>(ir, wfull, ring, tm, a, d, false)        /* step-1 images   */
+#define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 16, 8, false, 2, X1>(ir, wfull, ring, tm, a, d, false)   /* in-place 2 x 4 x [8|8] */
+#define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 16, 8, false, 1, X1>(ir, wfull, ring, tm, a, d, acc) /* in-place 2 x 3 x [8|8] */
 
-// OPT bit 0: only warp 0 polls the commit mbarrier of a group, the other warps sleep on a hardware barrier
-template <int OPT>
+// X1: the single-pass mode (A_hi W_hi only; opt-in, own tolerance: tests/test_gpu_parity.py)
+template <bool X1>
 __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArgs args)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -428,7 +415,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     const uint32_t tl = tm + lane_base;
     const uint32_t ring = smem_u32(wbuf);
     if (tid == 32) {
-        build_chunk_table(net.h16_layers_d, s_chunks, s_stage_beg);
+        build_chunk_table(net.h16_layers_d, s_chunks, s_stage_beg, X1 ? 1 : 2);
         for (int i = 0; i < NEV; ++i) s_iss.used_ev[i] = 0;
         s_iss.nused = s_iss.ubuf = s_iss.upar = 0;
         s_iss.nloaded = s_iss.nfree = s_iss.lbuf = 0;
@@ -459,16 +446,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         mbar_wait(&evb[(e) % NEV], (uint32_t)(((e) / NEV) & 1));        \
         tc_fence_after();                                               \
     } while (0)
-#define WAIT_EVENT(e)                                                                   \
-    do {                                                                                \
-        if (OPT & 1) {                                                                  \
-            if (warp == 0) { mbar_wait(&evb[(e) % NEV], (uint32_t)(((e) / NEV) & 1)); tc_fence_before(); } \
-            asm volatile("bar.sync 5, 256;" ::: "memory");                              \
-            tc_fence_after();                                                           \
-        } else {                                                                        \
-            WAIT_EVENT_POLL(e);                                                         \
-        }                                                                               \
-    } while (0)
+#define WAIT_EVENT(e) WAIT_EVENT_POLL(e)
 #define ISSUE_BEGIN() \
     IssReg ir;        \
     ir.buf = (uint32_t)s_iss.ubuf; ir.par = (uint32_t)s_iss.upar; ir.n = (uint32_t)s_iss.nused
@@ -546,7 +524,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     in14[7] = (float)rb[7]; in14[8] = (float)rb[8];
 #pragma unroll
                     for (int k = 0; k < 5; ++k) in14[9 + k] = (float)hb[k];
-                    rotate13<OPT>(in14, o);
+                    rotate13(in14, o);
                     if (tok >= tact) {               // padding row: not a token of its sample (no vote, no key, no value)
 #pragma unroll
                         for (int k = 0; k < XD; ++k) o[k] = 0.0f;
@@ -579,7 +557,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #pragma unroll
             for (int j = 0; j < 13; ++j) v[j] = bc2(0.0f);
             v[12].y = xh0;
-            st16_split<OPT>(a1, v, xph[0], xph[1], xph[2], xpl[0], xpl[1], xpl[2]);
+            st16_split<X1>(a1, v, xph[0], xph[1], xph[2], xpl[0], xpl[1], xpl[2]);
             if (tid < 96) s_need[tid] = 0;
         }
 
@@ -600,7 +578,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #pragma unroll
             for (int gate = 0; gate < 2; ++gate) {
                 if (gate == 1 && !kfull) break;
-                if (gate || (OPT & 16)) { MARK(); GROUP_BARRIER(); }
+                if (gate) { MARK(); GROUP_BARRIER(); }
                 const int e_g1 = nev++;
                 if (warp == 0) {
                     ISSUE_BEGIN();
@@ -612,7 +590,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 __syncwarp();
                 MARK(); WAIT_EVENT(e_g1); MARK();
                 PRODUCE(e_g1); MARK();
-                relu_inplace<64>(tl + D1 + 64 * half);
+                relu_inplace<64, X1>(tl + D1 + 64 * half);
                 MARK(); GROUP_BARRIER();
                 const int e_g2 = nev++;
                 if (warp == 0) {
@@ -625,16 +603,16 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 MARK(); WAIT_EVENT(e_g2); MARK();
                 PRODUCE(e_g2); MARK();
                 float2 v[13];
-                ld26p<OPT>(tl + D2 + 32 * half, v);
+                ld26p(tl + D2 + 32 * half, v);
                 tmem_wait_ld();
                 if (gate == 0) {
 #pragma unroll
-                    for (int j = 0; j < 13; ++j) z[j] = sigmoid_relu2<OPT>(v[j]);
+                    for (int j = 0; j < 13; ++j) z[j] = sigmoid_relu2(v[j]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 13; ++j) v[j] = mul2(sigmoid_relu2<OPT>(v[j]), hn[j]);
+                    for (int j = 0; j < 13; ++j) v[j] = mul2(sigmoid_relu2(v[j]), hn[j]);
                     v[12].y = xh0;
-                    st16_split<OPT>(tl + A3 + 16 * half, v, xph[0], xph[1], xph[2], xpl[0], xpl[1], xpl[2]);
+                    st16_split<X1>(tl + A3 + 16 * half, v, xph[0], xph[1], xph[2], xpl[0], xpl[1], xpl[2]);
                 }
             }
             // ---- q, h = (1 - z) h + z q
@@ -652,31 +630,26 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             PRODUCE(e_q); MARK();
             {
                 float2 v[13];
-                ld26p<OPT>(tl + D2 + 32 * half, v);
+                ld26p(tl + D2 + 32 * half, v);
                 tmem_wait_ld();
                 const float4 *pw = reinterpret_cast<const float4 *>(PB + PB_PW + 28 * half);
                 float2 pd = bc2(0.0f);
 #pragma unroll
                 for (int j = 0; j < 13; ++j) {
-                    const float2 qv = tanh2<OPT>(v[j]);
-                    if (OPT & 32) {
-                        hn[j].x = __fadd_rn(__fmul_rn(1.0f - z[j].x, hn[j].x), __fmul_rn(z[j].x, qv.x));
-                        hn[j].y = __fadd_rn(__fmul_rn(1.0f - z[j].y, hn[j].y), __fmul_rn(z[j].y, qv.y));
-                    } else {
-                        hn[j] = fma2(z[j], sub2(qv, hn[j]), hn[j]);
-                    }
+                    const float2 qv = tanh2(v[j]);
+                    hn[j] = fma2(z[j], sub2(qv, hn[j]), hn[j]);
                     if (j == 12) hn[12].y = 0.0f;                  // padding column
                     const float4 w4 = pw[j >> 1];
                     pd = fma2(hn[j], (j & 1) ? f2(w4.z, w4.w) : f2(w4.x, w4.y), pd);
                     v[j] = hn[j];
                 }
                 v[12].y = xh0;
-                st16_split<OPT>(tl + A1 + 16 * half, v, xph[0], xph[1], xph[2], xpl[0], xpl[1], xpl[2]);
+                st16_split<X1>(tl + A1 + 16 * half, v, xph[0], xph[1], xph[2], xpl[0], xpl[1], xpl[2]);
                 if (!net.act_fixed) {
                     sx[half * 128 + row] = pd.x + pd.y;
                     pair_sync(q4);
                     if (active) {
-                        const float p = (OPT & 4) ? sigmoid_legacy(sx[row] + sx[128 + row] + PB[PB_PWB]) : sigmoidf_(sx[row] + sx[128 + row] + PB[PB_PWB]);
+                        const float p = sigmoidf_(sx[row] + sx[128 + row] + PB[PB_PWB]);
                         P += p;
 #pragma unroll
                         for (int j = 0; j < 13; ++j) ACC[j] = fma2(bc2(p), hn[j], ACC[j]);
@@ -734,7 +707,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         // constant columns 13..15 of the encoder operands: zeros and the bias slot (slot 31 of half 1 = 1.0)
         const uint32_t one_hi = half ? 0x3C000000u : 0u;
         {
-            st16_split<OPT>(tl + AE + 16 * half, xres, 0u, 0u, one_hi, 0u, 0u, 0u);
+            st16_split<X1>(tl + AE + 16 * half, xres, 0u, 0u, one_hi, 0u, 0u, 0u);
         }
 
         // ---------------- phase 2: 3 x post-norm encoder layer ----------------
@@ -838,7 +811,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 for (int c = 0; c < 13; ++c) o[c] = oo[c];
                 o[12].y = 0.0f;
             }
-            if (live) st16_split<OPT>(tl + AATT + 16 * half, o, 0u, 0u, one_hi, 0u, 0u, 0u);
+            if (live) st16_split<X1>(tl + AATT + 16 * half, o, 0u, 0u, one_hi, 0u, 0u, 0u);
             // ---- out_proj + residual + LayerNorm1
             MARK(); GROUP_BARRIER();
             const int e_out = nev++;
@@ -873,7 +846,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     for (int c = 0; c < 2; ++c) {
                         MARK(); WAIT_EVENT(e_f1 + c); MARK();
                         PRODUCE(e_f1 + c); MARK();
-                        if (live) relu_inplace<48>(tl + (c ? DF1B : DF1A) + 48 * half);
+                        if (live) relu_inplace<48, X1>(tl + (c ? DF1B : DF1A) + 48 * half);
                         MARK(); GROUP_BARRIER();
                         if (warp == 0) {
                             if (c == 0) WAIT_EVENT_POLL(e_f1 + 1);   // F1B reads AE, which D_F2 aliases: complete before linear2 starts
@@ -891,7 +864,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 float2 s2 = bc2(0.0f);
                 {
                     float2 v[13];
-                    ld26p<OPT>(tl + (pass ? DF2 : DOUT) + 32 * half, v);
+                    ld26p(tl + (pass ? DF2 : DOUT) + 32 * half, v);
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 13; ++j) { xres[j] = add2(xres[j], v[j]); s2 = add2(s2, xres[j]); }
@@ -928,7 +901,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     a[12].y = selfs[0];
                     split2(f2(selfs[1], selfs[2]), h13, l13);
                 }
-                st16_split<OPT>(tl + AE + 16 * half, a, h13, 0u, one_hi, l13, 0u, 0u);
+                st16_split<X1>(tl + AE + 16 * half, a, h13, 0u, one_hi, l13, 0u, 0u);
             }
         }
 
@@ -945,7 +918,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         MARK(); WAIT_EVENT(e_a0); MARK();
         PRODUCE(e_a0); MARK();
         const bool live_a = q4 * 32 < nsamp;      // only token-0 rows feed the value head
-        if (live_a) relu_inplace<64>(tl + DA0 + 64 * half);
+        if (live_a) relu_inplace<64, X1>(tl + DA0 + 64 * half);
         MARK(); GROUP_BARRIER();
         const int e_a2 = nev++;
         if (warp == 0) {
@@ -961,7 +934,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             const float4 *w4 = reinterpret_cast<const float4 *>(PB + PB_A4 + 28 * half);
             float2 pd = bc2(0.0f);
             float2 v[13];
-            ld26p<OPT>(tl + DA2 + 32 * half, v);
+            ld26p(tl + DA2 + 32 * half, v);
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 13; ++j) {
@@ -1005,33 +978,16 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 
 }  // namespace h16
 
-cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStream_t st)
+cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStream_t st, bool single_pass)
 {
     static bool attr_set[64] = {false};
-    static int opt = -1;
-    if (opt < 0) {
-        const char *e = getenv("AEM_H16_OPT");
-        opt = e ? atoi(e) : 0;
-    }
-    void (*kern)(const LookaheadArgs) = h16::lookahead_h16_kernel<0>;
-    switch (opt) {
-    case 1: kern = h16::lookahead_h16_kernel<1>; break;
-    case 2: kern = h16::lookahead_h16_kernel<2>; break;
-    case 4: kern = h16::lookahead_h16_kernel<4>; break;
-    case 8: kern = h16::lookahead_h16_kernel<8>; break;
-    case 14: kern = h16::lookahead_h16_kernel<14>; break;
-    case 16: kern = h16::lookahead_h16_kernel<16>; break;
-    case 32: kern = h16::lookahead_h16_kernel<32>; break;
-    default: break;
-    }
+    void (*kern)(const LookaheadArgs) = single_pass ? h16::lookahead_h16_kernel<true> : h16::lookahead_h16_kernel<false>;
     if (!attr_set[h->device & 63]) {
-        void (*all[])(const LookaheadArgs) = {h16::lookahead_h16_kernel<0>, h16::lookahead_h16_kernel<1>, h16::lookahead_h16_kernel<2>,
-                                              h16::lookahead_h16_kernel<4>, h16::lookahead_h16_kernel<8>, h16::lookahead_h16_kernel<14>,
-                                              h16::lookahead_h16_kernel<16>, h16::lookahead_h16_kernel<32>};
-        for (auto k : all) {
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h16::SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = cudaFuncSetAttribute(h16::lookahead_h16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)h16::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(h16::lookahead_h16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h16::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
         attr_set[h->device & 63] = true;
     }
     const int ntiles = (a.total_samples + a.S - 1) / a.S;

@@ -69,9 +69,10 @@ class Engine:
         check(self.lib.aem_set_act_mode(self.h, int(bool(act_fixed)), int(act_steps)))
 
     def set_precision(self, precision):
-        """'fp32' (FFMA kernel, default: the parity anchor), 'tf32x3' (tcgen05, one tile / SM, FP32-range containers) or
-        'fp16x3' (tcgen05, two tiles / SM: the fastest, bench.py's default)"""
-        mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2, 0: 0, 1: 1, 2: 2}[precision]
+        """'fp32' (FFMA kernel, default: the parity anchor), 'tf32x3' (tcgen05, one tile / SM, FP32-range containers),
+        'fp16x3' (tcgen05, two tiles / SM: bench.py's default, FP32-grade) or 'fp16x1' (the same kernel with ONE fp16 pass per
+        product: opt-in, values within ~1e-2 relative -- its own tolerance, tests/test_gpu_parity.py)"""
+        mode = {"fp32": 0, "tf32x3": 1, "fp16x3": 2, "fp16x1": 3, 0: 0, 1: 1, 2: 2, 3: 3}[precision]
         check(self.lib.aem_set_precision(self.h, mode))
         self.precision = mode
 

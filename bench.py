@@ -302,7 +302,7 @@ def main():
     ap.add_argument("--pool", type=int, default=0, help="scenario pool size (default min(envs, 8192))")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-envs", type=int, default=256, help="--impl reference: envs per step (bounded sample)")
-    ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3"],
+    ap.add_argument("--precision", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3", "fp16x1"],
                     help="value-network GEMM arithmetic: tcgen05 FP16x3 with two tiles per SM (default), tcgen05 3xTF32, "
                          "or the FP32 FFMA kernel")
     ap.add_argument("--weights", default=None,
@@ -442,6 +442,7 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "kernel": {"tf32x3": "lookahead_tc_kernel", "fp16x3": "lookahead_h16_kernel",
+                           "fp16x1": "lookahead_h16_kernel<single pass>",
                            "fp32": "lookahead_kernel"}[args.precision],
                 "kernel_ms": kernel_ms,
                 "kernel_share_of_step": float(look_ms.sum() / step_ms.sum()),
@@ -449,6 +450,8 @@ def main():
                 "pipe": {"tf32x3": "tcgen05 kind::tf32, 3xTF32 split (3 MMAs per product, FP32 accumulate in TMEM)",
                          "fp16x3": "tcgen05 kind::f16, FP16 hi/lo split (3 MMAs per product, FP32 accumulate in TMEM), "
                                    "2 tiles in flight per SM",
+                         "fp16x1": "tcgen05 kind::f16, ONE fp16 pass per product (opt-in mode, value tolerance 2e-2), FP32 "
+                                   "accumulate in TMEM, 2 tiles in flight per SM",
                          "fp32": "fp32_ffma (no tensor-core math)"}[args.precision],
 
                 "fp32_pipe_peak_tflops": fp32_peak, "frac_fp32_pipe": achieved / fp32_peak,
@@ -495,6 +498,7 @@ def main():
                "scaling": cfg["scaling"], "vs_baseline": None,
                "dtype": {"tf32x3": "tf32x3 (fp32-equivalent split, fp32 accumulate)",
                          "fp16x3": "fp16x3 (fp16 hi/lo split = 22 mantissa bits, fp32 accumulate)",
+                         "fp16x1": "fp16 (single pass, 11 mantissa bits, fp32 accumulate): opt-in, NOT the parity mode",
                          "fp32": "f32"}[args.precision],
                "data": "synthetic",
                "config": {"baseline_config": cfg["name"],
