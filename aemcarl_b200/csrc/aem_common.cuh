@@ -130,6 +130,8 @@ struct aem_handle_s {
     size_t tr_stash_floats, tr_gru_floats;
     int32_t *nact_d;               // per-environment human counts (aem_set_active_counts), or null: every env has n humans
     const int32_t *pool_nact_d;    // the same for the scenario pool of aem_env_reset_done
+    float *tail_d;                 // lookahead_h16: staged token-0 rows
+    size_t tail_floats;
     double drop_p;                 // dropout of the fused training step (aem_set_train_dropout); 0 = eval() mode
     unsigned long long drop_seed, drop_ctr;
     long long tr_generation;   // bumped whenever the training scratch is reallocated (captured graphs hold its pointers)
@@ -201,7 +203,9 @@ struct LookaheadArgs {
     uint8_t *steps;
     float *gru_out;        // mode 2: [S*T][50]
     const int32_t *n_active;   // mode 0, optional: humans of every environment [B] ('mixed' scenes); token rows beyond it are padding
+    float *tail;           // lookahead_h16: per-CTA scratch of staged token-0 rows [grid][128][TAIL_ROW]
     long long *dbg;        // optional debug buffer (lookahead_h16.cu: AEM_H16_TIMELINE / AEM_H16_WATCHDOG builds)
+    int dbg_tile;          // timeline build: which of CTA 0's tiles is stamped
     int stagger_ns;        // lookahead_h16: start-up delay of the second CTA of every SM (anti-phase the two tiles)
 };
 }  // namespace aem

@@ -308,6 +308,7 @@ int aem_destroy(aem_handle h)
     cudaFree(h->s_rewards); cudaFree(h->s_dmin); cudaFree(h->s_hnext); cudaFree(h->s_values);
     cudaFree(h->s_oreward); cudaFree(h->s_info); cudaFree(h->s_best); cudaFree(h->s_odone); cudaFree(h->s_oinfo);
     if (h->s_stream) cudaStreamDestroy(as_stream(h->s_stream));
+    cudaFree(h->tail_d);
     cudaFree(h->tr_part); cudaFree(h->tr_sqerr); cudaFree(h->tr_stash); cudaFree(h->tr_flags); cudaFree(h->tr_gru);
     delete h;
     return AEM_OK;

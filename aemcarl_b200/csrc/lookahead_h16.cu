@@ -50,6 +50,11 @@ constexpr int WBUF_BYTES = 12288;       // one N = 96, K = 64 image; 16 KB image
 constexpr int KV_PITCH = 116;           // [k head 0 (28) | k head 1 (28) | v head 0 (28) | v head 1 (28)] + 4: float4 access, conflict-free
 constexpr int NEV = 4;
 constexpr int PBLK_MAX = H16_PBLK_FLOATS;
+// Token-0 compaction (SURVEY 8d "exact algorithmic savings"): after the last encoder layer's attention only token 0 of a
+// sample is needed, so its rows (attention output, residual stream, self state) are staged in a per-CTA scratch and
+// out_proj / FFN / LayerNorm / action MLP run ONCE for the token-0 rows of several tiles (a "tail" of up to 128 rows).
+constexpr int TAIL_HALF = 56;            // floats per (row, thread half): o 26 | residual 26 | self 3 | sample index (half 0)
+constexpr int TAIL_ROW = 2 * TAIL_HALF;
 
 // ---- tensor-memory column map: 256 columns per CTA ----
 constexpr uint32_t A1 = 0;              // [h;x]   K = 64  : hi cols [0,32) lo cols [32,64)
@@ -258,21 +263,25 @@ struct Issuer {
     int nloaded, nfree, lbuf;       // producer: chunks requested / released, ring slot of the next request
     int pf_cur, pf_end, pf_stage;   // producer: cursor into the chunk table; stage -1 = waiting for the ACT decision, -2 = done
     int tiles_left;
+    int tiles_done, tail_every;     // the tail stage follows every tail_every-th tile of the CTA (and its last one)
 };
 struct IssReg { uint32_t buf, par, n; };
 constexpr int MAX_CHUNKS = 128;
-__device__ __forceinline__ int stage_len(int st) { return st == 0 ? 3 : (st == 1 ? 5 : 23); }
+// stage 0: GRU step 1, 1: GRU steps 2.., 2: encoder layers 0, 1 and the in_proj of layer 2, 3: the tail (out_proj, FFN of layer 2
+// and the action MLP on the staged token-0 rows)
+__device__ __forceinline__ int stage_len(int st) { return st == 0 ? 3 : (st == 1 ? 5 : (st == 2 ? 16 : 7)); }
 __device__ __forceinline__ int layer_at(int st, int idx)
 {
     if (st == 0) return idx == 0 ? TL_Z1S : (idx == 1 ? TL_Z2 : TL_QS);
     if (st == 1) return idx == 0 ? TL_Z1 : (idx == 1 ? TL_Z2 : (idx == 2 ? TL_R1 : (idx == 3 ? TL_R2 : TL_Q)));
-    return idx < 21 ? TL_ENC + idx : (idx == 21 ? TL_A0 : TL_A2);
+    if (st == 2) return TL_ENC + idx;
+    return idx < 5 ? TL_ENC + 16 + idx : (idx == 5 ? TL_A0 : TL_A2);
 }
 // chunk table entry: offset into the image in units of 8 halves (16 B) | bytes / 16 << 20
 __device__ __noinline__ void build_chunk_table(const TcLayer *layers, uint32_t *chunks, int *stage_beg, int nparts)
 {
     int n = 0;
-    for (int st = 0; st < 3; ++st) {
+    for (int st = 0; st < 4; ++st) {
         stage_beg[st] = n;
         for (int i = 0; i < stage_len(st); ++i) {
             const TcLayer L = layers[layer_at(st, i)];
@@ -283,7 +292,7 @@ __device__ __noinline__ void build_chunk_table(const TcLayer *layers, uint32_t *
                     chunks[n++] = (uint32_t)(((part ? L.off_lo : L.off_hi) + sub * (bytes / 2)) >> 3) | ((uint32_t)(bytes >> 4) << 20);
         }
     }
-    stage_beg[3] = n;
+    stage_beg[4] = n;
 }
 __device__ __forceinline__ void set_stage(Issuer *s, const int *stage_beg, int st)
 {
@@ -307,8 +316,16 @@ __device__ __noinline__ void prefetch(Issuer *s, const uint32_t *chunks, const i
         ++nloaded; --room;
         if (++lbuf == NBUF) lbuf = 0;
         if (++cur == end) {
-            if (stage == 2 && tiles_left > 0) { --tiles_left; stage = 0; cur = stage_beg[0]; end = stage_beg[1]; }
-            else { stage = (stage == 2) ? -2 : -1; break; }
+            bool next_tile = false;
+            if (stage == 2) {               // the tile's own work is streamed: a tail now (same rule as the kernel's), else the next tile
+                ++s->tiles_done;
+                if (s->tiles_done % s->tail_every == 0 || tiles_left == 0) { stage = 3; cur = stage_beg[3]; end = stage_beg[4]; }
+                else next_tile = true;
+            } else if (stage == 3) {
+                if (tiles_left > 0) next_tile = true;
+                else { stage = -2; break; }
+            } else { stage = -1; break; }   // a GRU step: the halting vote decides what comes next
+            if (next_tile) { --tiles_left; stage = 0; cur = stage_beg[0]; end = stage_beg[1]; }
         }
     }
     s->nloaded = nloaded; s->lbuf = lbuf; s->pf_cur = cur; s->pf_end = end; s->pf_stage = stage; s->tiles_left = tiles_left;
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(evb + NEV);
     __shared__ Issuer s_iss;
     __shared__ uint32_t s_chunks[MAX_CHUNKS];
-    __shared__ int s_stage_beg[4];
+    __shared__ int s_stage_beg[5];
 
     const NetParams &net = args.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -420,6 +437,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         s_iss.nused = s_iss.ubuf = s_iss.upar = 0;
         s_iss.nloaded = s_iss.nfree = s_iss.lbuf = 0;
         s_iss.pf_cur = s_iss.pf_end = 0; s_iss.tiles_left = 0;
+        s_iss.tiles_done = 0; s_iss.tail_every = max(1, 128 / S);
         s_iss.pf_stage = -2;
         if ((int)blockIdx.x < ntiles) {
             s_iss.tiles_left = (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x;
@@ -472,7 +490,8 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     // clock64 stamps of three threads of CTA 0 (issuer warp, producer warp, last warp) over one steady-state tile
     int tl_n = 0;
     const int tl_slot = tid == 0 ? 0 : (tid == 32 ? 1 : (tid == 255 ? 2 : -1));
-#define MARK() do { if (args.dbg && tl_slot >= 0 && blockIdx.x == 0 && tile == (int)(2 * gridDim.x) && tl_n < 500) { \
+    const int tl_tile = (int)args.dbg_tile * (int)gridDim.x;     // the CTA's dbg_tile-th tile (AEM_H16_TL_TILE, default 2)
+#define MARK() do { if (args.dbg && tl_slot >= 0 && blockIdx.x == 0 && tile == tl_tile && tl_n < 500) { \
         args.dbg[tl_slot * 512 + tl_n++] = (clock64() << 12) | (long long)__LINE__; } } while (0)
 #elif defined(AEM_H16_MARKS)
 #define MARK() do { if (args.dbg && (tid == 0 || tid == 32)) { ((volatile long long *)args.dbg)[2 * blockIdx.x + (tid == 32)] = __LINE__ + 10000ll * tile; __threadfence_system(); } } while (0)
@@ -480,6 +499,9 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #define MARK() do { } while (0)
 #endif
 
+    const int tail_every = max(1, 128 / S);
+    float *tail = args.tail + (size_t)blockIdx.x * 128 * TAIL_ROW;
+    int staged = 0, ltile = 0;
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int s0 = tile * S;
@@ -711,6 +733,8 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         }
 
         // ---------------- phase 2: 3 x post-norm encoder layer ----------------
+        bool tail_ran = false;
+        int tail_gs = -1, tail_rows = 0;
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
             MARK(); GROUP_BARRIER();
@@ -727,7 +751,6 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             PRODUCE(e_in); MARK();
             // exact saving: the last layer needs k / v of every token but q, out_proj, FFN and LayerNorm of
             // token 0 only: warps without a token-0 row skip those epilogues (their MMA rows compute garbage nobody reads)
-            const bool live = l < 2 || q4 * 32 < nsamp;
             float2 o[13];
             {
                 // q stays in registers (28 slots, the last 3 zero) scaled by log2(e) / sqrt(head_dim = 25); k and v of this
@@ -756,7 +779,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 float2 oo[14];
 #pragma unroll
                 for (int j = 0; j < 14; ++j) oo[j] = bc2(0.0f);
-                if (samp >= 0 && live) {
+                if (samp >= 0 && (l < 2 || tok == 0)) {        // last layer: the query of token 0 only
                     // one pass over the T keys of the sample with a running maximum (streaming softmax, log2 domain);
                     // key 0 is the sample's token-0 row, keys 1.. are its block of human rows
                     const float *kb = kv + samp * KV_PITCH + 28 * half;
@@ -811,6 +834,59 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 for (int c = 0; c < 13; ++c) o[c] = oo[c];
                 o[12].y = 0.0f;
             }
+            int nlive = 128;                                // rows that are real in the rest of this layer
+            if (l == 2) {
+                // ---- stage the token-0 rows; every tail_every-th tile (and the CTA's last one) the tail runs on all staged rows
+                if (samp >= 0 && tok == 0) {
+                    float *dst = tail + (size_t)(staged + samp) * TAIL_ROW + half * TAIL_HALF;
+#pragma unroll
+                    for (int j = 0; j < 13; ++j) {
+                        *reinterpret_cast<float2 *>(dst + 2 * j) = o[j];
+                        *reinterpret_cast<float2 *>(dst + 26 + 2 * j) = xres[j];
+                    }
+                    dst[52] = selfs[0]; dst[53] = selfs[1]; dst[54] = selfs[2];
+                    if (half == 0) {
+                        dst[55] = __int_as_float(s0 + samp);
+                        if (args.steps) args.steps[s0 + samp] = (uint8_t)cnt;
+                    }
+                }
+                staged += nsamp;
+                ++ltile;
+                tail_ran = (ltile % tail_every == 0) || (tile + (int)gridDim.x >= ntiles);
+                if (!tail_ran) break;
+                __syncthreads();                            // the staged rows of this tile are visible; k / v are consumed
+                nlive = staged;
+                staged = 0;
+                {
+                    // coalesced copy of the staged rows into the (now free) k / v buffer, then every thread takes its row:
+                    // per-thread row loads straight from global memory serialised on their L2 round trips (~18 k cycles per tail)
+                    const float4 *g4 = reinterpret_cast<const float4 *>(tail);
+                    float4 *s4 = reinterpret_cast<float4 *>(kv);
+                    const int n4 = nlive * (TAIL_ROW / 4);
+                    float4 t[14];
+#pragma unroll
+                    for (int i = 0; i < 14; ++i) {
+                        const int e = tid + NT * i;
+                        t[i] = e < n4 ? __ldcg(g4 + e) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 14; ++i) {
+                        const int e = tid + NT * i;
+                        if (e < 128 * (TAIL_ROW / 4)) s4[(e / (TAIL_ROW / 4)) * (KV_PITCH / 4) + e % (TAIL_ROW / 4)] = t[i];
+                    }
+                    __syncthreads();
+                    const float *src = kv + row * KV_PITCH + half * TAIL_HALF;
+#pragma unroll
+                    for (int j = 0; j < 13; ++j) {
+                        o[j] = *reinterpret_cast<const float2 *>(src + 2 * j);
+                        xres[j] = *reinterpret_cast<const float2 *>(src + 26 + 2 * j);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) selfs[i] = src[52 + i];
+                    tail_gs = row < nlive ? __float_as_int(kv[row * KV_PITCH + 55]) : -1;
+                }
+            }
+            const bool live = q4 * 32 < nlive;
             if (live) st16_split<X1>(tl + AATT + 16 * half, o, 0u, 0u, one_hi, 0u, 0u, 0u);
             // ---- out_proj + residual + LayerNorm1
             MARK(); GROUP_BARRIER();
@@ -903,6 +979,12 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 }
                 st16_split<X1>(tl + AE + 16 * half, a, h13, 0u, one_hi, l13, 0u, 0u);
             }
+            if (l == 2) tail_rows = nlive;
+        }
+        if (!tail_ran) {                   // this tile's token-0 rows wait in the scratch for a later tail
+            MARK();
+            __syncthreads();
+            continue;
         }
 
         // ---------------- phase 3: action_mlp ----------------
@@ -917,7 +999,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         __syncwarp();
         MARK(); WAIT_EVENT(e_a0); MARK();
         PRODUCE(e_a0); MARK();
-        const bool live_a = q4 * 32 < nsamp;      // only token-0 rows feed the value head
+        const bool live_a = q4 * 32 < tail_rows;  // the staged token-0 rows
         if (live_a) relu_inplace<64, X1>(tl + DA0 + 64 * half);
         MARK(); GROUP_BARRIER();
         const int e_a2 = nev++;
@@ -943,12 +1025,11 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             }
             sx[half * 128 + row] = pd.x + pd.y;
             pair_sync(q4);
-            if (half == 0 && samp >= 0 && tok == 0) {
+            if (half == 0 && tail_gs >= 0) {
                 const float val = sx[row] + sx[128 + row] + PB[PB_A4B];
-                const int gs = s0 + samp;
+                const int gs = tail_gs;
                 if (args.net_values) args.net_values[gs] = val;
                 if (args.values) args.values[gs] = __dadd_rn(args.rewards[gs], __dmul_rn(args.gamma_bar, (double)val));
-                if (args.steps) args.steps[gs] = (uint8_t)cnt;
             }
         }
         MARK();
@@ -994,7 +1075,17 @@ cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStrea
     if (ntiles <= 0) return cudaSuccess;
     const int maxgrid = 2 * h->num_sms;        // two CTAs (two tiles in flight) per SM
     const int grid = ntiles < maxgrid ? ntiles : maxgrid;
+    const size_t tail_floats = (size_t)maxgrid * 128 * h16::TAIL_ROW;      // staged token-0 rows, L2-resident (17 MB)
+    if (h->tail_floats < tail_floats) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return e;
+        cudaFree(h->tail_d);
+        h->tail_d = nullptr; h->tail_floats = 0;
+        if ((e = cudaMalloc(&h->tail_d, tail_floats * sizeof(float))) != cudaSuccess) return e;
+        h->tail_floats = tail_floats;
+    }
     LookaheadArgs b = a;
+    b.tail = h->tail_d;
     static int stagger = -1;
     if (stagger < 0) {
         const char *e = getenv("AEM_H16_STAGGER_NS");
@@ -1007,6 +1098,7 @@ cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStrea
         cudaHostAlloc((void **)&host, 3 * 512 * sizeof(long long), cudaHostAllocMapped);
         for (int i = 0; i < 3 * 512; ++i) host[i] = 0;
         b.dbg = host;
+        b.dbg_tile = getenv("AEM_H16_TL_TILE") ? atoi(getenv("AEM_H16_TL_TILE")) : 2;
         kern<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
         cudaError_t e = cudaStreamSynchronize(st);
         if (FILE *f = fopen(path, "w")) {
