@@ -48,6 +48,7 @@ constexpr int NT = 256;
 constexpr int NBUF = 4;                 // a two-layer issue group (in_proj heads, linear1 chunks) holds 4 chunks at once
 constexpr int WBUF_BYTES = 12288;       // one N = 96, K = 64 image; 16 KB images (N*K = 8192 fp16) stream as two 8 KB k-halves
 constexpr int KV_PITCH = 116;           // [k head 0 (28) | k head 1 (28) | v head 0 (28) | v head 1 (28)] + 4: float4 access, conflict-free
+static_assert((NBUF & (NBUF - 1)) == 0, "ring slots: power of two");
 constexpr int NEV = 4;
 constexpr int PBLK_MAX = H16_PBLK_FLOATS;
 // Token-0 compaction (SURVEY 8d "exact algorithmic savings"): after the last encoder layer's attention only token 0 of a
@@ -330,6 +331,35 @@ __device__ __noinline__ void prefetch(Issuer *s, const uint32_t *chunks, const i
     }
     s->nloaded = nloaded; s->lbuf = lbuf; s->pf_cur = cur; s->pf_end = end; s->pf_stage = stage; s->tiles_left = tiles_left;
 }
+// Fast path of the producer (inline, straight-line): the `room` chunks to request do not end a stage, so no cursor logic is
+// needed -- one table word, one expect_tx and one bulk copy per chunk.  (The general walker above costs ~200 dependent
+// instructions per call on ONE thread, ~850 cycles that its warp then arrives late at the next group barrier:
+// profiles/r02_lookahead_h16_ncu.md.)
+__device__ __forceinline__ void prefetch_fast(Issuer *s, const uint32_t *chunks, const int *stage_beg, uint8_t *wbuf,
+                                              uint64_t *wfull, const __half *img, uint32_t ring_s, uint32_t wfull_s)
+{
+    const int stage = s->pf_stage, nloaded = s->nloaded, cur = s->pf_cur, lbuf = s->lbuf;
+    const int room = NBUF - (nloaded - s->nfree);
+    if (stage < 0 || room <= 0) return;
+    if (cur + room >= s->pf_end) { prefetch(s, chunks, stage_beg, wbuf, wfull, img); return; }
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i) {
+        if (i < room) {
+            const uint32_t c = chunks[cur + i];
+            const uint32_t bytes = (c >> 20) << 4;
+            const uint32_t slot = (uint32_t)(lbuf + i) & (uint32_t)(NBUF - 1);
+            const uint32_t bar = wfull_s + 8u * slot;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             ring_s + slot * (uint32_t)WBUF_BYTES),
+                         "l"(img + (size_t)(c & 0xFFFFFu) * 8), "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+    }
+    s->nloaded = nloaded + room;
+    s->lbuf = (lbuf + room) & (NBUF - 1);
+    s->pf_cur = cur + room;
+}
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -480,7 +510,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     do {                                                                              \
         if (tid == 32) {                                                              \
             s_iss.nfree = s_iss.used_ev[(e) % NEV];                                   \
-            prefetch(&s_iss, s_chunks, s_stage_beg, wbuf, wfull, net.h16_img);        \
+            prefetch_fast(&s_iss, s_chunks, s_stage_beg, wbuf, wfull, net.h16_img, ring, smem_u32(wfull)); \
         }                                                                             \
         __syncwarp();                                                                 \
     } while (0)
