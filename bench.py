@@ -125,16 +125,19 @@ def cpu_baseline(robot, humans, gt, W, actions, gbar, budget_s=12.0):
     return out
 
 
-def reference_python_baseline(cores, n, seconds=12.0):
+def reference_python_baseline(cores, n, seconds=10.0):
     """The AS-SHIPPED Python reference (oracle/_ref: an uncommitted copy made by oracle/make_ref.py, run under
-    oracle/ref_shim.py) on the same host cores, one single-thread process per core -- context next to the C port."""
+    oracle/ref_shim.py) on host cores of the same box, one single-thread process per core -- context next to the C port.
+    Four processes only (`cores` in the result says so): 16 simultaneous cold starts (torch import + numba JIT of the
+    reference's gridmap kernels) take minutes on a fresh box, and the per-core rate is what the comparison needs."""
+    cores = min(int(cores), 4)
     ref = os.path.join(ROOT, "oracle", "_ref")
     if not os.path.isdir(os.path.join(ref, "crowd_nav")):
         return {"unavailable": "oracle/_ref is absent (python oracle/make_ref.py in the build container)"}
     try:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--procs", str(cores), "--seconds",
                             str(seconds), "--humans", str(n)], env=dict(os.environ, AEM_REFERENCE=ref), capture_output=True,
-                           text=True, timeout=seconds * 6 + 120)
+                           text=True, timeout=seconds * 6 + 240)
         return json.loads(r.stdout.strip().split("\n")[-1])
     except Exception as e:                                     # context only: never fail the bench line
         return {"unavailable": "oracle/ref_bench.py failed: %r" % (e,)}
