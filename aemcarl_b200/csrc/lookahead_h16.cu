@@ -254,19 +254,17 @@ __device__ __forceinline__ void rotate13(const float *s, float *o)
 // ------------------------------------------------------------------------------------------------
 // weight ring: consumer = warp 0 (issues the MMAs), producer = lane 0 of warp 1 (requests the bulk copies)
 // ------------------------------------------------------------------------------------------------
-// Neither role works between a group barrier and the group's first MMA: the ring read position travels in registers
-// (IssReg) while a group is issued and at every commit lane 0 publishes how many chunks the committed MMAs cover; the
-// producer, after waiting on an event like every other thread, releases exactly those slots and requests the next chunks
-// from a flat table of {offset, bytes} built once per CTA.
+// Neither role works between a group barrier and the group's first MMA.  The ring read position is a register every
+// thread carries (`wn` = chunks consumed so far; each issue_t call advances it by a compile-time count, control flow is
+// CTA-uniform): the issuer derives slot and mbarrier parity from it, and the producer warp, after waiting on an event like
+// every other thread, releases exactly the slots consumed up to that event's commit and requests the next chunks from a
+// flat table of {offset, bytes} built once per CTA -- no shared-memory hand-off and no fence on the issue path.
 struct Issuer {
-    int used_ev[NEV];               // consumer -> producer: chunks consumed when event e was committed, at [e % NEV]
-    int nused, ubuf, upar;          // consumer: running chunk count, ring slot and mbarrier parity of the next chunk
     int nloaded, nfree, lbuf;       // producer: chunks requested / released, ring slot of the next request
     int pf_cur, pf_end, pf_stage;   // producer: cursor into the chunk table; stage -1 = waiting for the ACT decision, -2 = done
     int tiles_left;
     int tiles_done, tail_every;     // the tail stage follows every tail_every-th tile of the CTA (and its last one)
 };
-struct IssReg { uint32_t buf, par, n; };
 constexpr int MAX_CHUNKS = 128;
 // stage 0: GRU step 1, 1: GRU steps 2.., 2: encoder layers 0, 1 and the in_proj of layer 2, 3: the tail (out_proj, FFN of layer 2
 // and the action MLP on the staged token-0 rows)
@@ -331,34 +329,42 @@ __device__ __noinline__ void prefetch(Issuer *s, const uint32_t *chunks, const i
     }
     s->nloaded = nloaded; s->lbuf = lbuf; s->pf_cur = cur; s->pf_end = end; s->pf_stage = stage; s->tiles_left = tiles_left;
 }
-// Fast path of the producer (inline, straight-line): the `room` chunks to request do not end a stage, so no cursor logic is
-// needed -- one table word, one expect_tx and one bulk copy per chunk.  (The general walker above costs ~200 dependent
-// instructions per call on ONE thread, ~850 cycles that its warp then arrives late at the next group barrier:
-// profiles/r02_lookahead_h16_ncu.md.)
-__device__ __forceinline__ void prefetch_fast(Issuer *s, const uint32_t *chunks, const int *stage_beg, uint8_t *wbuf,
-                                              uint64_t *wfull, const __half *img, uint32_t ring_s, uint32_t wfull_s)
+// Fast path of the producer, executed by the whole producer warp: the `room` chunks to request do not end a stage, so no
+// cursor logic is needed, and lane i requests chunk i (its table word, expect_tx and bulk copy computed in parallel with
+// the other lanes').  `nf` = chunks the consumer has finished with.  (Round-2 timelines: the same work as dependent scalar
+// code on ONE thread took ~770 cycles, by which its warp arrived late at every group barrier; the general walker above
+// costs ~200 dependent instructions per call and remains for the stage ends.)
+__device__ __forceinline__ void produce_fast(Issuer *s, int nf, int lane, const uint32_t *chunks, const int *stage_beg,
+                                             uint8_t *wbuf, uint64_t *wfull, const __half *img, uint32_t ring_s, uint32_t wfull_s)
 {
-    const int stage = s->pf_stage, nloaded = s->nloaded, cur = s->pf_cur, lbuf = s->lbuf;
-    const int room = NBUF - (nloaded - s->nfree);
-    if (stage < 0 || room <= 0) return;
-    if (cur + room >= s->pf_end) { prefetch(s, chunks, stage_beg, wbuf, wfull, img); return; }
-#pragma unroll
-    for (int i = 0; i < NBUF; ++i) {
-        if (i < room) {
-            const uint32_t c = chunks[cur + i];
-            const uint32_t bytes = (c >> 20) << 4;
-            const uint32_t slot = (uint32_t)(lbuf + i) & (uint32_t)(NBUF - 1);
-            const uint32_t bar = wfull_s + 8u * slot;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             ring_s + slot * (uint32_t)WBUF_BYTES),
-                         "l"(img + (size_t)(c & 0xFFFFFu) * 8), "r"(bytes), "r"(bar)
-                         : "memory");
-        }
+    const int stage = s->pf_stage, nloaded = s->nloaded, cur = s->pf_cur, end = s->pf_end;
+    __syncwarp();                                   // every lane has read the state before lane 0 rewrites it
+    const int room = NBUF - (nloaded - nf);
+    if (stage < 0 || room <= 0) {
+        if (lane == 0) s->nfree = nf;
+        return;
     }
-    s->nloaded = nloaded + room;
-    s->lbuf = (lbuf + room) & (NBUF - 1);
-    s->pf_cur = cur + room;
+    if (cur + room >= end) {
+        if (lane == 0) { s->nfree = nf; prefetch(s, chunks, stage_beg, wbuf, wfull, img); }
+        return;
+    }
+    if (lane < room) {
+        const uint32_t c = chunks[cur + lane];
+        const uint32_t bytes = (c >> 20) << 4;
+        const uint32_t slot = (uint32_t)(nloaded + lane) & (uint32_t)(NBUF - 1);
+        const uint32_t bar = wfull_s + 8u * slot;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ring_s + slot * (uint32_t)WBUF_BYTES),
+                     "l"(img + (size_t)(c & 0xFFFFFu) * 8), "r"(bytes), "r"(bar)
+                     : "memory");
+    }
+    if (lane == 0) {
+        s->nfree = nf;
+        s->nloaded = nloaded + room;
+        s->lbuf = (nloaded + room) & (NBUF - 1);
+        s->pf_cur = cur + room;
+    }
 }
 __device__ __forceinline__ bool elect_one()
 {
@@ -377,27 +383,41 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         : "memory");
 }
 
+#ifdef AEM_H16_TIMELINE
+#define TL_ARG , long long &tl_first
+#define TL_PASS , tl_first
+#else
+#define TL_ARG
+#define TL_PASS
+#endif
 // One layer: KS k-steps (16 K values = 8 operand columns each) per pass.  Operand column of k-step ks:
 //   a_base + HSTRIDE * (ks / KSH) + KSTR * (ks % KSH), lo part LO columns further.  SPECIAL: step-1 images use the
 //   k-steps {1, 3} of A1 (the x slots).
 template <int N, int KS, int KSH, int HSTRIDE, int KSTR, int LO, bool SPECIAL, int SPLIT, bool X1>
-__device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t ring, uint32_t tm, uint32_t a_base, uint32_t d,
-                                        bool accumulate)
+__device__ __forceinline__ void issue_t(uint32_t &wn, bool issuer, uint64_t *wfull, uint32_t ring, uint32_t tm, uint32_t a_base,
+                                        uint32_t d, bool accumulate TL_ARG)
 {
     constexpr uint32_t LBO = (uint32_t)N * 16;
     constexpr uint64_t DHI = ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // F16 x F16 -> F32
     constexpr int KSS = KS / SPLIT;                      // k-steps per streamed chunk
     static_assert(KS % SPLIT == 0, "split");
+    // Every thread calls this (uniform control flow) and advances its copy of the ring read position `wn` = chunks consumed
+    // so far (slot = wn % NBUF, mbarrier parity = (wn / NBUF) & 1); only the issuer warp waits for the chunks and issues.
+    constexpr uint32_t NCH = (uint32_t)SPLIT * (X1 ? 1u : 2u);
+    if (issuer) {
     const bool leader = elect_one();
 #pragma unroll
     for (int part = 0; part < (X1 ? 1 : 2); ++part) {    // part 0: W_hi (A_hi and A_lo passes), part 1: W_lo (A_hi pass)
 #pragma unroll
         for (int sub = 0; sub < SPLIT; ++sub) {
-            mbar_wait(&wfull[r.buf], r.par);         // all lanes, uniform
-            const uint32_t base = ((ring + r.buf * (uint32_t)WBUF_BYTES) & 0x3FFFFu) >> 4;
-            if (++r.buf == (uint32_t)NBUF) { r.buf = 0; r.par ^= 1u; }
-            ++r.n;
+            const uint32_t cn = wn + (uint32_t)(part * SPLIT + sub);
+            const uint32_t cbuf = cn & (uint32_t)(NBUF - 1);
+            mbar_wait(&wfull[cbuf], (cn / (uint32_t)NBUF) & 1u);         // all lanes, uniform
+#ifdef AEM_H16_TIMELINE
+            if (tl_first == 0) tl_first = clock64();
+#endif
+            const uint32_t base = ((ring + cbuf * (uint32_t)WBUF_BYTES) & 0x3FFFFu) >> 4;
 #pragma unroll
             for (int kk = 0; kk < KSS; ++kk) {
                 const int ks = sub * KSS + kk;
@@ -415,13 +435,15 @@ __device__ __forceinline__ void issue_t(IssReg &r, uint64_t *wfull, uint32_t rin
             }
         }
     }
+    }
+    wn += NCH;
 }
 // shorthand for the three operand layouts
 // (images larger than one ring slot -- N * K = 8192 -- are streamed as two k-halves: SPLIT = 2)
-#define ISSUE_K64(N, a, d, acc) issue_t<N, 4, 4, 0, 8, 32, false, ((N) * 64 > 6144 ? 2 : 1), X1>(ir, wfull, ring, tm, a, d, acc)
-#define ISSUE_K64S(N, a, d) issue_t<N, 2, 4, 0, 8, 32, true, 1, X1>(ir, wfull, ring, tm, a, d, false)        /* step-1 images   */
-#define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 16, 8, false, 2, X1>(ir, wfull, ring, tm, a, d, false)   /* in-place 2 x 4 x [8|8] */
-#define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 16, 8, false, 1, X1>(ir, wfull, ring, tm, a, d, acc) /* in-place 2 x 3 x [8|8] */
+#define ISSUE_K64(N, a, d, acc) issue_t<N, 4, 4, 0, 8, 32, false, ((N) * 64 > 6144 ? 2 : 1), X1>(wn, warp == 0, wfull, ring, tm, a, d, acc TL_PASS)
+#define ISSUE_K64S(N, a, d) issue_t<N, 2, 4, 0, 8, 32, true, 1, X1>(wn, warp == 0, wfull, ring, tm, a, d, false TL_PASS)        /* step-1 images   */
+#define ISSUE_K128(N, a, d) issue_t<N, 8, 4, 64, 16, 8, false, 2, X1>(wn, warp == 0, wfull, ring, tm, a, d, false TL_PASS)   /* in-place 2 x 4 x [8|8] */
+#define ISSUE_K96(N, a, d, acc) issue_t<N, 6, 3, 48, 16, 8, false, 1, X1>(wn, warp == 0, wfull, ring, tm, a, d, acc TL_PASS) /* in-place 2 x 3 x [8|8] */
 
 // X1: the single-pass mode (A_hi W_hi only; opt-in, own tolerance: tests/test_gpu_parity.py)
 template <bool X1>
@@ -463,8 +485,6 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     const uint32_t ring = smem_u32(wbuf);
     if (tid == 32) {
         build_chunk_table(net.h16_layers_d, s_chunks, s_stage_beg, X1 ? 1 : 2);
-        for (int i = 0; i < NEV; ++i) s_iss.used_ev[i] = 0;
-        s_iss.nused = s_iss.ubuf = s_iss.upar = 0;
         s_iss.nloaded = s_iss.nfree = s_iss.lbuf = 0;
         s_iss.pf_cur = s_iss.pf_end = 0; s_iss.tiles_left = 0;
         s_iss.tiles_done = 0; s_iss.tail_every = max(1, 128 / S);
@@ -477,6 +497,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
     }
     __syncthreads();
     int nev = 0;
+    uint32_t wn = 0;            // weight chunks consumed so far: the ring read position, carried by every thread (issue_t)
     // the two CTAs of an SM run identical work: offset the second one so that its epilogues fall into the first one's
     // MMA / commit waits instead of colliding with its epilogues
     if ((int)blockIdx.x >= (int)gridDim.x / 2 && args.stagger_ns > 0) __nanosleep((unsigned)args.stagger_ns);
@@ -495,26 +516,30 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         tc_fence_after();                                               \
     } while (0)
 #define WAIT_EVENT(e) WAIT_EVENT_POLL(e)
-#define ISSUE_BEGIN() \
-    IssReg ir;        \
-    ir.buf = (uint32_t)s_iss.ubuf; ir.par = (uint32_t)s_iss.upar; ir.n = (uint32_t)s_iss.nused
-#define ISSUE_COMMIT(e)                                                         \
-    do {                                                                        \
-        if (lane == 0) { s_iss.used_ev[(e) % NEV] = (int)ir.n; __threadfence_block(); COMMIT(e); } /* publish BEFORE the commit */ \
-        __syncwarp();                                                           \
+#ifdef AEM_H16_TIMELINE
+    long long tl_first = 0;     // clock64 when the group's first weight chunk was there
+#define ISSUE_BEGIN() tl_first = 0; MARK()
+#define ISSUE_END() do { if (args.dbg && tl_slot == 0 && blockIdx.x == 0 && tile == tl_tile && tl_n < 500) { \
+        args.dbg[tl_n++] = (tl_first << 12) | 1; args.dbg[tl_n++] = (clock64() << 12) | 2; } } while (0)
+#else
+#define ISSUE_BEGIN() do { } while (0)
+#define ISSUE_END() do { } while (0)
+#endif
+    // the MMAs are issued by the elected lane of warp 0 (issue_t); the same thread commits them to the group's event
+#define ISSUE_COMMIT(e)                                       \
+    do {                                                      \
+        if (warp == 0) { if (elect_one()) COMMIT(e); __syncwarp(); } \
     } while (0)
-#define ISSUE_END() \
-    do { if (lane == 0) { s_iss.nused = (int)ir.n; s_iss.ubuf = (int)ir.buf; s_iss.upar = (int)ir.par; } } while (0)
-// after an event has been waited on: the producer releases the ring slots its MMAs read and requests the next chunks
-#define PRODUCE(e)                                                                    \
+// after an event has been waited on: the producer warp releases the ring slots the event's MMAs read (`nf` = chunks
+// consumed when the event was committed; every thread carries that count in `wn`) and requests the next chunks
+#define PRODUCE_N(nf)                                                                 \
     do {                                                                              \
-        if (tid == 32) {                                                              \
-            s_iss.nfree = s_iss.used_ev[(e) % NEV];                                   \
-            prefetch_fast(&s_iss, s_chunks, s_stage_beg, wbuf, wfull, net.h16_img, ring, smem_u32(wfull)); \
+        if (warp == 1) {                                                              \
+            produce_fast(&s_iss, (int)(nf), lane, s_chunks, s_stage_beg, wbuf, wfull, net.h16_img, ring, smem_u32(wfull)); \
+            __syncwarp();                                                             \
         }                                                                             \
-        __syncwarp();                                                                 \
     } while (0)
-
+#define PRODUCE(e) PRODUCE_N(wn)
     const float *PB = pblk;
 #if defined(AEM_H16_TIMELINE)
     // clock64 stamps of three threads of CTA 0 (issuer warp, producer warp, last warp) over one steady-state tile
@@ -632,26 +657,20 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                 if (gate == 1 && !kfull) break;
                 if (gate) { MARK(); GROUP_BARRIER(); }
                 const int e_g1 = nev++;
-                if (warp == 0) {
-                    ISSUE_BEGIN();
-                    if (kfull) ISSUE_K64(128, A1, D1, false);
-                    else ISSUE_K64S(128, A1, D1);
-                    ISSUE_COMMIT(e_g1);
-                    ISSUE_END();
-                }
-                __syncwarp();
+                ISSUE_BEGIN();
+                if (kfull) ISSUE_K64(128, A1, D1, false);
+                else ISSUE_K64S(128, A1, D1);
+                ISSUE_COMMIT(e_g1);
+                ISSUE_END();
                 MARK(); WAIT_EVENT(e_g1); MARK();
                 PRODUCE(e_g1); MARK();
                 relu_inplace<64, X1>(tl + D1 + 64 * half);
                 MARK(); GROUP_BARRIER();
                 const int e_g2 = nev++;
-                if (warp == 0) {
-                    ISSUE_BEGIN();
-                    ISSUE_K128(64, D1, D2);
-                    ISSUE_COMMIT(e_g2);
-                    ISSUE_END();
-                }
-                __syncwarp();
+                ISSUE_BEGIN();
+                ISSUE_K128(64, D1, D2);
+                ISSUE_COMMIT(e_g2);
+                ISSUE_END();
                 MARK(); WAIT_EVENT(e_g2); MARK();
                 PRODUCE(e_g2); MARK();
                 float2 v[13];
@@ -670,14 +689,11 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             // ---- q, h = (1 - z) h + z q
             MARK(); GROUP_BARRIER();
             const int e_q = nev++;
-            if (warp == 0) {
-                ISSUE_BEGIN();
-                if (kfull) ISSUE_K64(64, A3, D2, false);
-                else ISSUE_K64S(64, A1, D2);
-                ISSUE_COMMIT(e_q);
-                ISSUE_END();
-            }
-            __syncwarp();
+            ISSUE_BEGIN();
+            if (kfull) ISSUE_K64(64, A3, D2, false);
+            else ISSUE_K64S(64, A1, D2);
+            ISSUE_COMMIT(e_q);
+            ISSUE_END();
             MARK(); WAIT_EVENT(e_q); MARK();
             PRODUCE(e_q); MARK();
             {
@@ -769,14 +785,11 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         for (int l = 0; l < 3; ++l) {
             MARK(); GROUP_BARRIER();
             const int e_in = nev++;
-            if (warp == 0) {
-                ISSUE_BEGIN();
+            ISSUE_BEGIN();
 #pragma unroll 1
-                for (int hd = 0; hd < 2; ++hd) ISSUE_K64(96, AE, DIN + 96 * hd, false);
-                ISSUE_COMMIT(e_in);
-                ISSUE_END();
-            }
-            __syncwarp();
+            for (int hd = 0; hd < 2; ++hd) ISSUE_K64(96, AE, DIN + 96 * hd, false);
+            ISSUE_COMMIT(e_in);
+            ISSUE_END();
             MARK(); WAIT_EVENT(e_in); MARK();
             PRODUCE(e_in); MARK();
             // exact saving: the last layer needs k / v of every token but q, out_proj, FFN and LayerNorm of
@@ -921,13 +934,10 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
             // ---- out_proj + residual + LayerNorm1
             MARK(); GROUP_BARRIER();
             const int e_out = nev++;
-            if (warp == 0) {
-                ISSUE_BEGIN();
-                ISSUE_K64(64, AATT, DOUT, false);
-                ISSUE_COMMIT(e_out);
-                ISSUE_END();
-            }
-            __syncwarp();
+            ISSUE_BEGIN();
+            ISSUE_K64(64, AATT, DOUT, false);
+            ISSUE_COMMIT(e_out);
+            ISSUE_END();
             MARK(); WAIT_EVENT(e_out); MARK();
             PRODUCE(e_out); MARK();
             // pass 0: out_proj + residual + LayerNorm1; pass 1: FFN + residual + LayerNorm2 (one copy of the LayerNorm code)
@@ -939,29 +949,25 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
                     const int e_f1 = nev;          // chunk c completes on event e_f1 + c
                     const int e_f2 = nev + 2;
                     nev += 3;
-                    if (warp == 0) {
-                        ISSUE_BEGIN();
-                        ISSUE_K64(96, AE, DF1A, false);
-                        ISSUE_COMMIT(e_f1);
-                        ISSUE_K64(96, AE, DF1B, false);
-                        ISSUE_COMMIT(e_f1 + 1);
-                        ISSUE_END();
-                    }
-                    __syncwarp();
+                    ISSUE_BEGIN();
+                    ISSUE_K64(96, AE, DF1A, false);
+                    ISSUE_COMMIT(e_f1);
+                    const uint32_t wn_f1a = wn;     // chunks covered by event e_f1 (the producer may release exactly those)
+                    ISSUE_K64(96, AE, DF1B, false);
+                    ISSUE_COMMIT(e_f1 + 1);
+                    const uint32_t wn_f1b = wn;
+                    ISSUE_END();
 #pragma unroll 1
                     for (int c = 0; c < 2; ++c) {
                         MARK(); WAIT_EVENT(e_f1 + c); MARK();
-                        PRODUCE(e_f1 + c); MARK();
+                        PRODUCE_N(c ? wn_f1b : wn_f1a); MARK();
                         if (live) relu_inplace<48, X1>(tl + (c ? DF1B : DF1A) + 48 * half);
                         MARK(); GROUP_BARRIER();
-                        if (warp == 0) {
-                            if (c == 0) WAIT_EVENT_POLL(e_f1 + 1);   // F1B reads AE, which D_F2 aliases: complete before linear2 starts
-                            ISSUE_BEGIN();
-                            ISSUE_K96(64, c ? DF1B : DF1A, DF2, c != 0);
-                            if (c) ISSUE_COMMIT(e_f2);
-                            ISSUE_END();
-                        }
-                        __syncwarp();
+                        if (warp == 0 && c == 0) WAIT_EVENT_POLL(e_f1 + 1);   // F1B reads AE, which D_F2 aliases: complete before linear2 starts
+                        ISSUE_BEGIN();
+                        ISSUE_K96(64, c ? DF1B : DF1A, DF2, c != 0);
+                        if (c) ISSUE_COMMIT(e_f2);
+                        ISSUE_END();
                     }
                     MARK(); WAIT_EVENT(e_f2); MARK();
                     PRODUCE(e_f2); MARK();
@@ -1020,26 +1026,20 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
         // ---------------- phase 3: action_mlp ----------------
         MARK(); GROUP_BARRIER();
         const int e_a0 = nev++;
-        if (warp == 0) {
-            ISSUE_BEGIN();
-            ISSUE_K64(128, AE, DA0, false);
-            ISSUE_COMMIT(e_a0);
-            ISSUE_END();
-        }
-        __syncwarp();
+        ISSUE_BEGIN();
+        ISSUE_K64(128, AE, DA0, false);
+        ISSUE_COMMIT(e_a0);
+        ISSUE_END();
         MARK(); WAIT_EVENT(e_a0); MARK();
         PRODUCE(e_a0); MARK();
         const bool live_a = q4 * 32 < tail_rows;  // the staged token-0 rows
         if (live_a) relu_inplace<64, X1>(tl + DA0 + 64 * half);
         MARK(); GROUP_BARRIER();
         const int e_a2 = nev++;
-        if (warp == 0) {
-            ISSUE_BEGIN();
-            ISSUE_K128(64, DA0, DA2);
-            ISSUE_COMMIT(e_a2);
-            ISSUE_END();
-        }
-        __syncwarp();
+        ISSUE_BEGIN();
+        ISSUE_K128(64, DA0, DA2);
+        ISSUE_COMMIT(e_a2);
+        ISSUE_END();
         MARK(); WAIT_EVENT(e_a2); MARK();
         PRODUCE(e_a2); MARK();
         if (live_a) {
@@ -1084,6 +1084,7 @@ __global__ void __launch_bounds__(NT, 2) lookahead_h16_kernel(const LookaheadArg
 #undef ISSUE_BEGIN
 #undef ISSUE_COMMIT
 #undef ISSUE_END
+#undef PRODUCE_N
 #undef PRODUCE
 }
 
@@ -1129,7 +1130,14 @@ cudaError_t launch_lookahead_h16(aem_handle h, const LookaheadArgs &a, cudaStrea
         for (int i = 0; i < 3 * 512; ++i) host[i] = 0;
         b.dbg = host;
         b.dbg_tile = getenv("AEM_H16_TL_TILE") ? atoi(getenv("AEM_H16_TL_TILE")) : 2;
-        kern<<<grid, h16::NT, h16::SMEM_BYTES, st>>>(b);
+        size_t smem = h16::SMEM_BYTES;
+        int tl_grid = grid;
+        if (getenv("AEM_H16_SOLO")) {           // one CTA per SM: the chain of a tile without a neighbour on the tensor pipe
+            smem = 200 * 1024;
+            tl_grid = ntiles < h->num_sms ? ntiles : h->num_sms;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        kern<<<tl_grid, h16::NT, smem, st>>>(b);
         cudaError_t e = cudaStreamSynchronize(st);
         if (FILE *f = fopen(path, "w")) {
             for (int s = 0; s < 3; ++s)
