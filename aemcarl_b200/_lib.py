@@ -64,6 +64,8 @@ SYMBOLS = {
     "aem_env_lookahead": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 9),
     "aem_lookahead": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, ctypes.c_double] + [_VP] * 5),
     "aem_env_apply": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 13),
+    "aem_env_prepare": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 9),
+    "aem_env_finish": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 15 + [ctypes.c_int, _VP, ctypes.c_int, _VP, _VP]),
     "aem_env_reset_done": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int] + [_VP] * 7 + [ctypes.c_int, _VP, ctypes.c_int, _VP, _VP]),
     "aem_value_forward": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),
     "aem_gru_act": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),

@@ -159,7 +159,14 @@ cudaError_t launch_orca(int B, int n, const double *humans, const double *robot,
 cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const double *humans,
                                  const double *new_vel, const double *global_time, const double *actions,
                                  int action_env_stride, const double *lut, const aem_env_params &p, double amax, double *rewards,
-                                 int32_t *info, double *dmin, double *humans_next, cudaStream_t st, const int32_t *nact = nullptr);
+                                 int32_t *info, double *dmin, double *humans_next, cudaStream_t st, const int32_t *nact = nullptr,
+                                 double *new_vel_out = nullptr);     // new_vel_out: ORCA runs inside the same launch (env_prepare)
+cudaError_t launch_env_finish(int B, int n, int A, const double *values, double *robot, double *humans, const double *new_vel,
+                              double *global_time, const double *actions, int action_env_stride, const double *rewards,
+                              const int32_t *info, const double *dmin, double time_step, int32_t *best, double *out_reward,
+                              int32_t *out_done, int32_t *out_info, double *out_dmin, int32_t *nact, const double *pool_robot,
+                              const double *pool_humans, int P, int32_t *case_idx, int case_stride,
+                              unsigned long long *outcome_counts, const int32_t *pool_nact, cudaStream_t st);
 cudaError_t launch_env_apply(int B, int n, int A, double *robot, double *humans, const double *new_vel,
                              double *global_time, const double *actions, int action_env_stride,
                              const int32_t *chosen,

@@ -481,7 +481,7 @@ int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const doubl
     if (rc) return rc;
     if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
     if (B == 0) return AEM_OK;
-    if (!robot_d || !humans_next_d || !rewards_d || !values_d || !best_d)
+    if (!robot_d || !humans_next_d || !rewards_d || !values_d)
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
     if ((long long)B * h->A > 0x7fffffffLL) return aem_set_error(AEM_ERR_INVALID, "B * A overflows int32");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
@@ -503,8 +503,8 @@ int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const doubl
     AEM_CUDA_CHECK(h->precision >= 2 ? launch_lookahead_h16(h, a, as_stream(stream), h->precision == 3)
                    : h->precision == 1 ? launch_lookahead_tc(h, a, as_stream(stream))
                                        : launch_lookahead(h, a, as_stream(stream)));
-    AEM_CUDA_CHECK(launch_select(values_d, robot_d, B, h->A, best_d, as_stream(stream)));
-    h->launches += 2 * (B > 0);
+    if (best_d) AEM_CUDA_CHECK(launch_select(values_d, robot_d, B, h->A, best_d, as_stream(stream)));
+    h->launches += (best_d ? 2 : 1) * (B > 0);
     return AEM_OK;
 }
 
@@ -524,6 +524,46 @@ int aem_env_apply(aem_handle h, int B, int n, double *robot_d, double *humans_d,
                                     rewards_d, info_d, dmin_d, h->params.time_step, out_reward_d, out_done_d,
                                     out_info_d, out_dmin_d, as_stream(stream), h->nact_d));
     h->launches += (B > 0);
+    return AEM_OK;
+}
+
+int aem_env_prepare(aem_handle h, int B, int n, const double *robot_d, const double *humans_d, const double *global_time_d,
+                    double *new_vel_d, double *rewards_d, int32_t *info_d, double *dmin_d, double *humans_next_d, void *stream)
+{
+    int rc = check_ready(h, false, true);
+    if (rc) return rc;
+    if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (B == 0) return AEM_OK;
+    if (n - 1 + (h->params.robot_visible ? 1 : 0) > 32) return aem_set_error(AEM_ERR_INVALID, "too many neighbours");
+    if (!robot_d || !humans_d || !new_vel_d || !global_time_d || !rewards_d)
+        return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_env_lookahead(B, n, h->A, robot_d, humans_d, nullptr, global_time_d, h->actions_d, 0, h->lut_d,
+                                        h->params, action_amax(h), rewards_d, info_d, dmin_d, humans_next_d,
+                                        as_stream(stream), h->nact_d, new_vel_d));
+    h->launches += 1;
+    return AEM_OK;
+}
+
+int aem_env_finish(aem_handle h, int B, int n, const double *values_d, double *robot_d, double *humans_d,
+                   const double *new_vel_d, double *global_time_d, const double *rewards_d, const int32_t *info_d,
+                   const double *dmin_d, int32_t *best_d, double *out_reward_d, int32_t *out_done_d, int32_t *out_info_d,
+                   double *out_dmin_d, const double *pool_robot_d, const double *pool_humans_d, int P, int32_t *case_idx_d,
+                   int case_stride, unsigned long long *outcome_counts_d, void *stream)
+{
+    int rc = check_ready(h, false, true);
+    if (rc) return rc;
+    if (B < 0 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
+    if (B == 0) return AEM_OK;
+    if (!values_d || !robot_d || !humans_d || !new_vel_d || !global_time_d || !rewards_d || !info_d)
+        return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    if (pool_robot_d && (!pool_humans_d || !case_idx_d || P < 1)) return aem_set_error(AEM_ERR_INVALID, "bad scenario pool");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_env_finish(B, n, h->A, values_d, robot_d, humans_d, new_vel_d, global_time_d, h->actions_d, 0,
+                                     rewards_d, info_d, dmin_d, h->params.time_step, best_d, out_reward_d, out_done_d,
+                                     out_info_d, out_dmin_d, h->nact_d, pool_robot_d, pool_humans_d, P, case_idx_d,
+                                     case_stride, outcome_counts_d, h->pool_nact_d, as_stream(stream)));
+    h->launches += 1;
     return AEM_OK;
 }
 
@@ -680,16 +720,15 @@ int aem_decide_step_host(aem_handle h, int B, int n, double gamma_bar, double *r
     AEM_CUDA_CHECK(cudaMemcpyAsync(h->s_robot, robot_h, sizeof(double) * B * 9, cudaMemcpyHostToDevice, st));
     AEM_CUDA_CHECK(cudaMemcpyAsync(h->s_humans, humans_h, sizeof(double) * B * n * 8, cudaMemcpyHostToDevice, st));
     AEM_CUDA_CHECK(cudaMemcpyAsync(h->s_time, global_time_h, sizeof(double) * B, cudaMemcpyHostToDevice, st));
-    rc = aem_orca(h, B, n, h->s_humans, h->s_robot, h->s_newvel, st);
+    // three launches: ORCA + env lookahead, the value lookahead, argmax + env step
+    rc = aem_env_prepare(h, B, n, h->s_robot, h->s_humans, h->s_time, h->s_newvel, h->s_rewards, h->s_info, h->s_dmin,
+                         h->s_hnext, st);
     if (rc) return rc;
-    rc = aem_env_lookahead(h, B, n, h->s_robot, h->s_humans, h->s_newvel, h->s_time, h->s_rewards, h->s_info,
-                           h->s_dmin, h->s_hnext, st);
+    rc = aem_lookahead(h, B, n, h->s_robot, h->s_hnext, h->s_rewards, gamma_bar, h->s_values, nullptr, nullptr, nullptr, st);
     if (rc) return rc;
-    rc = aem_lookahead(h, B, n, h->s_robot, h->s_hnext, h->s_rewards, gamma_bar, h->s_values, nullptr, h->s_best,
-                       nullptr, st);
-    if (rc) return rc;
-    rc = aem_env_apply(h, B, n, h->s_robot, h->s_humans, h->s_newvel, h->s_time, h->s_best, h->s_rewards, h->s_info,
-                       h->s_dmin, h->s_oreward, h->s_odone, h->s_oinfo, nullptr, st);
+    rc = aem_env_finish(h, B, n, h->s_values, h->s_robot, h->s_humans, h->s_newvel, h->s_time, h->s_rewards, h->s_info,
+                        h->s_dmin, h->s_best, h->s_oreward, h->s_odone, h->s_oinfo, nullptr, nullptr, nullptr, 0, nullptr, 0,
+                        nullptr, st);
     if (rc) return rc;
     AEM_CUDA_CHECK(cudaMemcpyAsync(robot_h, h->s_robot, sizeof(double) * B * 9, cudaMemcpyDeviceToHost, st));
     AEM_CUDA_CHECK(cudaMemcpyAsync(humans_h, h->s_humans, sizeof(double) * B * n * 8, cudaMemcpyDeviceToHost, st));

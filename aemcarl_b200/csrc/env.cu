@@ -14,7 +14,7 @@
 // (round-half-even, truncating LUT index, exclusive upper bounds, lower clamp at 0) follows the reference bit for bit.
 // DEVIATION: blob cells whose index is outside [0, 600) are dropped (the reference wraps negative indices and is
 // out-of-bounds above 599).
-#include "aem_common.cuh"
+#include "orca_device.cuh"     // env_prepare = ORCA + env lookahead in one launch (this file is built with -fmad=false)
 
 namespace aem {
 
@@ -105,8 +105,12 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
     const double *__restrict__ new_vel, const double *__restrict__ global_time, const double *__restrict__ actions_all,
     int action_env_stride, const double *__restrict__ lut, const aem_env_params p, double amax, int tile_cap,
     double *__restrict__ rewards, int32_t *__restrict__ info, double *__restrict__ dmin_out,
-    double *__restrict__ humans_next, const int32_t *__restrict__ nact)
+    double *__restrict__ humans_next, const int32_t *__restrict__ nact, double *new_vel_out, int robot_visible)
 {
+    // fused mode (new_vel_out != nullptr, aem_env_prepare): the CTA first solves ORCA for its own humans, one warp per
+    // human exactly like orca_kernel, and writes the new velocities; `new_vel` is not read
+    __shared__ Line s_lines[ENV_THREADS / 32][32];
+    __shared__ Line s_proj[ENV_THREADS / 32][32];
     extern __shared__ __align__(16) double dsm[];
     double *tile = dsm;                         // [tile_cap]
     double *partial = tile + tile_cap;          // [ENV_THREADS]
@@ -124,7 +128,22 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
     for (int i = tid; i < n * 8; i += ENV_THREADS) sh[i] = humans[(size_t)b * nstride * 8 + i];
     if (tid < 9) sr9[tid] = robot[(size_t)b * 9 + tid];
     if (tid < AEM_MAX_ACTIONS) prob[tid] = 0.0;
+    if (new_vel_out) {
+        const int lane = tid & 31, wib = tid >> 5;
+        for (int i = wib; i < nstride; i += ENV_THREADS / 32) {
+            double *o = new_vel_out + ((size_t)b * nstride + i) * 2;
+            if (i >= n) {
+                if (lane == 0) { o[0] = 0.0; o[1] = 0.0; }
+                continue;
+            }
+            const V2 res = orca_agent(humans + (size_t)b * nstride * 8, robot + (size_t)b * 9, i, n, (float)p.time_step,
+                                      p.orca_safety_space, robot_visible, s_lines[wib], s_proj[wib], lane);
+            if (lane == 0) { o[0] = (double)res.x; o[1] = (double)res.y; }
+            __syncwarp();
+        }
+    }
     __syncthreads();
+    const double *nv = new_vel_out ? new_vel_out : new_vel;
     const double rx = sr9[0], ry = sr9[1], rrad = sr9[4];
     const double search_radius = rrad + (n > 0 ? sh[4] : 0.0);   // crowd_sim.py:169-173
     const int TPA = ENV_THREADS / A;                              // threads per action (>= 2 for A <= 128)
@@ -220,7 +239,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
         o[0] = o[1] = o[2] = o[3] = o[4] = 0.0;
     }
     if (humans_next && tid < n) {                          // agent.py:63-74
-        const double vx = new_vel[((size_t)b * nstride + tid) * 2], vy = new_vel[((size_t)b * nstride + tid) * 2 + 1];
+        const double vx = nv[((size_t)b * nstride + tid) * 2], vy = nv[((size_t)b * nstride + tid) * 2 + 1];
         double *o = humans_next + ((size_t)b * nstride + tid) * 5;
         o[0] = sh[tid * 8] + vx * p.time_step;
         o[1] = sh[tid * 8 + 1] + vy * p.time_step;
@@ -270,13 +289,14 @@ static int g_tile_cap[64] = {0};     // per device: cudaFuncSetAttribute is a pe
 cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const double *humans,
                                     const double *new_vel, const double *global_time, const double *actions,
                                     int action_env_stride, const double *lut, const aem_env_params &p, double amax, double *rewards,
-                                    int32_t *info, double *dmin, double *humans_next, cudaStream_t st, const int32_t *nact)
+                                    int32_t *info, double *dmin, double *humans_next, cudaStream_t st, const int32_t *nact,
+                                    double *new_vel_out)
 {
     if (B <= 0) return cudaSuccess;
     const int side = 2 * (int)ceil(1.5 * p.human_timestep / GRID_RES) + 3;
     const int tile_cap = side * side;
     const size_t smem = (size_t)(tile_cap + ENV_THREADS + 8 + AEM_MAX_ACTIONS + AEM_MAX_HUMANS * 8 + 9 + 1) * 8;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (smem + 2 * (ENV_THREADS / 32) * 32 * sizeof(Line) > 227 * 1024) return cudaErrorInvalidValue;
     int dev = 0;
     cudaGetDevice(&dev);
     if (tile_cap > g_tile_cap[dev & 63]) {
@@ -287,7 +307,8 @@ cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const
     }
     env_lookahead_kernel<<<B, ENV_THREADS, smem, st>>>(B, n, A, robot, humans, new_vel, global_time, actions,
                                                        action_env_stride, lut, p,
-                                                       amax, tile_cap, rewards, info, dmin, humans_next, nact);
+                                                       amax, tile_cap, rewards, info, dmin, humans_next, nact, new_vel_out,
+                                                       p.robot_visible);
     return cudaGetLastError();
 }
 
@@ -342,6 +363,104 @@ cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double
     env_reset_kernel<<<(B + threads - 1) / threads, threads, 0, st>>>(B, n, robot, humans, global_time, done, info,
                                                                       pool_robot, pool_humans, P, case_idx,
                                                                       case_stride, outcome_counts, nact, pool_nact);
+    return cudaGetLastError();
+}
+
+// The end of a decision step in one launch, one warp per environment: the argmax of select_kernel (multi_human_rl.py:
+// 321-322, 368-372), step(update=True) of env_apply_kernel for the action it chose, and -- when a scenario pool is given --
+// the re-seeding of env_reset_kernel for the environments that finished.  Same arithmetic, same order per environment.
+__global__ void __launch_bounds__(256) env_finish_kernel(
+    int B, int n, int A, const double *__restrict__ values, double *__restrict__ robot, double *__restrict__ humans,
+    const double *__restrict__ new_vel, double *__restrict__ global_time, const double *__restrict__ actions_all,
+    int action_env_stride, const double *__restrict__ rewards, const int32_t *__restrict__ info,
+    const double *__restrict__ dmin, double time_step, int32_t *__restrict__ best, double *__restrict__ out_reward,
+    int32_t *__restrict__ out_done, int32_t *__restrict__ out_info, double *__restrict__ out_dmin, int32_t *nact,
+    const double *__restrict__ pool_robot, const double *__restrict__ pool_humans, int P, int32_t *__restrict__ case_idx,
+    int case_stride, unsigned long long *__restrict__ outcome_counts, const int32_t *__restrict__ pool_nact)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const unsigned FULLM = 0xffffffffu;
+    // ---- select: first strict maximum, NaN never wins; the goal short-circuit picks action 0
+    const double *v = values + (size_t)b * A;
+    double bv = -INFINITY;
+    int bi = -1;
+    for (int a = lane; a < A; a += 32) {
+        const double x = v[a];
+        if (x > bv) { bv = x; bi = a; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(FULLM, bv, off);
+        const int oi = __shfl_xor_sync(FULLM, bi, off);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    double *rb = robot + (size_t)b * 9;
+    {
+        const double dx = rb[0] - rb[5], dy = rb[1] - rb[6];
+        if (sqrt(dy * dy + dx * dx) < rb[4]) bi = 0;
+    }
+    if (lane == 0 && best) best[b] = bi;
+    __syncwarp();                       // every lane has read the robot row before lane 0 advances it
+    // ---- apply (crowd_sim.py:653-669, agent.py:122-131)
+    const int na = nact ? min(max(nact[b], 0), n) : n;
+    int a = bi;
+    if (a < 0 || a >= A) a = 0;
+    const double *__restrict__ actions = actions_all + (size_t)b * action_env_stride;
+    const double ax = actions[2 * a], ay = actions[2 * a + 1];
+    const int code = info[(size_t)b * A + a];
+    const int done = (code >= AEM_INFO_REACHGOAL) ? 1 : 0;
+    const bool reseed = pool_robot != nullptr && done;
+    if (lane == 0) {
+        if (out_reward) out_reward[b] = rewards[(size_t)b * A + a];
+        if (out_info) out_info[b] = code;
+        if (out_done) out_done[b] = done;
+        if (dmin && out_dmin) out_dmin[b] = dmin[(size_t)b * A + a];
+    }
+    if (!reseed) {
+        if (lane == 0) {
+            rb[0] = rb[0] + ax * time_step;
+            rb[1] = rb[1] + ay * time_step;
+            rb[2] = ax; rb[3] = ay;
+            global_time[b] += time_step;
+        }
+        for (int i = lane; i < na; i += 32) {
+            double *hh = humans + ((size_t)b * n + i) * 8;
+            const double vx = new_vel[((size_t)b * n + i) * 2], vy = new_vel[((size_t)b * n + i) * 2 + 1];
+            hh[0] = hh[0] + vx * time_step;
+            hh[1] = hh[1] + vy * time_step;
+            hh[2] = vx; hh[3] = vy;
+        }
+        return;
+    }
+    // ---- the episode ended: the next scenario of this environment (the applied state would be overwritten)
+    const int c = case_idx[b];
+    const int src = ((c % P) + P) % P;
+    __syncwarp();
+    for (int k = lane; k < 9; k += 32) robot[(size_t)b * 9 + k] = pool_robot[(size_t)src * 9 + k];
+    for (int k = lane; k < n * 8; k += 32) humans[(size_t)b * n * 8 + k] = pool_humans[(size_t)src * n * 8 + k];
+    if (lane == 0) {
+        if (nact && pool_nact) nact[b] = pool_nact[src];
+        global_time[b] = 0.0;
+        case_idx[b] = c + case_stride;
+        if (outcome_counts && code >= 0 && code < 5) atomicAdd(outcome_counts + code, 1ULL);
+    }
+}
+
+cudaError_t launch_env_finish(int B, int n, int A, const double *values, double *robot, double *humans, const double *new_vel,
+                              double *global_time, const double *actions, int action_env_stride, const double *rewards,
+                              const int32_t *info, const double *dmin, double time_step, int32_t *best, double *out_reward,
+                              int32_t *out_done, int32_t *out_info, double *out_dmin, int32_t *nact, const double *pool_robot,
+                              const double *pool_humans, int P, int32_t *case_idx, int case_stride,
+                              unsigned long long *outcome_counts, const int32_t *pool_nact, cudaStream_t st)
+{
+    if (B <= 0) return cudaSuccess;
+    const int threads = 256;
+    const int blocks = (int)(((long long)B * 32 + threads - 1) / threads);
+    env_finish_kernel<<<blocks, threads, 0, st>>>(B, n, A, values, robot, humans, new_vel, global_time, actions,
+                                                  action_env_stride, rewards, info, dmin, time_step, best, out_reward,
+                                                  out_done, out_info, out_dmin, nact, pool_robot, pool_humans, P, case_idx,
+                                                  case_stride, outcome_counts, pool_nact);
     return cudaGetLastError();
 }
 

@@ -108,6 +108,43 @@ class Engine:
                                          _ptr(rewards), _ptr(info), _ptr(dmin), _ptr(hnext), self._stream()))
         return rewards, info, dmin, hnext
 
+    def env_prepare(self, robot, humans, global_time, out=None):
+        """aem_orca + aem_env_lookahead in one launch -> (new_vel, rewards, info, dmin, humans_next)"""
+        B, n, _ = humans.shape
+        A = self.A
+        self._chk(humans, F64, (B, n, 8)); self._chk(robot, F64, (B, 9)); self._chk(global_time, F64, (B,))
+        if out is None:
+            out = (torch.empty((B, n, 2), dtype=F64, device=self.device),
+                   torch.empty((B, A), dtype=F64, device=self.device), torch.empty((B, A), dtype=I32, device=self.device),
+                   torch.empty((B, A), dtype=F64, device=self.device),
+                   torch.empty((B, n, 5), dtype=F64, device=self.device))
+        new_vel, rewards, info, dmin, hnext = out
+        check(self.lib.aem_env_prepare(self.h, B, n, _ptr(robot), _ptr(humans), _ptr(global_time), _ptr(new_vel),
+                                       _ptr(rewards), _ptr(info), _ptr(dmin), _ptr(hnext), self._stream()))
+        return new_vel, rewards, info, dmin, hnext
+
+    def env_finish(self, values, robot, humans, new_vel, global_time, rewards, info, dmin, best=None, pool=None):
+        """argmax + aem_env_apply (+ aem_env_reset_done when `pool` = (pool_robot, pool_humans, case_idx, case_stride,
+        outcome_counts)) in one launch -> (reward, done, info, dmin) [B]; `best` [B] i32 receives the chosen actions"""
+        B, n, _ = humans.shape
+        self._chk(values, F64, (B, self.A))
+        o_reward = torch.empty((B,), dtype=F64, device=self.device)
+        o_done = torch.empty((B,), dtype=I32, device=self.device)
+        o_info = torch.empty((B,), dtype=I32, device=self.device)
+        o_dmin = torch.empty((B,), dtype=F64, device=self.device)
+        if pool is not None:
+            pool_robot, pool_humans, case_idx, case_stride, outcome_counts = pool
+            P = pool_robot.shape[0]
+            self._chk(case_idx, I32, (B,)); self._chk(pool_robot, F64, (P, 9)); self._chk(pool_humans, F64, (P, n, 8))
+        else:
+            pool_robot = pool_humans = case_idx = outcome_counts = None
+            P = case_stride = 0
+        check(self.lib.aem_env_finish(self.h, B, n, _ptr(values), _ptr(robot), _ptr(humans), _ptr(new_vel), _ptr(global_time),
+                                      _ptr(rewards), _ptr(info), _ptr(dmin), _ptr(best), _ptr(o_reward), _ptr(o_done),
+                                      _ptr(o_info), _ptr(o_dmin), _ptr(pool_robot), _ptr(pool_humans), int(P),
+                                      _ptr(case_idx), int(case_stride), _ptr(outcome_counts), self._stream()))
+        return o_reward, o_done, o_info, o_dmin
+
     def lookahead(self, robot, humans_next, rewards, gamma_bar, out=None, want_net=True):
         B, n, _ = humans_next.shape
         A = self.A

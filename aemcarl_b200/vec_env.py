@@ -96,9 +96,8 @@ class VecCrowdSim:
         """predict(): ORCA for the humans, per-action env lookahead, fused value lookahead, argmax."""
         e = self.engine
         e.set_active_counts(self.n_active, self.pool_n_active)          # None, None for uniform batches
-        e.orca(self.humans, self.robot, out=self.new_vel)
-        e.env_lookahead(self.robot, self.humans, self.new_vel, self.global_time,
-                        out=(self.rewards, self.info, self.dmin, self.humans_next))
+        e.env_prepare(self.robot, self.humans, self.global_time,
+                      out=(self.new_vel, self.rewards, self.info, self.dmin, self.humans_next))
         e.lookahead(self.robot, self.humans_next, self.rewards, self.gamma_bar(),
                     out=(self.values, self.net_values, self.best, self.act_steps))
         return self.best
@@ -117,8 +116,18 @@ class VecCrowdSim:
         return out
 
     def decide_and_step(self, auto_reset=True):
-        self.lookahead()
-        return self.apply(auto_reset=auto_reset)
+        """lookahead() + apply() in three launches: ORCA + env lookahead, the value lookahead, argmax + env step + re-seeding"""
+        e = self.engine
+        e.set_active_counts(self.n_active, self.pool_n_active)
+        e.env_prepare(self.robot, self.humans, self.global_time,
+                      out=(self.new_vel, self.rewards, self.info, self.dmin, self.humans_next))
+        e.lookahead(self.robot, self.humans_next, self.rewards, self.gamma_bar(),
+                    out=(self.values, self.net_values, None, self.act_steps))
+        pool = (self.pool_robot, self.pool_humans, self.case_idx, self.case_stride, self.outcomes) if auto_reset else None
+        out = e.env_finish(self.values, self.robot, self.humans, self.new_vel, self.global_time, self.rewards, self.info,
+                           self.dmin, best=self.best, pool=pool)
+        self.last = out
+        return out
 
     def narrow(self, n):
         """a view of the first n environments (all per-environment buffers sliced, the scenario pool shared): the kernels of a

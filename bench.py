@@ -369,16 +369,18 @@ def main():
         e = eng
         if ev:
             ev[0].record()
-        e.orca(env.humans, env.robot, out=env.new_vel)
-        e.env_lookahead(env.robot, env.humans, env.new_vel, env.global_time,
-                        out=(env.rewards, env.info, env.dmin, env.humans_next))
+        # three launches per step: ORCA + env lookahead | the value lookahead | argmax + env step + re-seeding
+        e.env_prepare(env.robot, env.humans, env.global_time,
+                      out=(env.new_vel, env.rewards, env.info, env.dmin, env.humans_next))
         if ev:
             ev[1].record()
         e.lookahead(env.robot, env.humans_next, env.rewards, gbar,
-                    out=(env.values, env.net_values, env.best, env.act_steps))
+                    out=(env.values, env.net_values, None, env.act_steps))
         if ev:
             ev[2].record()
-        env.apply(auto_reset=True)
+        env.last = e.env_finish(env.values, env.robot, env.humans, env.new_vel, env.global_time, env.rewards, env.info,
+                                env.dmin, best=env.best,
+                                pool=(env.pool_robot, env.pool_humans, env.case_idx, env.case_stride, env.outcomes))
         if ev:
             ev[3].record()
 
@@ -514,13 +516,13 @@ def main():
                           "(256 MB memset outside the event pairs)", "parallelism": "env-sharded x%d" % world},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                "cpu_baseline": cpu,
-               "kernel_ms": {"lookahead": kernel_ms, "orca+env_lookahead": float(np.mean(
-                   [e[0].elapsed_time(e[1]) for e in evs])), "apply+reset": float(np.mean(
+               "kernel_ms": {"lookahead": kernel_ms, "env_prepare (orca + env lookahead)": float(np.mean(
+                   [e[0].elapsed_time(e[1]) for e in evs])), "env_finish (argmax + apply + reset)": float(np.mean(
                        [e[2].elapsed_time(e[3]) for e in evs]))}}
         # the small kernels next to the dominant one, against the HBM roof (they stream the env state; latency-bound)
         A = 81
-        step_bytes = {"orca+env_lookahead": B * ((9 + 8 * n + 1) * 8 + 2 * n * 2 * 8 + A * (8 + 4 + 8) + n * 5 * 8),
-                      "apply+reset": B * (2 * (9 + 8 * n + 1) * 8 + n * 2 * 8 + 4 + 3 * 8 + 4 * 8)}
+        step_bytes = {"env_prepare (orca + env lookahead)": B * ((9 + 8 * n + 1) * 8 + 2 * n * 2 * 8 + A * (8 + 4 + 8) + n * 5 * 8),
+                      "env_finish (argmax + apply + reset)": B * (2 * (9 + 8 * n + 1) * 8 + n * 2 * 8 + 4 + 3 * 8 + 4 * 8)}
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         out["other_kernels"] = [{"name": k, "ms": out["kernel_ms"][k], "bound": "hbm", "algorithmic_bytes": int(v),
                                  "achieved": v / (out["kernel_ms"][k] / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",

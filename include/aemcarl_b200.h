@@ -13,6 +13,9 @@
  *                          cadrl.py:239-274, ValueNetworkTransformerAndGRU.forward qnetwork_factory.py:641-687,
  *                          ATCBasic/GRUEXND components.py:38-137, r + gamma^(dt*v_pref) * V, strict-'>' argmax)
  *   aem_env_apply       <- crowd_sim/envs/crowd_sim.py:653-669 (step(update=True): advance robot/humans/time)
+ *   aem_env_prepare     <- aem_orca + aem_env_lookahead in ONE launch (crowd_sim.py:554-651 calls ORCA at :562-568 itself)
+ *   aem_env_finish      <- argmax of aem_lookahead + aem_env_apply + aem_env_reset_done in ONE launch (multi_human_rl.py:368-372,
+ *                          crowd_sim.py:653-669, explorer.py:44-47)
  *   aem_env_reset_done  <- CrowdSim.reset for finished episodes of a batch (crowd_sim.py:486-552, explorer.py:44-47)
  *   aem_value_forward   <- model(state) on already rotated states (explorer.py:137, trainer.py:52,75)
  *   aem_gru_act         <- ATCBasic.forward components.py:107-137 (fused GRU-cell / adaptive-computation-time)
@@ -129,7 +132,8 @@ int aem_env_lookahead(aem_handle h, int B, int n, const double *robot_d, const d
                       double *dmin_d, double *humans_next_d, void *stream);
 
 /* values_d = rewards + gamma_bar * V (f64); best_d = first strict maximum (-1 if every value is NaN; 0 when the
- * robot already is at its goal, policy.py:45-49).  net_values_d / act_steps_d may be NULL. */
+ * robot already is at its goal, policy.py:45-49).  net_values_d / act_steps_d may be NULL; best_d may be NULL when
+ * aem_env_finish takes the argmax (one launch less). */
 int aem_lookahead(aem_handle h, int B, int n, const double *robot_d, const double *humans_next_d,
                   const double *rewards_d, double gamma_bar, double *values_d, float *net_values_d,
                   int32_t *best_d, uint8_t *act_steps_d, void *stream);
@@ -139,6 +143,21 @@ int aem_env_apply(aem_handle h, int B, int n, double *robot_d, double *humans_d,
                   double *global_time_d, const int32_t *chosen_d, const double *rewards_d, const int32_t *info_d,
                   const double *dmin_d, double *out_reward_d, int32_t *out_done_d, int32_t *out_info_d,
                   double *out_dmin_d, void *stream);
+
+/* The decision step in three launches: aem_env_prepare, aem_lookahead (best_d = NULL), aem_env_finish.
+ * aem_env_prepare = aem_orca followed by aem_env_lookahead, bit for bit, in one kernel: every environment's CTA solves
+ * ORCA for its own humans first (new_vel_d [B][n][2] is an OUTPUT here). */
+int aem_env_prepare(aem_handle h, int B, int n, const double *robot_d, const double *humans_d, const double *global_time_d,
+                    double *new_vel_d, double *rewards_d, int32_t *info_d, double *dmin_d, double *humans_next_d, void *stream);
+
+/* aem_env_finish = the argmax of aem_lookahead over values_d [B][A] (-> best_d, may be NULL), aem_env_apply for that action
+ * and, when pool_robot_d != NULL, aem_env_reset_done for the environments that finished -- one kernel, one warp per
+ * environment, the same results as the three calls.  out_* [B] may each be NULL; without a pool pass NULL / 0 for the last six. */
+int aem_env_finish(aem_handle h, int B, int n, const double *values_d, double *robot_d, double *humans_d,
+                   const double *new_vel_d, double *global_time_d, const double *rewards_d, const int32_t *info_d,
+                   const double *dmin_d, int32_t *best_d, double *out_reward_d, int32_t *out_done_d, int32_t *out_info_d,
+                   double *out_dmin_d, const double *pool_robot_d, const double *pool_humans_d, int P, int32_t *case_idx_d,
+                   int case_stride, unsigned long long *outcome_counts_d, void *stream);
 
 /* Vectorised Explorer reset (explorer.py:44-47 + CrowdSim.reset crowd_sim.py:486-552): every env with done_d[b] != 0
  * is re-seeded from scenario `case_idx_d[b] mod P` of a host-generated pool (pool_robot_d [P][9], pool_humans_d

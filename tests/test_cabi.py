@@ -44,3 +44,16 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(EnvParams) == 10 * 8 + 8 + 8
     from oracle.pyoracle import EnvParams as OP
     assert ctypes.sizeof(OP) == ctypes.sizeof(EnvParams)
+
+
+def test_ctypes_signatures_have_the_argument_count_of_the_header():
+    """every binding in aemcarl_b200/_lib.py passes as many arguments as the prototype in include/aemcarl_b200.h declares"""
+    from aemcarl_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "aemcarl_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = dict(re.findall(r"\b(aem_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(protos) == set(_lib.SYMBOLS)
+    for name, args in protos.items():
+        args = args.strip()
+        n = 0 if args in ("", "void") else len(args.split(","))
+        assert n == len(_lib.SYMBOLS[name][1]), (name, n, len(_lib.SYMBOLS[name][1]))
