@@ -402,6 +402,8 @@ int aem_set_action_space(aem_handle h, const double *actions, int A)
 {
     if (!h || !actions) return aem_set_error(AEM_ERR_INVALID, "null argument");
     if (A < 1 || A > AEM_MAX_ACTIONS) return aem_set_error(AEM_ERR_INVALID, "A must be in [1, 128]");
+    if (h->actions_set && h->A == A && memcmp(h->actions_h, actions, sizeof(double) * 2 * A) == 0)
+        return AEM_OK;                     // the same table again (serial callers set it before every step): nothing to upload
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     AEM_CUDA_CHECK(cudaDeviceSynchronize());
     memcpy(h->actions_h, actions, sizeof(double) * 2 * A);

@@ -522,7 +522,7 @@ def main():
         # the small kernels next to the dominant one, against the HBM roof (they stream the env state; latency-bound)
         A = 81
         step_bytes = {"env_prepare (orca + env lookahead)": B * ((9 + 8 * n + 1) * 8 + 2 * n * 2 * 8 + A * (8 + 4 + 8) + n * 5 * 8),
-                      "env_finish (argmax + apply + reset)": B * (2 * (9 + 8 * n + 1) * 8 + n * 2 * 8 + 4 + 3 * 8 + 4 * 8)}
+                      "env_finish (argmax + apply + reset)": B * (A * 8 + 2 * (9 + 8 * n + 1) * 8 + n * 2 * 8 + 4 + 3 * 8 + 4 * 8)}
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         out["other_kernels"] = [{"name": k, "ms": out["kernel_ms"][k], "bound": "hbm", "algorithmic_bytes": int(v),
                                  "achieved": v / (out["kernel_ms"][k] / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
