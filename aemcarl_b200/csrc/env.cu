@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
     // human exactly like orca_kernel, and writes the new velocities; `new_vel` is not read
     __shared__ Line s_lines[ENV_THREADS / 32][32];
     __shared__ Line s_proj[ENV_THREADS / 32][32];
+    __shared__ int s_near[AEM_MAX_HUMANS];
     extern __shared__ __align__(16) double dsm[];
     double *tile = dsm;                         // [tile_cap]
     double *partial = tile + tile_cap;          // [ENV_THREADS]
@@ -148,10 +149,29 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
     const double search_radius = rrad + (n > 0 ? sh[4] : 0.0);   // crowd_sim.py:169-173
     const int TPA = ENV_THREADS / A;                              // threads per action (>= 2 for A <= 128)
 
-    for (int h = 0; h < n; ++h) {
-        const double hpx = sh[h * 8], hpy = sh[h * 8 + 1], hvx = sh[h * 8 + 2], hvy = sh[h * 8 + 3];
+    // The disc test of crowd_sim.py:176-178, sqrt(dx^2 + dy^2) * res > search_radius, is monotone in the integer dx^2 + dy^2
+    // (correctly rounded sqrt, multiplication by a positive constant): find the largest integer that still fails it with
+    // the SAME FP64 expression once, then every cell of every candidate disc is an integer comparison.
+    int disc_s;
+    {
+        const double q = search_radius / GRID_RES;
+        const double q2 = q * q;
+        int s0 = (q2 >= 0.0 && q2 < 720000.0) ? (int)q2 : (q2 >= 720000.0 ? 720000 : 0);
+        while (s0 < 720001 && !(sqrt((double)(s0 + 1)) * GRID_RES > search_radius)) ++s0;
+        while (s0 >= 0 && sqrt((double)s0) * GRID_RES > search_radius) --s0;
+        disc_s = s0;
+    }
+    // which humans' blobs can reach a candidate disc at all: one thread per human (two FP64 hypot each -- a quarter of the
+    // kernel's instructions when all 256 threads evaluated the test for every human)
+    if (tid < n) {
+        const double hpx = sh[tid * 8], hpy = sh[tid * 8 + 1], hvx = sh[tid * 8 + 2], hvy = sh[tid * 8 + 3];
         const double m0 = hypot(hvx * p.human_timestep, hvy * p.human_timestep);
-        if (hypot(hpx - rx, hpy - ry) > m0 + search_radius + amax + 0.1) continue;   // cannot touch any disc (exact)
+        s_near[tid] = !(hypot(hpx - rx, hpy - ry) > m0 + search_radius + amax + 0.1);   // else: cannot touch any disc (exact)
+    }
+    __syncthreads();
+    for (int h = 0; h < n; ++h) {
+        if (!s_near[h]) continue;
+        const double hpx = sh[h * 8], hpy = sh[h * 8 + 1], hvx = sh[h * 8 + 2], hvy = sh[h * 8 + 3];
         const Blob bl = blob_setup(hpx, hpy, hvx, hvy, p.human_timestep);
         const int cells = bl.rw * bl.rh;
         if (cells <= 0) continue;
@@ -189,8 +209,9 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
             y0 = max(max(y0, bl.ylo), 0); y1 = min(min(y1, bl.yhi), GRID_W);
             for (int y = y0 + j; y < y1; y += TPA) {
                 const double *trow = tile + (y - bl.ylo) * bl.rw - bl.xlo;
+                const int dy2 = (y - acy) * (y - acy);
                 for (int x = x0; x < x1; ++x) {
-                    if (int_hypot(x - acx, y - acy) * GRID_RES > search_radius) continue;
+                    if ((x - acx) * (x - acx) + dy2 > disc_s) continue;       // == int_hypot(..) * GRID_RES > search_radius
                     psum += trow[x];
                 }
             }
