@@ -109,8 +109,6 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
 {
     // fused mode (new_vel_out != nullptr, aem_env_prepare): the CTA first solves ORCA for its own humans, one warp per
     // human exactly like orca_kernel, and writes the new velocities; `new_vel` is not read
-    __shared__ Line s_lines[ENV_THREADS / 32][32];
-    __shared__ Line s_proj[ENV_THREADS / 32][32];
     __shared__ int s_near[AEM_MAX_HUMANS];
     extern __shared__ __align__(16) double dsm[];
     double *tile = dsm;                         // [tile_cap]
@@ -119,6 +117,9 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
     double *prob = red + 8;                     // [AEM_MAX_ACTIONS]
     double *sh = prob + AEM_MAX_ACTIONS;        // [n][8] humans
     double *sr9 = sh + AEM_MAX_HUMANS * 8;      // [9] robot
+    // ORCA's half-plane lists (8 warps x 32 lines x 2) live in the tile, which nobody touches before the ORCA phase is over
+    Line(*s_lines)[32] = reinterpret_cast<Line(*)[32]>(tile);
+    Line(*s_proj)[32] = s_lines + ENV_THREADS / 32;
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -315,9 +316,10 @@ cudaError_t launch_env_lookahead(int B, int n, int A, const double *robot, const
 {
     if (B <= 0) return cudaSuccess;
     const int side = 2 * (int)ceil(1.5 * p.human_timestep / GRID_RES) + 3;
-    const int tile_cap = side * side;
+    const int orca_doubles = 2 * (ENV_THREADS / 32) * 32 * (int)sizeof(Line) / 8;      // the fused ORCA phase borrows the tile
+    const int tile_cap = side * side > orca_doubles ? side * side : orca_doubles;
     const size_t smem = (size_t)(tile_cap + ENV_THREADS + 8 + AEM_MAX_ACTIONS + AEM_MAX_HUMANS * 8 + 9 + 1) * 8;
-    if (smem + 2 * (ENV_THREADS / 32) * 32 * sizeof(Line) > 227 * 1024) return cudaErrorInvalidValue;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
     int dev = 0;
     cudaGetDevice(&dev);
     if (tile_cap > g_tile_cap[dev & 63]) {
