@@ -18,6 +18,13 @@ ROOT = os.path.dirname(HERE)
 
 
 def worker(rank, procs, seconds, humans, q):
+    try:
+        q.put(measure(rank, procs, seconds, humans))
+    except BaseException as e:           # a dead worker must not leave the parent waiting on the queue
+        q.put(("error", "%s: %s" % (type(e).__name__, e)))
+
+
+def measure(rank, procs, seconds, humans):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     sys.path.insert(0, ROOT)
     import logging
@@ -41,7 +48,7 @@ def worker(rank, procs, seconds, humans, q):
         if done:
             case += procs
             ob = env.reset("test", case % 500)
-    q.put((steps, time.perf_counter() - t0))
+    return steps, time.perf_counter() - t0
 
 
 def main():
@@ -52,6 +59,9 @@ def main():
     a = ap.parse_args()
     ref = os.environ.get("AEM_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference") else os.path.join(HERE, "_ref"))
     os.environ["AEM_REFERENCE"] = os.path.abspath(ref)
+    # this is the CPU baseline: hide the GPU from the workers, so that the reference's hard-coded .cuda() calls are the
+    # identity of oracle/ref_shim.py on a GPU box too (with a visible GPU they would move the inputs of a CPU model there)
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     ps = [ctx.Process(target=worker, args=(r, a.procs, a.seconds, a.humans, q)) for r in range(a.procs)]
@@ -61,6 +71,10 @@ def main():
     res = [q.get() for _ in ps]
     for p in ps:
         p.join()
+    bad = [r[1] for r in res if r[0] == "error"]
+    if bad:
+        print(json.dumps({"unavailable": "reference worker failed: " + bad[0][:300]}))
+        return
     steps = sum(s for s, _ in res)
     rate = sum(s / t for s, t in res)
     print(json.dumps({"value": rate, "unit": "env-steps/s", "cores": a.procs, "kind": "reference",
