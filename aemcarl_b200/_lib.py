@@ -73,6 +73,7 @@ SYMBOLS = {
     "aem_env_step_xy": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, ctypes.c_double, _VP, _VP, _VP,
                                        _VP, _VP, _VP]),
     "aem_transform": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP]),
+    "aem_generate_mixed_scenarios": (ctypes.c_int, [_VP, ctypes.c_uint32, ctypes.c_int] + [_VP] * 5),
     "aem_generate_scenarios": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(ScenarioParams), _VP, _VP, _VP]),
     "aem_set_active_counts": (ctypes.c_int, [_VP, _VP, _VP]),

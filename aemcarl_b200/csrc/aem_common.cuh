@@ -180,7 +180,7 @@ cudaError_t launch_env_reset(int B, int n, double *robot, double *humans, double
                              int32_t *nact = nullptr, const int32_t *pool_nact = nullptr);
 
 cudaError_t launch_scenarios(int rule, uint32_t first_seed, int count, int n, const aem_scenario_params &p, double *robot,
-                             double *humans, cudaStream_t st);
+                             double *humans, cudaStream_t st, int32_t *n_active = nullptr);
 cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, const float *states, const float *targets,
                               float *grad, float *loss, float *values, int32_t *steps, cudaStream_t st, float *loss_sum = nullptr,
                               const unsigned long long *drop_ctr_dev = nullptr);

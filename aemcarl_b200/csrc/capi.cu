@@ -759,6 +759,19 @@ int aem_generate_scenarios(aem_handle h, int rule, uint32_t first_seed, int coun
     return AEM_OK;
 }
 
+int aem_generate_mixed_scenarios(aem_handle h, uint32_t first_seed, int count, const aem_scenario_params *p, double *robot_d,
+                                 double *humans_d, int32_t *n_active_d, void *stream)
+{
+    if (!h || !p) return aem_set_error(AEM_ERR_INVALID, "null argument");
+    if (count < 0) return aem_set_error(AEM_ERR_INVALID, "bad count");
+    if (count == 0) return AEM_OK;
+    if (!robot_d || !humans_d || !n_active_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
+    AEM_CUDA_CHECK(cudaSetDevice(h->device));
+    AEM_CUDA_CHECK(launch_scenarios(2, first_seed, count, 5, *p, robot_d, humans_d, as_stream(stream), n_active_d));
+    h->launches += 1;
+    return AEM_OK;
+}
+
 int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const float *states_d, const float *targets_d,
                    float *grad_d, float *loss_d, float *values_d, int32_t *steps_d, void *stream)
 {

@@ -49,8 +49,11 @@ constexpr int SCN_MAX_TRIES = 20000;
 __device__ __forceinline__ double norm2(double dx, double dy) { return sqrt(dx * dx + dy * dy); }
 
 // agents so far: robot + humans [0, m); layout of `humans` rows: px,py,vx,vy,radius,gx,gy,v_pref
+// rule 2 = 'mixed' (crowd_sim.py:337-386): a static scene with probability 0.2, else a dynamic one; the number of humans
+// (<= 5) is part of the draw and goes to n_active_out, rows beyond it are padding (parked at (0, -100), zero velocity).
 __global__ void __launch_bounds__(64) scenario_kernel(int rule, uint32_t first_seed, int count, int n, aem_scenario_params p,
-                                                      double *__restrict__ robot_out, double *__restrict__ humans_out)
+                                                      double *__restrict__ robot_out, double *__restrict__ humans_out,
+                                                      int32_t *__restrict__ n_active_out)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= count) return;
@@ -62,14 +65,57 @@ __global__ void __launch_bounds__(64) scenario_kernel(int rule, uint32_t first_s
     rb[0] = rpx; rb[1] = rpy; rb[2] = 0.0; rb[3] = 0.0; rb[4] = p.robot_radius; rb[5] = rgx; rb[6] = rgy;
     rb[7] = p.robot_v_pref; rb[8] = PI / 2;
     bool failed = false;
-    for (int m = 0; m < n && !failed; ++m) {
+    int humans_here = n;            // humans of this case (the 'mixed' rule draws it)
+    bool is_static = false;
+    if (rule == 2) {
+        is_static = rs.random_sample() < 0.2;
+        double prob = rs.random_sample();
+        const double ps[6] = {0.05, 0.2, 0.2, 0.3, 0.1, 0.15};     // static scenes: 0..5 humans
+        const double pd[5] = {0.3, 0.3, 0.2, 0.1, 0.1};            // dynamic scenes: 1..5 humans
+        humans_here = 5;                                           // (the reference keeps its configured 5 if no entry matches)
+        for (int k = 0; k < (is_static ? 6 : 5); ++k) {
+            const double pk = is_static ? ps[k] : pd[k];
+            if (prob - pk <= 0) { humans_here = is_static ? k : k + 1; break; }
+            prob -= pk;
+        }
+        for (int m = 0; m < n; ++m) {                              // padding rows first; real humans overwrite theirs
+            double *h = hs + m * 8;
+            h[0] = 0.0; h[1] = -100.0; h[2] = 0.0; h[3] = 0.0; h[4] = p.human_radius; h[5] = 0.0; h[6] = -100.0; h[7] = 0.0;
+        }
+        if (is_static && humans_here == 0) {                       // one dummy human parked at (0, -10), crowd_sim.py:355-358
+            hs[0] = 0.0; hs[1] = -10.0; hs[4] = p.human_radius; hs[5] = 0.0; hs[6] = -10.0; hs[7] = p.human_v_pref;
+            if (n_active_out) n_active_out[c] = 1;
+            return;
+        }
+        if (n_active_out) n_active_out[c] = humans_here;
+    }
+    for (int m = 0; m < humans_here && !failed; ++m) {
+        // kind of this human: 0 crosses the circle, 1 crosses the square, 2 stands still ('mixed': static scenes; in a
+        // dynamic scene the first two cross the circle, the others the square)
+        const int kind = rule < 2 ? rule : (is_static ? 2 : (m < 2 ? 0 : 1));
         double v_pref = p.human_v_pref, radius = p.human_radius;
-        if (p.randomize_attributes) {
+        if (p.randomize_attributes && kind != 2) {
             v_pref = rs.uniform(0.5, 1.5);
             radius = rs.uniform(0.3, 0.5);
         }
         double px = 0.0, py = 0.0, gx = 0.0, gy = 0.0;
-        if (rule == 0) {                                   // circle crossing: start on the circle, goal opposite
+        if (kind == 2) {                                   // a static obstacle in a 4 x 8 box, goal = start
+            const double sign = rs.random_sample() > 0.5 ? -1.0 : 1.0;
+            for (int tries = 0;; ++tries) {
+                if (tries >= SCN_MAX_TRIES) { failed = true; break; }
+                px = rs.random_sample() * 4.0 * 0.5 * sign;
+                py = (rs.random_sample() - 0.5) * 8.0;
+                bool collide = false;
+                for (int a = -1; a < m && !collide; ++a) {
+                    const double apx = a < 0 ? rpx : hs[a * 8 + 0], apy = a < 0 ? rpy : hs[a * 8 + 1];
+                    const double ar = a < 0 ? p.robot_radius : hs[a * 8 + 4];
+                    collide = !(norm2(px - apx, py - apy) >= radius + ar + p.discomfort_dist);
+                }
+                if (!collide) break;
+            }
+            gx = px;
+            gy = py;
+        } else if (kind == 0) {                            // circle crossing: start on the circle, goal opposite
             for (int tries = 0;; ++tries) {
                 if (tries >= SCN_MAX_TRIES) { failed = true; break; }
                 const double angle = rs.random_sample() * PI * 2;
@@ -122,13 +168,14 @@ __global__ void __launch_bounds__(64) scenario_kernel(int rule, uint32_t first_s
     if (failed) {
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
         for (int i = 0; i < n * 8; ++i) hs[i] = nan;
+        if (n_active_out) n_active_out[c] = 0;
     }
 }
 
 cudaError_t launch_scenarios(int rule, uint32_t first_seed, int count, int n, const aem_scenario_params &p, double *robot,
-                             double *humans, cudaStream_t st)
+                             double *humans, cudaStream_t st, int32_t *n_active)
 {
-    scenario_kernel<<<(count + 63) / 64, 64, 0, st>>>(rule, first_seed, count, n, p, robot, humans);
+    scenario_kernel<<<(count + 63) / 64, 64, 0, st>>>(rule, first_seed, count, n, p, robot, humans, n_active);
     return cudaGetLastError();
 }
 

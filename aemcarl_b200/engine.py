@@ -242,6 +242,22 @@ class Engine:
                                               ctypes.byref(p), _ptr(robot), _ptr(humans), self._stream()))
         return robot, humans
 
+    def generate_mixed_scenarios(self, phase, first_case, count, circle_radius=4.0, square_width=10.0, discomfort_dist=0.2,
+                                 robot_radius=0.3, robot_v_pref=1.0, human_radius=0.3, human_v_pref=1.0,
+                                 randomize_attributes=False):
+        """the 'mixed' rule on the device; the layout of scenarios.generate_mixed_pool -> (robot [count, 9], humans
+        [count, 5, 8] padded, n_active [count] int32) device tensors"""
+        from . import scenarios
+        p = _lib.ScenarioParams(circle_radius, square_width, discomfort_dist, robot_radius, robot_v_pref, human_radius,
+                                human_v_pref, int(bool(randomize_attributes)), 0)
+        robot = torch.empty((count, 9), dtype=F64, device=self.device)
+        humans = torch.empty((count, scenarios.MIXED_MAX_HUMANS, 8), dtype=F64, device=self.device)
+        counts = torch.empty((count,), dtype=I32, device=self.device)
+        seed = scenarios.case_seed(phase, int(first_case))
+        check(self.lib.aem_generate_mixed_scenarios(self.h, ctypes.c_uint32(seed & 0xffffffff), int(count), ctypes.byref(p),
+                                                    _ptr(robot), _ptr(humans), _ptr(counts), self._stream()))
+        return robot, humans, counts
+
     # ---- value-network regression step (trainer.py:47-58) ------------------------------------------------
     def train_grad(self, params, states, targets, grad, loss=None, values=None, steps=None):
         """forward + MSE + backward of the flag-5 network on [B, n, 13] rotated states (batch-global ACT halting);

@@ -31,11 +31,17 @@ class VecCrowdSim:
         if rule == "mixed":
             # per-environment human count (crowd_sim.py:337-386): padded rows + counts, aem_set_active_counts
             self.n = scenarios.MIXED_MAX_HUMANS
-            pr, ph, pc = scenarios.generate_mixed_pool(phase, first_case, self.pool_size, **kw)
-            self.pool_robot_h, self.pool_humans_h = pr, ph
-            self.pool_robot = torch.from_numpy(pr).to(self.device)
-            self.pool_humans = torch.from_numpy(ph).to(self.device)
-            self.pool_n_active = torch.from_numpy(pc).to(self.device)
+            if device_scenarios:       # aem_generate_mixed_scenarios: the same draws on the device
+                self.pool_robot, self.pool_humans, self.pool_n_active = engine.generate_mixed_scenarios(
+                    phase, first_case, self.pool_size, **kw)
+                self.pool_robot_h = self.pool_robot[:1].cpu().numpy()
+                self.pool_humans_h = None
+            else:
+                pr, ph, pc = scenarios.generate_mixed_pool(phase, first_case, self.pool_size, **kw)
+                self.pool_robot_h, self.pool_humans_h = pr, ph
+                self.pool_robot = torch.from_numpy(pr).to(self.device)
+                self.pool_humans = torch.from_numpy(ph).to(self.device)
+                self.pool_n_active = torch.from_numpy(pc).to(self.device)
             self.n_active = torch.zeros((self.B,), dtype=I32, device=self.device)
         elif device_scenarios:
             # aem_generate_scenarios: the same seeded MT19937 draws on the device (square rule bit-exact, circle rule

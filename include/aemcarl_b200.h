@@ -22,6 +22,7 @@
  *   aem_env_step_xy     <- CrowdSim.step for one arbitrary ActionXY per environment (imitation phase, train.py:171-204)
  *   aem_transform       <- MultiHumanRL.transform multi_human_rl.py:423-438 (replay-memory sample of the current state)
  *   aem_generate_scenarios <- CrowdSim.reset's seeded scenario draw, crowd_sim.py:486-552,390-442
+ *   aem_generate_mixed_scenarios <- the 'mixed' rule of that draw (1..5 humans per case), crowd_sim.py:337-386
  *   aem_train_grad      <- Trainer.optimize_batch / optimize_epoch forward + MSE + backward (crowd_nav/utils/trainer.py:47-58,70-82)
  *   aem_train_step_adam <- one iteration of Trainer.optimize_batch with Adam (sample + forward/backward + update), trainer.py:66-86
  *   aem_sample_batch    <- next(iter(DataLoader(memory, batch_size, shuffle=True))), trainer.py:70-72 + memory.py
@@ -176,6 +177,14 @@ int aem_env_reset_done(aem_handle h, int B, int n, double *robot_d, double *huma
  * come from libdevice (<= 1 ulp from numpy's). */
 int aem_generate_scenarios(aem_handle h, int rule, uint32_t first_seed, int count, int n, const aem_scenario_params *p,
                            double *robot_d, double *humans_d, void *stream);
+
+/* The 'mixed' rule of the same draw (crowd_sim.py:337-386): a static scene with probability 0.2 (0..5 standing humans in a
+ * 4 x 8 box, goal = start; none -> one dummy human parked at (0, -10)), else a dynamic one (1..5 humans, the first two cross
+ * the circle, the others the square).  -> robot_d [count][9], humans_d [count][5][8] (rows beyond a case's human count are
+ * padding: parked at (0, -100), zero velocity) and n_active_d [count] i32, the per-environment counts aem_set_active_counts
+ * takes.  Static and square-crossing humans bit-exact, circle-crossing ones within an ulp of cos / sin. */
+int aem_generate_mixed_scenarios(aem_handle h, uint32_t first_seed, int count, const aem_scenario_params *p, double *robot_d,
+                                 double *humans_d, int32_t *n_active_d, void *stream);
 
 /* states_d [S][n][13] f32 (rotated joint states) -> values_d [S] f32, steps_d [S] u8 (may be NULL) */
 int aem_value_forward(aem_handle h, int S, int n, const float *states_d, float *values_d, uint8_t *steps_d,

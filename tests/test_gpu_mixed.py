@@ -113,3 +113,43 @@ def test_mixed_episodes_outcomes_match_the_oracle(oracle, actions):
     print("mixed scenes: counts %s, outcomes (success, collision, timeout) %d %d %d, excused %d"
           % (np.bincount(counts, minlength=6).tolist(), out["success"], out["collision"], out["timeout"], len(excused)))
     eng.close()
+
+
+@pytest.mark.parametrize("randomize", [False, True])
+def test_device_mixed_scenarios_replay_the_host_draw(randomize):
+    """aem_generate_mixed_scenarios against scenarios.generate_mixed_pool (which reproduces the reference's recorded mixed
+    cases bit for bit): the same static / dynamic decision and human count for every case, static and square-crossing
+    humans bit-exact, circle-crossing ones (the first two of a dynamic scene) within 2 ulp of the 4 m radius"""
+    eng = Engine(0)
+    for phase, first in (("train", 77), ("val", 0), ("test", 400)):
+        r_h, h_h, c_h = scenarios.generate_mixed_pool(phase, first, 512, randomize_attributes=randomize)
+        r_d, h_d, c_d = eng.generate_mixed_scenarios(phase, first, 512, randomize_attributes=randomize)
+        r_d, h_d, c_d = r_d.cpu().numpy(), h_d.cpu().numpy(), c_d.cpu().numpy()
+        assert np.array_equal(c_d, c_h) and np.array_equal(r_d, r_h)
+        assert len(set(c_h.tolist())) >= 4
+        static = np.array([(h_h[i, :c_h[i], 0:2] == h_h[i, :c_h[i], 5:7]).all() for i in range(512)])
+        assert 0.1 < static.mean() < 0.3                                    # goal = start: the static scenes
+        assert np.array_equal(h_d[static], h_h[static])
+        assert np.array_equal(h_d[:, 2:], h_h[:, 2:])                        # square-crossing humans and padding rows
+        assert np.abs(h_d - h_h).max() <= 2 * np.spacing(4.0)
+        assert np.array_equal(h_d[:, :, [2, 3, 4, 7]], h_h[:, :, [2, 3, 4, 7]])
+
+
+def test_vec_env_runs_device_generated_mixed_scenes():
+    """VecCrowdSim(rule='mixed', device_scenarios=True): the pool and its counts never touch the host; the outcomes equal the
+    host-generated pool's wherever no circle-crossing human's last-ulp difference matters (all of them here)"""
+    W = wts.synthetic_weights(2, -0.05)
+    res = []
+    for dev_scn in (False, True):
+        eng = Engine(0)
+        eng.set_action_space(np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden",
+                                                               "action_rotate.npz"))["actions"])
+        eng.set_env_params(make_env_params())
+        eng.load_weights(W)
+        eng.set_precision("fp16x3")
+        env = VecCrowdSim(eng, 64, 5, rule="mixed", phase="test", pool_size=128, device_scenarios=dev_scn)
+        for _ in range(120):
+            env.decide_and_step()
+        torch.cuda.synchronize()
+        res.append(env.outcomes.cpu().numpy().copy())
+    assert res[0].sum() >= 64 and np.array_equal(res[0], res[1])
