@@ -79,6 +79,32 @@ class ATCBasic(nn.Module):
                 break
         return accum_hx / step_count, step_count
 
+    def forward_per_sample(self, input, hx=None):
+        """The halting rule of batch-1 calls applied to every sample of a batch on its own: sample b goes on while any of
+        its rows has accum_p < 1 - epsilon (what components.py:132-134 tests when the reference evaluates one state at a
+        time, explorer.py:137 / multi_human_rl.py:351); the kernels' rule.  Returns (mean accumulated state, steps [B])."""
+        B, T = input.shape[0], input.shape[1]
+        x = input.reshape(-1, input.shape[2])
+        if self.act_fixed:
+            for _ in range(self.act_steps):
+                hx = self.rnn_cell(x, hx)
+            return hx, torch.full((B,), self.act_steps, device=x.device, dtype=torch.int64)
+        accum_p = torch.zeros([x.shape[0], 1], device=x.device, dtype=x.dtype)
+        accum_hx = torch.zeros([x.shape[0], self.rnn_hidden_dim], device=x.device, dtype=x.dtype)
+        active = torch.ones((B,), device=x.device, dtype=torch.bool)
+        count = torch.zeros((B,), device=x.device, dtype=torch.int64)
+        for k in range(1, self.max_ponder + 1):
+            hx = self.rnn_cell(x, hx)
+            halten_p = torch.sigmoid(self.ponder_linear(hx))
+            rows = active.repeat_interleave(T).unsqueeze(1).to(x.dtype)
+            accum_p = accum_p + halten_p * rows
+            accum_hx = accum_hx + halten_p * hx * rows
+            count = torch.where(active, torch.full_like(count, k), count)
+            active = active & (accum_p.view(B, T) < 1 - self.epsilon).any(dim=1)
+            if not bool(active.any()):
+                break
+        return accum_hx / count.repeat_interleave(T).unsqueeze(1).to(x.dtype), count
+
     def forward_static(self, input, hx=None):
         """The same function without host-side control flow, so that a training step can be captured in a CUDA graph:
         all max_ponder steps are evaluated and the result of the step at which the reference's batch-global test
@@ -186,15 +212,19 @@ class ValueNetworkTransformerAndGRU(nn.Module):
         tok[:, 12] = tok[:, 3]
         return tok.unsqueeze(1)
 
-    def forward_torch(self, state, static=False):
+    def forward_torch(self, state, static=False, per_sample=False):
         """differentiable restatement of qnetwork_factory.py:641-687 (dropout inactive: the module is used in
         eval mode -- see hazard 1 in SURVEY.md; call .train() to get the reference's stochastic behaviour).
-        static=True: no host-side control flow (CUDA-graph capturable), same result."""
+        static=True: no host-side control flow (CUDA-graph capturable), same result.  per_sample=True: every sample of
+        the batch halts on its own, i.e. the result of evaluating the states one at a time like explorer.py:137."""
         size = state.shape
         self_state = state[:, 0, :self.self_state_dim].clone().detach()
         x = torch.cat([self._robot_token(state), state], dim=1)
         h0 = torch.zeros([size[0] * (size[1] + 1), self.in_mlp_dims[-1]], device=state.device, dtype=state.dtype)
-        out, self.step_cnt = self.in_mlp.forward_static(x, h0) if static else self.in_mlp(x, h0)
+        if per_sample:
+            out, self.step_cnt = self.in_mlp.forward_per_sample(x, h0)
+        else:
+            out, self.step_cnt = self.in_mlp.forward_static(x, h0) if static else self.in_mlp(x, h0)
         enc_in = out.view(size[0], -1, 50).transpose(0, 1).contiguous()
         enc_out = self.transformer_encoder(enc_in).transpose(0, 1).contiguous()
         env_info = enc_out[:, 0, :]

@@ -65,6 +65,9 @@ def main(argv=None):
     ap.add_argument("--dropout", action="store_true",
                     help="optimise in train() mode like the reference (it never calls eval(): the encoder layers' dropout, "
                          "p = 0.1 at 4 sites per layer, is live in every optimisation step; qnetwork_factory.py:628)")
+    ap.add_argument("--target_dropout", action="store_true",
+                    help="vectorised RL phase: evaluate the target network in train() mode as well (the reference's V_target "
+                         "of explorer.py:132-139 is a stochastic forward because it never calls eval())")
     ap.add_argument("--no_final_test", action="store_true",
                     help="skip the reference's episode-0 validation and closing run_k_episodes(test) (train.py:229-230,246) "
                          "-- benchmarks / unit tests only")
@@ -126,7 +129,7 @@ def main(argv=None):
     if args.vectorised > 0:
         vec = VecExplorer(policy, args.vectorised, params, memory, policy.gamma, human_num=args.human_num,
                           rule=env.train_val_sim, seed=args.seed * 1000 + rank,
-                          il_safety_space=il_policy.safety_space)
+                          il_safety_space=il_policy.safety_space, target_train_mode=args.target_dropout)
     if args.resume:
         if not os.path.exists(rl_weight_file):
             logging.error("RL weights does not exist")

@@ -108,7 +108,7 @@ class VecExplorer(object):
     `num_envs` episodes are in flight at once."""
 
     def __init__(self, policy, num_envs, env_params, memory=None, gamma=None, human_num=5, rule="circle_crossing",
-                 seed=0, scenario_kw=None, il_safety_space=0.0, device_scenarios=None):
+                 seed=0, scenario_kw=None, il_safety_space=0.0, device_scenarios=None, target_train_mode=False):
         self.policy = policy
         self.env_params = env_params          # aem_env_params of the configured CrowdSim (env.env_params())
         self.il_safety_space = float(il_safety_space)     # [imitation_learning] safety_space of the ORCA teacher
@@ -119,6 +119,10 @@ class VecExplorer(object):
         self.gamma = policy.gamma if gamma is None else gamma
         self.device = policy.device
         self.target_model = None
+        # True: the target network is evaluated in train() mode, dropout live, like the reference's (it never calls eval(),
+        # so the V_target of explorer.py:132-139 is a stochastic forward of one state at a time); default: the eval()-mode
+        # network through aem_value_forward
+        self.target_train_mode = bool(target_train_mode)
         self.scenario_kw = scenario_kw
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed))
@@ -141,6 +145,14 @@ class VecExplorer(object):
         from aemcarl_b200.engine import get_engine
         if self.target_model is None:
             raise ValueError("update_target_model() has not been called")
+        if self.target_train_mode:
+            # torch forward with live dropout; every state halts on its own as in the reference's batch-1 calls
+            self.target_model.train()
+            out = []
+            with torch.no_grad():
+                for i in range(0, states.shape[0], 8192):
+                    out.append(self.target_model.forward_torch(states[i:i + 8192].contiguous(), per_sample=True)[0].reshape(-1))
+            return torch.cat(out) if out else states.new_zeros((0,))
         if self._target_engine is None:
             self._target_engine = get_engine(self.device.index or 0, role="target")
         eng = self.target_model.sync_engine(self._target_engine)

@@ -233,3 +233,35 @@ def test_repacking_the_running_environments_changes_nothing():
     assert np.array_equal(np.asarray(a[0]["cumulative_rewards"]), np.asarray(b[0]["cumulative_rewards"]))
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert a[0]["timeout"] > 0 and a[0]["success"] + a[0]["collision"] > 0      # the wave really had a long tail
+
+
+def test_target_network_in_train_mode_is_the_references_stochastic_target():
+    """target_train_mode: V_target of explorer.py:132-139 from the torch module with dropout live (the reference never calls
+    eval()).  With p = 0 the torch path (per-sample halting) must give the targets of the eval()-mode kernel path; with the
+    reference's p = 0.1 the targets scatter around them and differ from call to call."""
+    env, robot, policy = setup()
+    dev = torch.device("cuda:0")
+    policy.set_phase("train")
+
+    def targets(train_mode, p=None, seed=0):
+        dmem = DeviceReplayMemory(100000, 5, dev)
+        vec = VecExplorer(policy, 8, env.env_params(), dmem, policy.gamma, human_num=5, target_train_mode=train_mode)
+        vec.update_target_model(policy.get_model())
+        if p is not None:
+            for m in vec.target_model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = p
+                if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+                    m.dropout = p                      # nn.MultiheadAttention keeps its own probability
+        torch.manual_seed(seed)
+        vec.run_k_episodes(8, "train", update_memory=True, epsilon=0.0, first_case=0)
+        return _sorted_pairs(dmem.states[:len(dmem)].cpu().numpy(), dmem.values[:len(dmem)].cpu().numpy())
+
+    s0, v0 = targets(False)
+    s1, v1 = targets(True, p=0.0)
+    assert np.array_equal(s0, s1) and np.abs(v0 - v1).max() <= 5e-5
+    s2, v2 = targets(True, seed=1)
+    s3, v3 = targets(True, seed=2)
+    assert np.array_equal(s0, s2) and np.isfinite(v2).all()
+    d = np.abs(v2 - v0)
+    assert 1e-4 < d.max() < 0.5 and not np.array_equal(v2, v3)

@@ -252,3 +252,32 @@ def test_device_scenario_params_struct_matches_header():
     import ctypes
     from aemcarl_b200._lib import ScenarioParams
     assert ctypes.sizeof(ScenarioParams) == 7 * 8 + 8
+
+
+def test_per_sample_halting_forward_equals_one_state_at_a_time():
+    """forward_torch(per_sample=True) on a batch == the module called on every state alone (the reference's batch-1 calls at
+    explorer.py:137 / multi_human_rl.py:351): the rule VecExplorer's train()-mode target network uses"""
+    import torch
+    from aemcarl_b200 import weights as wts
+    from aemcarl_b200.crowd_nav.common.value_network import ValueNetworkTransformerAndGRU
+    rng = np.random.RandomState(5)
+    states = rng.uniform(-1, 1, size=(40, 5, 13))
+    states[:, :, :6] = states[:, :1, :6]
+    st = torch.as_tensor(states, dtype=torch.float64)
+    model = ValueNetworkTransformerAndGRU().double().eval()
+    model.load_flat_weights(wts.synthetic_weights(3, -0.05))          # mixed halting: 2 and 3 steps
+    with torch.no_grad():
+        batch, _ = model.forward_torch(st, per_sample=True)
+        steps = model.step_cnt.clone()
+        single, ks = [], []
+        for i in range(st.shape[0]):
+            v, _ = model.forward_torch(st[i:i + 1])
+            single.append(float(v))
+            ks.append(int(model.step_cnt))
+    assert len(set(ks)) >= 2 and steps.tolist() == ks
+    assert np.abs(batch.numpy().reshape(-1) - np.array(single)).max() <= 1e-12
+    model.train()                                                     # dropout live: a different, finite answer every call
+    with torch.no_grad():
+        a, _ = model.forward_torch(st, per_sample=True)
+        b, _ = model.forward_torch(st, per_sample=True)
+    assert torch.isfinite(a).all() and not torch.equal(a, b)
