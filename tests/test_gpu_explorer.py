@@ -255,7 +255,10 @@ def test_target_network_in_train_mode_is_the_references_stochastic_target():
                     m.dropout = p                      # nn.MultiheadAttention keeps its own probability
         torch.manual_seed(seed)
         vec.run_k_episodes(8, "train", update_memory=True, epsilon=0.0, first_case=0)
-        return _sorted_pairs(dmem.states[:len(dmem)].cpu().numpy(), dmem.values[:len(dmem)].cpu().numpy())
+        st = dmem.states[:len(dmem)].cpu().numpy().astype(np.float64).reshape(len(dmem), -1)
+        va = dmem.values[:len(dmem)].cpu().numpy().astype(np.float64).reshape(-1)
+        key = np.lexsort(st.T[::-1])                     # by the state alone: the same order whatever the targets are
+        return st[key], va[key]
 
     s0, v0 = targets(False)
     s1, v1 = targets(True, p=0.0)
