@@ -298,9 +298,9 @@ class Trainer(object):
     def _step(self, inputs, values):
         """one optimisation step; returns the loss as a 0-dim tensor (the callers synchronise once per call, not per step)"""
         if self.fused:
-            if getattr(self.model, "act_fixed", False):
-                raise NotImplementedError("the fused training step covers the adaptive-computation-time network "
-                                          "(act_fixed = False); use the eager / graphed step for act_fixed")
+            if getattr(self.model, "act_fixed", False) and int(self.model.act_steps) > 3:
+                raise NotImplementedError("the fused training step keeps at most 3 GRU steps (max_ponder of the adaptive "
+                                          "network); use the eager / graphed step for act_fixed with more")
             if self._fused is None:
                 self._fused = FusedStep(self.model, self.optimizer, inputs.device)
             return self._fused(inputs, values)
@@ -346,7 +346,7 @@ class Trainer(object):
         fast = self._device_memory()
         if fast and self.fused and isinstance(self.optimizer, optim.Adam) and self.memory.device.type == "cuda" \
                 and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) \
-                and not getattr(self.model, "act_fixed", False):
+                and not (getattr(self.model, "act_fixed", False) and int(self.model.act_steps) > 3):
             if self._fused is None:
                 self._fused = FusedStep(self.model, self.optimizer, self.memory.device)
             average_loss = float(self._fused.run_batches(self.memory, self.batch_size, num_batches, use_graph=self.cuda_graph))

@@ -779,7 +779,7 @@ int aem_train_grad(aem_handle h, int B, int n, const float *params_d, const floa
     if (B < 1 || n < 1 || n > AEM_MAX_HUMANS) return aem_set_error(AEM_ERR_INVALID, "bad B / n");
     if (!params_d || !states_d || !targets_d || !grad_d) return aem_set_error(AEM_ERR_INVALID, "null buffer");
     if (((uintptr_t)params_d & 15) != 0) return aem_set_error(AEM_ERR_INVALID, "params_d must be 16-byte aligned (bulk copies)");
-    if (h->net.act_fixed) return aem_set_error(AEM_ERR_INVALID, "aem_train_grad implements the adaptive (act_fixed = 0) network");
+    if (h->net.act_fixed && h->net.act_steps > 3) return aem_set_error(AEM_ERR_INVALID, "aem_train_grad: act_fixed with at most 3 steps");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     AEM_CUDA_CHECK(launch_train_grad(h, B, n, params_d, states_d, targets_d, grad_d, loss_d, values_d, steps_d, as_stream(stream)));
     h->launches += 3;
@@ -842,7 +842,7 @@ int aem_train_step_adam(aem_handle h, int N, int k, int n, const float *ring_sta
         !batch_states_d || !batch_values_d)
         return aem_set_error(AEM_ERR_INVALID, "null buffer");
     if (((uintptr_t)params_d & 15) != 0) return aem_set_error(AEM_ERR_INVALID, "params_d must be 16-byte aligned (bulk copies)");
-    if (h->net.act_fixed) return aem_set_error(AEM_ERR_INVALID, "aem_train_step_adam implements the adaptive (act_fixed = 0) network");
+    if (h->net.act_fixed && h->net.act_steps > 3) return aem_set_error(AEM_ERR_INVALID, "aem_train_step_adam: act_fixed with at most 3 steps");
     if (!(beta1 >= 0 && beta1 < 1) || !(beta2 >= 0 && beta2 < 1)) return aem_set_error(AEM_ERR_INVALID, "bad betas");
     AEM_CUDA_CHECK(cudaSetDevice(h->device));
     AEM_CUDA_CHECK(launch_train_step_adam(h, N, k, n, ring_states_d, ring_values_d, seed, dev_state_d, adam_scal_d, params_d, grad_d,

@@ -415,8 +415,10 @@ __device__ void load_tokens(const float *__restrict__ state, int n, float *x, fl
 // ---- the GRU-ACT forward (components.py:46-53,107-137): K steps, everything kept in the stash; A = sum_k p_k h_k ----
 // Expects Z1W in flight and hxb = [h_0 ; x]; leaves (Wnext, On, In) in flight.  6 barrier phases per step.
 // pk (optional): pk[(k - 1) * T + r] = halting probability of row r at step k
+// fixed_steps > 0 (act_fixed): the output is h_K itself, i.e. the "halting probability" is the constant [k == fixed_steps]
+// and nothing flows into ponder_linear.
 __device__ void gru_forward(const float *__restrict__ w, float *st, const TrLayout &L, int T, int K, float *A, float *hxb,
-                            WPipe &pipe, float *pk, const float *Wnext, int On, int In)
+                            WPipe &pipe, float *pk, const float *Wnext, int On, int In, int fixed_steps)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int k = 1; k <= K; ++k) {
@@ -459,7 +461,7 @@ __device__ void gru_forward(const float *__restrict__ w, float *st, const TrLayo
             float s = h0 * __ldg(w + OFF_PW + lane);
             if (two) s = fmaf(h1, __ldg(w + OFF_PW + lane + 32), s);
             for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-            const float p = sigmoidf_(s + __ldg(w + OFF_PB));
+            const float p = fixed_steps > 0 ? (k == fixed_steps ? 1.0f : 0.0f) : sigmoidf_(s + __ldg(w + OFF_PB));
             if (lane == 0) {
                 g.p[r] = p;
                 if (pk) pk[(k - 1) * T + r] = p;
@@ -485,6 +487,7 @@ struct TrainArgs {
     float *gru_g;       // [B][layout.enc]: the probe's GRU-ACT intermediates (x, h_0..3, three step blocks) handed to the
                         // forward / backward kernel, or null (the probe keeps one step block, the main kernel recomputes)
     int B, n;
+    int fixed_steps;    // act_fixed (components.py:109-112): run exactly this many GRU steps and hand on h_K; 0 = adaptive
     // dropout of nn.TransformerEncoderLayer (qnetwork_factory.py:628: p = 0.1 at 4 sites per layer, live because the reference
     // never calls eval()): inverted-dropout masks from a counter-based generator, recomputed in the backward pass
     float drop_p;                              // 0 = eval() mode
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_probe_kernel(TrainArgs a)
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         load_tokens(a.states + (size_t)b * a.n * 13, a.n, st + L.x, hxb, st + L.h, A);
         const bool more = b + (int)gridDim.x < a.B;
-        gru_forward(a.params, st, L, T, 3, A, hxb, pipe, pk, more ? a.params + OFF_Z1W : nullptr, 100, 63);
+        gru_forward(a.params, st, L, T, 3, A, hxb, pipe, pk, more ? a.params + OFF_Z1W : nullptr, 100, 63, a.fixed_steps);
         if (threadIdx.x < 32) {
             int un1 = 0, un2 = 0;
             for (int r = threadIdx.x; r < T; r += 32) {
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_probe_kernel(TrainArgs a)
                 un1 |= p1 < 1.0f - ACT_EPS;
                 un2 |= p2 < 1.0f - ACT_EPS;
             }
+            if (a.fixed_steps > 0) { un1 = a.fixed_steps >= 2; un2 = a.fixed_steps >= 3; }     // K is given, not voted
             un1 = __any_sync(0xffffffffu, un1);
             un2 = __any_sync(0xffffffffu, un2);
             if (threadIdx.x == 0) {
@@ -579,7 +583,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
     const float *w = a.params;
     float *G = a.part + (size_t)blockIdx.x * NUM_WEIGHTS;
     const int K = a.flags[0] == 0 ? 1 : (a.flags[1] == 0 ? 2 : 3);
-    const float invK = 1.0f / (float)K;
+    const float invK = a.fixed_steps > 0 ? 1.0f : 1.0f / (float)K;     // act_fixed hands on h_K, not the mean
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     const DropGen drop = make_dropgen(a);
 
@@ -609,7 +613,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
             psync();
         } else {
             load_tokens(state, a.n, st + L.x, hxb, st + L.h, A);
-            gru_forward(w, st, L, T, K, A, hxb, pipe, nullptr, w + OFF_ENC + ENC_INW, 150, 50);
+            gru_forward(w, st, L, T, K, A, hxb, pipe, nullptr, w + OFF_ENC + ENC_INW, 150, 50, a.fixed_steps);
         }
         for (int l = 0; l < 3; ++l) {
             const float *E = w + OFF_ENC + l * ENC_SIZE;
@@ -812,7 +816,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_fwdbwd_kernel(TrainArgs a
                 float s = 0.0f;
                 for (int j = lane; j < 50; j += 32) s = fmaf(dX[r * 50 + j], hn[r * 50 + j], s);
                 for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-                const float dl = s * p * (1.0f - p);                 // d/dlogit of p_k (dA . h_k)
+                const float dl = a.fixed_steps > 0 ? 0.0f : s * p * (1.0f - p);     // d/dlogit of p_k (dA . h_k)
                 if (lane == 0) dlog[r] = dl;
                 for (int j = lane; j < 50; j += 32) {
                     const int e = r * 50 + j;
@@ -1072,6 +1076,7 @@ cudaError_t launch_train_grad(aem_handle h, int B, int n, const float *params, c
     a.stash_g = in_smem ? nullptr : h->tr_stash;
     a.gru_g = handoff ? h->tr_gru : nullptr;
     a.B = B; a.n = n;
+    a.fixed_steps = h->net.act_fixed ? h->net.act_steps : 0;
     a.drop_p = (float)h->drop_p; a.drop_seed = h->drop_seed;
     a.drop_ctr_dev = drop_ctr_dev;
     a.drop_ctr = drop_ctr_dev ? 0ull : h->drop_ctr++;          // a fresh set of masks per optimisation step

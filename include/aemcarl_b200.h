@@ -208,7 +208,9 @@ int aem_transform(aem_handle h, int B, int n, const double *robot_d, const doubl
 /* Value-network regression step (crowd_nav/utils/trainer.py:47-58,70-82: outputs = model(inputs); loss = MSELoss(outputs,
  * values); loss.backward()): forward of ValueNetworkTransformerAndGRU (qnetwork_factory.py:641-687) on B rotated states with
  * the reference's BATCH-GLOBAL halting (components.py:132-134), mean squared error against targets_d, and the gradient with
- * respect to every live parameter.  Dropout is inactive (the eval()-mode network every other entry point evaluates).
+ * respect to every live parameter.  Dropout follows aem_set_train_dropout (default: inactive, the eval()-mode network every
+ * other entry point evaluates); with aem_set_act_mode(act_fixed = 1, act_steps <= 3) exactly act_steps GRU steps run and h_K
+ * is handed on (components.py:109-112), nothing flows into ponder_linear.
  * params_d [AEM_NUM_WEIGHTS] f32 (blob order; the caller's live parameters, not the handle's copy), states_d [B][n][13] f32,
  * targets_d [B] f32 -> grad_d [AEM_NUM_WEIGHTS] f32 (overwritten; deterministic summation order), loss_d [1] f32,
  * values_d [B] f32, steps_d [1] i32 = the batch's GRU step count (the last three may be NULL).  Three kernel launches. */

@@ -35,14 +35,23 @@ def run_kernel(eng, flat, states, targets):
     return float(loss[0]), g.cpu().numpy().astype(np.float64), values.cpu().numpy().astype(np.float64), int(steps[0])
 
 
-def check_grad(grad, ref, atol=0.0):
-    """atol: float32 noise floor for batches whose 1 / B scaling makes whole tensors' gradients ~1e-4 and smaller"""
+def check_grad(grad, ref, atol=0.0, kink_frac=0.0):
+    """atol: float32 noise floor for batches whose 1 / B scaling makes whole tensors' gradients ~1e-4 and smaller.
+    kink_frac: a float32 kernel and a float64 reference can disagree on the side of a ReLU kink for a pre-activation within
+    rounding of zero; that unit's derivative then differs (one bias element / one weight row, ~1e-3 of the tensor's largest
+    entry) while everything else agrees to 2e-6.  Up to this fraction of a tensor's elements (at least one) may exceed the
+    tolerance if they stay within 5e-3 of the tensor's largest entry -- an error of the algorithm moves every element."""
     assert np.isfinite(grad).all()
     for key, (off, shape) in wts.weight_offsets().items():
         n = int(np.prod(shape))
         a, b = grad[off:off + n], ref[off:off + n]
         scale = max(np.abs(b).max(), 1e-4)
-        assert np.abs(a - b).max() <= GRAD_RTOL * scale + atol, (key, np.abs(a - b).max(), scale)
+        err = np.abs(a - b)
+        if kink_frac > 0.0:
+            out = err > GRAD_RTOL * scale + atol
+            assert out.sum() <= max(1, int(kink_frac * n)) and err.max() <= 5e-3 * scale, (key, int(out.sum()), err.max(), scale)
+        else:
+            assert err.max() <= GRAD_RTOL * scale + atol, (key, err.max(), scale)
 
 
 @pytest.mark.parametrize("ponder_bias,expect_K", [(4.0, 1), (None, 2), (-2.0, 3)])
@@ -60,6 +69,38 @@ def test_train_grad_matches_autograd(eng, ponder_bias, expect_K, B, n):
     assert np.abs(values - val_r).max() < VALUE_ATOL
     assert loss == pytest.approx(loss_r, rel=1e-4)
     check_grad(grad, grad_r)
+
+
+@pytest.mark.parametrize("act_steps", [1, 2, 3])
+@pytest.mark.parametrize("B,n", [(100, 5), (9, 18), (300, 5)])
+def test_train_grad_act_fixed_matches_autograd(eng, act_steps, B, n):
+    """act_fixed (components.py:109-112): exactly act_steps GRU steps, h_K handed on, nothing flows into ponder_linear"""
+    from aemcarl_b200.crowd_nav.common.value_network import ValueNetworkTransformerAndGRU
+    flat = wts.synthetic_weights(4, ponder_bias=None)
+    states, targets = random_batch(1000 + B + n + act_steps, B, n)
+    states = states.astype(np.float32).astype(np.float64)
+    targets = targets.astype(np.float32).astype(np.float64)
+    model = ValueNetworkTransformerAndGRU(act_fixed=True, act_steps=act_steps).double().eval()
+    model.load_flat_weights(flat)
+    model = model.to("cuda:0")
+    out, _ = model.forward_torch(torch.as_tensor(states, dtype=torch.float64, device="cuda:0"))
+    loss_t = torch.nn.functional.mse_loss(out, torch.as_tensor(targets, dtype=torch.float64, device="cuda:0").view(-1, 1))
+    loss_t.backward()
+    named = dict(model.named_parameters())
+    grad_r = np.concatenate([(named[k].grad if named[k].grad is not None else torch.zeros_like(named[k])).detach().cpu().numpy()
+                             .reshape(-1) for k, _ in wts.WEIGHT_SPEC])
+    try:
+        eng.set_act_mode(True, act_steps)
+        loss, grad, values, K = run_kernel(eng, flat, states, targets)
+    finally:
+        eng.set_act_mode(False, 1)
+    assert K == act_steps
+    assert np.abs(values - out.detach().cpu().numpy().reshape(-1)).max() < VALUE_ATOL
+    assert loss == pytest.approx(float(loss_t), rel=1e-4)
+    check_grad(grad, grad_r, atol=1e-7, kink_frac=0.01)     # (atol: the r gate's gradients are below 1e-4 here)
+    off, shape = wts.weight_offsets()["in_mlp.ponder_linear.weight"] if "in_mlp.ponder_linear.weight" in wts.weight_offsets() \
+        else next(v for k, v in wts.weight_offsets().items() if "ponder" in k and "weight" in k)
+    assert (grad[off:off + int(np.prod(shape))] == 0).all()
 
 
 @pytest.mark.parametrize("p,B,n,ponder_bias", [(0.1, 24, 5, None), (0.1, 9, 10, -2.0), (0.3, 16, 5, 4.0), (0.1, 200, 5, None)])
@@ -320,3 +361,26 @@ def test_optimize_batch_single_call_and_graph_replay():
     assert flats["single_call"][1:] == flats["graph"][1:]
     assert torch.allclose(flats["stepwise"][0], flats["single_call"][0], rtol=1e-5, atol=1e-6)
     assert flats["stepwise"][1] == pytest.approx(flats["single_call"][1], rel=1e-5)
+
+
+def test_fused_trainer_with_act_fixed_walks_with_the_eager_trainer():
+    """act_fixed = True, act_steps = 2 (train.py --act_fixed --act_steps 2): the fused step against the eager torch step"""
+    from aemcarl_b200.crowd_nav.common.value_network import ValueNetworkTransformerAndGRU
+    from aemcarl_b200.crowd_nav.utils.trainer import Trainer
+    dev = torch.device("cuda:0")
+    model_a = ValueNetworkTransformerAndGRU(act_fixed=True, act_steps=2).eval()
+    model_a.load_flat_weights(wts.synthetic_weights(8))
+    model_a = model_a.to(dev)
+    model_b = copy.deepcopy(model_a)
+    g = torch.Generator(device=dev).manual_seed(9)
+    batches = [(torch.randn((100, 5, 13), device=dev, generator=g), torch.randn((100, 1), device=dev, generator=g))
+               for _ in range(5)]
+    losses = {}
+    for name, model, fused in (("eager", model_a, False), ("fused", model_b, True)):
+        tr = Trainer(model, None, dev, 100, fused=fused)
+        tr.set_learning_rate(1e-3, "Adam")
+        losses[name] = [float(tr._step(x, v)) for x, v in batches]
+    assert np.allclose(losses["eager"], losses["fused"], rtol=2e-4, atol=1e-6), (losses["eager"], losses["fused"])
+    for (k, pa), pb in zip(model_a.named_parameters(), model_b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-3, atol=2e-5), (k, float((pa - pb).abs().max()))
+    assert losses["fused"][0] != losses["fused"][-1]

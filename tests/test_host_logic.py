@@ -244,8 +244,13 @@ def test_fused_training_step_fails_loudly_without_cuda():
     fixed = ValueNetworkTransformerAndGRU(act_fixed=True, act_steps=2).eval()
     tr2 = Trainer(fixed, None, torch.device("cpu"), 4, fused=True)
     tr2.set_learning_rate(1e-3, "Adam")
-    with pytest.raises(NotImplementedError):         # act_fixed stays outside the fused kernels
+    with pytest.raises(RuntimeError, match="CUDA"):  # act_fixed (<= 3 steps) is inside the fused kernels: same loud failure
         tr2._step(torch.zeros((4, 5, 13)), torch.zeros((4, 1)))
+    fixed5 = ValueNetworkTransformerAndGRU(act_fixed=True, act_steps=5).eval()
+    tr3 = Trainer(fixed5, None, torch.device("cpu"), 4, fused=True)
+    tr3.set_learning_rate(1e-3, "Adam")
+    with pytest.raises(NotImplementedError):         # more steps than the kernels' stash holds
+        tr3._step(torch.zeros((4, 5, 13)), torch.zeros((4, 1)))
 
 
 def test_device_scenario_params_struct_matches_header():
