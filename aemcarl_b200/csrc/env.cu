@@ -158,9 +158,10 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
         const double q = search_radius / GRID_RES;
         const double q2 = q * q;
         int s0 = (q2 >= 0.0 && q2 < 720000.0) ? (int)q2 : (q2 >= 720000.0 ? 720000 : 0);
+        if (search_radius != search_radius) s0 = 720001;        // NaN radius: the comparison is false for every cell
         while (s0 < 720001 && !(sqrt((double)(s0 + 1)) * GRID_RES > search_radius)) ++s0;
         while (s0 >= 0 && sqrt((double)s0) * GRID_RES > search_radius) --s0;
-        disc_s = s0;
+        disc_s = s0;                                            // (2 * 600^2 = 720000 bounds dx^2 + dy^2 on the grid)
     }
     // which humans' blobs can reach a candidate disc at all: one thread per human (two FP64 hypot each -- a quarter of the
     // kernel's instructions when all 256 threads evaluated the test for every human)
