@@ -65,7 +65,8 @@ def build_variant(name, defines, verbose=False):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "aem_common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(HERE, "..", "include", "aemcarl_b200.h"),
+    headers = [os.path.join(CSRC, "aem_common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "orca_device.cuh"),
+               os.path.join(HERE, "..", "include", "aemcarl_b200.h"),
                os.path.abspath(__file__)]
     objs = []
     for src, extra in SOURCES.items():
