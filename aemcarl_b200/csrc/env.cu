@@ -210,12 +210,16 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
             x0 = max(max(x0, bl.xlo), 0); x1 = min(min(x1, bl.xhi), GRID_W);
             y0 = max(max(y0, bl.ylo), 0); y1 = min(min(y1, bl.yhi), GRID_W);
             for (int y = y0 + j; y < y1; y += TPA) {
+                // cells of this row inside the disc: (x - acx)^2 + dy^2 <= disc_s  (== !(int_hypot(..) * GRID_RES > search_radius)),
+                // i.e. the chord |x - acx| <= floor(sqrt(disc_s - dy^2)): walk the chord only, in the reference's order
+                const int rem = disc_s - (y - acy) * (y - acy);
+                if (rem < 0) continue;
+                int w = (int)sqrt((double)rem);
+                while (w * w > rem) --w;
+                while ((w + 1) * (w + 1) <= rem) ++w;
+                const int xl = max(x0, acx - w), xh = min(x1 - 1, acx + w);
                 const double *trow = tile + (y - bl.ylo) * bl.rw - bl.xlo;
-                const int dy2 = (y - acy) * (y - acy);
-                for (int x = x0; x < x1; ++x) {
-                    if ((x - acx) * (x - acx) + dy2 > disc_s) continue;       // == int_hypot(..) * GRID_RES > search_radius
-                    psum += trow[x];
-                }
+                for (int x = xl; x <= xh; ++x) psum += trow[x];
             }
         }
         partial[tid] = psum;
