@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
     // fused mode (new_vel_out != nullptr, aem_env_prepare): the CTA first solves ORCA for its own humans, one warp per
     // human exactly like orca_kernel, and writes the new velocities; `new_vel` is not read
     __shared__ int s_near[AEM_MAX_HUMANS];
+    __shared__ Blob s_blob[AEM_MAX_HUMANS];
     extern __shared__ __align__(16) double dsm[];
     double *tile = dsm;                         // [tile_cap]
     double *partial = tile + tile_cap;          // [ENV_THREADS]
@@ -169,12 +170,12 @@ __global__ void __launch_bounds__(ENV_THREADS) env_lookahead_kernel(
         const double hpx = sh[tid * 8], hpy = sh[tid * 8 + 1], hvx = sh[tid * 8 + 2], hvy = sh[tid * 8 + 3];
         const double m0 = hypot(hvx * p.human_timestep, hvy * p.human_timestep);
         s_near[tid] = !(hypot(hpx - rx, hpy - ry) > m0 + search_radius + amax + 0.1);   // else: cannot touch any disc (exact)
+        if (s_near[tid]) s_blob[tid] = blob_setup(hpx, hpy, hvx, hvy, p.human_timestep);  // (FP64 hypot + atan2: once, not x 256)
     }
     __syncthreads();
     for (int h = 0; h < n; ++h) {
         if (!s_near[h]) continue;
-        const double hpx = sh[h * 8], hpy = sh[h * 8 + 1], hvx = sh[h * 8 + 2], hvy = sh[h * 8 + 3];
-        const Blob bl = blob_setup(hpx, hpy, hvx, hvy, p.human_timestep);
+        const Blob bl = s_blob[h];
         const int cells = bl.rw * bl.rh;
         if (cells <= 0) continue;
         if (cells > tile_cap) {               // faster human than the host sized the tile for: flag with NaN
