@@ -393,9 +393,11 @@ def main():
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     if sampler:                                    # nvidia-smi needs ~0.1 s to start streaming: keep the GPU under the same
         sampler.start()                            # load (untimed extra warm-up steps) until its first row arrives
-    for _ in range(60):
+    for i in range(200):                           # (at least 40, so that the timed steps start from the same states run to run)
         step()
         torch.cuda.synchronize()
+        if i < 39:
+            continue
         ready = torch.tensor([1 if (sampler is None or len(sampler.rows) > 0) else 0], device=dev)
         if world > 1:
             dist.broadcast(ready, 0)
